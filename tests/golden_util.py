@@ -1,0 +1,43 @@
+"""Load the golden fixtures written by tests/golden/make_golden.py."""
+import glob
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    g["meta"] = json.loads(str(g["meta"]))
+    first = g["ind_first"]
+    g["envs_r"] = [g["ind_r"][first[m] : first[m + 1]] for m in range(len(first) - 1)]
+    g["envs_b"] = [g["ind_b"][first[m] : first[m + 1]] for m in range(len(first) - 1)]
+    return g
+
+
+def golden_radii(meta):
+    """Z -> length unit, as the reference's kernel had it (DefaultRadii: H 0.5, else 1.0,
+    descriptor/sesoap.py:84-99; UniversalSoap: one unit for all, soap.py:724-728)."""
+    if meta["kernel"]["kind"] == "universal":
+        return {int(z): float(meta["unit"]) for z in meta["species"]}, float(meta["unit"])
+    return {1: 0.5}, 1.0
+
+
+def oracle_model(g, big=False):
+    from oracle.sgpr_oracle import OracleModel
+
+    k = g["meta"]["kernel"]
+    radii, default = golden_radii(g["meta"])
+    return OracleModel(
+        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], radii=radii, default_radius=default,
+        ind_Z=g["ind_Z"], ind_r=g["envs_r"], ind_b=g["envs_b"], mu=g["mu_big"] if big else g["mu"],
+        mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()}, choli=g["choli"],
+        vscale={int(z): v for z, v in g["meta"]["vscale"].items()}, a_not=tuple(k.get("a_not", ())),
+    )

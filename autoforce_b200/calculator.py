@@ -1,0 +1,131 @@
+"""Calculator facade: ActiveCalculator.calculate() in prediction mode on the GPU.
+
+Mirrors what theforce.calculator.active.ActiveCalculator produces when
+``calculator=None`` (calculator/active.py:425-611): ``results['energy']`` (0-d float64
+ndarray), ``results['forces']`` [N,3], ``results['stress']`` Voigt (xx,yy,zz,yz,xz,xy) in
+eV/A^3 = (W / V).flat[[0,4,8,5,2,1]] with V = -2 when there is no cell (active.py:604-611),
+``results['free_energy']`` (active.py:527).  The on-the-fly training control flow, the
+ab initio calls and the M x M algebra stay with the reference.
+
+Works with any object exposing positions / cell / pbc / numbers (ase.Atoms does); when
+ASE is importable the class is also a proper ase Calculator.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import SgprEngine
+from .model import SgprModel
+
+try:  # optional
+    from ase.calculators.calculator import Calculator as _AseCalculator
+    from ase.calculators.calculator import all_changes as _all_changes
+except Exception:  # pragma: no cover
+    _AseCalculator = object
+    _all_changes = ["positions", "numbers", "cell", "pbc"]
+
+
+def _as_model(covariance):
+    if isinstance(covariance, SgprModel):
+        return covariance
+    if isinstance(covariance, str):
+        if covariance.endswith(".npz"):
+            return SgprModel.load(covariance)
+        # a folder pickled by the reference (gppotential.py:1073-1119,1342-1368): needs theforce importable
+        from theforce.regression.gppotential import PosteriorPotentialFromFolder
+
+        return SgprModel.from_posterior_potential(PosteriorPotentialFromFolder(covariance, load_data=False, update_data=False))
+    if hasattr(covariance, "gp") and hasattr(covariance, "X"):
+        return SgprModel.from_posterior_potential(covariance)
+    raise TypeError(f"cannot build an SGPR model from {type(covariance)}")
+
+
+class B200Calculator(_AseCalculator):
+    implemented_properties = ["energy", "forces", "stress", "free_energy"]
+
+    def __init__(self, covariance, calculator=None, process_group=None, device=None, gather_forces=True, logfile=None, **kw):
+        if _AseCalculator is not object:
+            super().__init__()
+        if calculator is not None:
+            raise NotImplementedError(
+                "on-the-fly training stays on the reference path: use theforce's ActiveCalculator with the "
+                "GPU kernel plugged in (INTEGRATION.md); B200Calculator is the prediction-mode drop-in")
+        self.model = _as_model(covariance)
+        self.process_group = process_group
+        self.gather_forces = gather_forces
+        self.results = {}
+        self.step = 0
+        self._engine = None
+        self._device = device
+        self.atoms = None
+
+    # ------------------------------------------------------------------ distributed
+    def _dist(self):
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                return dist, dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+        except Exception:
+            pass
+        return None, 0, 1
+
+    def _get_engine(self, numbers):
+        import torch
+
+        need = set(int(z) for z in np.unique(numbers))
+        if self._engine is None or not need.issubset(self._engine.species):
+            if self._engine is not None:
+                self._engine.close()
+            dev = self._device if self._device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+            self._engine = SgprEngine(self.model, species=sorted(need), device=dev)
+        return self._engine
+
+    # ------------------------------------------------------------------ the call
+    def calculate(self, atoms=None, properties=("energy",), system_changes=_all_changes):
+        if atoms is not None:
+            self.atoms = atoms.copy() if hasattr(atoms, "copy") else atoms
+        a = self.atoms
+        pos = np.asarray(a.positions, dtype=np.float64)
+        numbers = np.asarray(a.numbers)
+        cell = np.asarray(a.cell, dtype=np.float64).reshape(3, 3)
+        pbc = np.broadcast_to(np.asarray(a.pbc), (3,))
+        eng = self._get_engine(numbers)
+        dist, rank, world = self._dist()
+        E, F, W, owned = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world)
+        if world > 1:
+            import torch
+
+            dev = torch.device("cuda", eng.device)
+            ew = torch.tensor([E] + list(W.reshape(-1)), dtype=torch.float64, device=dev)
+            dist.all_reduce(ew, group=self.process_group)  # 10 doubles: energy + 3x3 virial
+            ew = ew.cpu().numpy()
+            E, W = float(ew[0]), ew[1:].reshape(3, 3)
+            if self.gather_forces:  # reference-conformant: every rank sees all forces (active.py:601)
+                ft = torch.as_tensor(F, device=dev)
+                dist.all_reduce(ft, group=self.process_group)
+                F = ft.cpu().numpy()
+        vol = abs(np.linalg.det(cell))
+        if vol == 0.0:
+            vol = -2.0  # calculator/active.py:606-609
+        stress = (W / vol).reshape(-1)[[0, 4, 8, 5, 2, 1]]
+        self.results = {
+            "energy": np.array(E, dtype=np.float64),
+            "forces": F,
+            "stress": stress,
+            "free_energy": np.array(E, dtype=np.float64),
+        }
+        self.owned = owned
+        self.maximum_force = float(np.abs(F).max()) if F.size else 0.0
+        self.step += 1
+        return self.results
+
+    # plain getters for non-ASE callers
+    def get_potential_energy(self, atoms=None):
+        return float(self.calculate(atoms)["energy"]) if atoms is not None or not self.results else float(self.results["energy"])
+
+    def get_forces(self, atoms=None):
+        return (self.calculate(atoms) if atoms is not None or not self.results else self.results)["forces"]
+
+    def get_stress(self, atoms=None):
+        return (self.calculate(atoms) if atoms is not None or not self.results else self.results)["stress"]

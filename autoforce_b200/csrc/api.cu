@@ -1,0 +1,748 @@
+// C-ABI entry points of libsgpr_b200.so (include/sgpr_b200.h) and the per-step pipeline.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "sgpr_internal.cuh"
+
+namespace sgpr {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::ensure(size_t need) {
+    if (need <= bytes) return SGPR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        bytes = 0;
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return SGPR_ERR_NOMEM;
+    }
+    bytes = want;
+    return SGPR_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// small kernels of the pipeline
+// ---------------------------------------------------------------------------------
+__global__ void transpose_zhat_kernel(int D, int ldp, int m0, int Ms, int ld_zt, const double* __restrict__ zhat,
+                                      double* __restrict__ zt) {
+    // zt[e][m] = zhat[m0+m][e]
+    __shared__ double tile[32][33];
+    const int e0 = blockIdx.x * 32, mm0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int m = mm0 + r, e = e0 + threadIdx.x;
+        tile[r][threadIdx.x] = (m < Ms && e < D) ? zhat[(size_t)(m0 + m) * ldp + e] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int e = e0 + r, m = mm0 + threadIdx.x;
+        if (e < D && m < ld_zt) zt[(size_t)e * ld_zt + m] = tile[threadIdx.x][r];
+    }
+}
+
+// per-atom terms outside the GEMM: constant mean (gppotential.py:219-227), the
+// "lone atoms" kernel term (similarity.py:94-103), scatter of forces to caller order
+__global__ void atom_terms_kernel(int64_t N, int n_active, const int* __restrict__ active,
+                                  const AtomRec* __restrict__ atoms, const long long* __restrict__ nl_first,
+                                  const unsigned char* __restrict__ owned, const double* __restrict__ mean_w,
+                                  const double* __restrict__ lone_mu, double* __restrict__ part) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n_active; env += gridDim.x * blockDim.x) {
+        const int c = active ? active[env] : env;
+        if (owned && !owned[c]) continue;
+        const int sp = meta_species(atoms[c].meta);
+        s += mean_w[sp];
+        if (nl_first[env + 1] == nl_first[env]) s += lone_mu[sp];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ atoms, const double* __restrict__ fcell,
+                                      const unsigned char* __restrict__ owned, double* __restrict__ F,
+                                      unsigned char* __restrict__ owned_out) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const int i = meta_orig(atoms[c].meta);
+    F[3 * (size_t)i] = fcell[3 * c];
+    F[3 * (size_t)i + 1] = fcell[3 * c + 1];
+    F[3 * (size_t)i + 2] = fcell[3 * c + 2];
+    if (owned_out) owned_out[i] = owned ? owned[c] : 1;
+}
+
+__global__ void final_reduce_kernel(int n_e, const double* __restrict__ epart, int n_x, const double* __restrict__ xpart,
+                                    int n_w, const double* __restrict__ wpart, double* __restrict__ E,
+                                    double* __restrict__ W) {
+    // one block, fixed summation order -> run-to-run reproducible E and W
+    __shared__ double red[256];
+    const int t = threadIdx.x;
+    double s = 0.0;
+    for (int i = t; i < n_e; i += 256) s += epart[i];
+    for (int i = t; i < n_x; i += 256) s += xpart[i];
+    red[t] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+    }
+    if (t == 0) E[0] = red[0];
+    __syncthreads();
+    for (int q = 0; q < 9; ++q) {
+        double w = 0.0;
+        for (int i = t; i < n_w; i += 256) w += wpart[i * 9 + q];
+        red[t] = w;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (t < o) red[t] += red[t + o];
+            __syncthreads();
+        }
+        if (t == 0) W[q] = red[0];
+        __syncthreads();
+    }
+}
+
+__global__ void row_to_orig_kernel(int64_t N, const AtomRec* __restrict__ atoms, const int* __restrict__ rowof,
+                                   int* __restrict__ orig_of_row) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    orig_of_row[rowof[c]] = meta_orig(atoms[c].meta);
+}
+__global__ void orig_to_row_kernel(int64_t N, const AtomRec* __restrict__ atoms, const int* __restrict__ rowof,
+                                   int* __restrict__ row_of_orig) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    row_of_orig[meta_orig(atoms[c].meta)] = rowof[c];
+}
+
+__global__ void lone_k_kernel(int n_active, const int* __restrict__ active, const AtomRec* __restrict__ atoms,
+                              const long long* __restrict__ nl_first, int M, const int* __restrict__ ind_sp,
+                              const unsigned char* __restrict__ ind_lone, double* __restrict__ K) {
+    // K[i,m] += 1 when both LCEs have no neighbours and the same species (similarity.py:94-103)
+    for (int env = blockIdx.x; env < n_active; env += gridDim.x) {
+        if (nl_first[env + 1] != nl_first[env]) continue;
+        const int c = active ? active[env] : env;
+        const int sp = meta_species(atoms[c].meta);
+        const int i = meta_orig(atoms[c].meta);
+        for (int m = threadIdx.x; m < M; m += blockDim.x)
+            if (ind_lone[m] && ind_sp[m] == sp) K[(size_t)i * M + m] += 1.0;
+    }
+}
+
+// CSR neighbour list in the caller's atom order (parity hook)
+__global__ void nl_count_orig_kernel(int64_t N, const AtomRec* __restrict__ atoms, const long long* __restrict__ nl_first,
+                                     long long* __restrict__ cnt) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > N) return;
+    if (c == N) {
+        cnt[N] = 0;
+        return;
+    }
+    cnt[meta_orig(atoms[c].meta)] = nl_first[c + 1] - nl_first[c];
+}
+__global__ void nl_export_kernel(int64_t N, const AtomRec* __restrict__ atoms, const PairRec* __restrict__ pairs,
+                                 const long long* __restrict__ nl_first, const long long* __restrict__ first_out,
+                                 int32_t* __restrict__ j_out, int8_t* __restrict__ S_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (c >= N) return;
+    const AtomRec ai = atoms[c];
+    const long long o = first_out[meta_orig(ai.meta)];
+    const long long beg = nl_first[c], end = nl_first[c + 1];
+    for (long long k = beg + lane; k < end; k += 32) {
+        const PairRec pr = pairs[k];
+        const AtomRec aj = atoms[pr.j];
+        j_out[o + (k - beg)] = meta_orig(aj.meta);
+        for (int q = 0; q < 3; ++q)
+            S_out[3 * (o + (k - beg)) + q] = (int8_t)(pr.sb[q] - meta_w(aj.meta, q) + meta_w(ai.meta, q));
+    }
+}
+
+}  // namespace sgpr
+
+using namespace sgpr;
+
+// =====================================================================================
+// life cycle
+// =====================================================================================
+extern "C" __attribute__((visibility("default"))) const char* sgpr_last_error(void) { return g_err; }
+extern "C" __attribute__((visibility("default"))) int sgpr_abi_version(void) { return SGPR_ABI_VERSION; }
+
+static int upload(DevBuf& b, const void* src, size_t bytes) {
+    SGPR_TRY(b.ensure(bytes ? bytes : 8));
+    if (bytes) SGPR_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return SGPR_OK;
+}
+
+static int upload_weights(sgpr_context* h, const double* mu_h, const double* mean_w_h, const double* choli_h,
+                          const double* vscale_h, const int64_t* ind_first_h) {
+    const int M = h->M, S = h->S;
+    if (mu_h) {
+        h->mu_host.assign(mu_h, mu_h + M);
+        std::vector<double> mus(M);
+        for (int p = 0; p < M; ++p) mus[p] = mu_h[h->ind_perm[p]];
+        SGPR_TRY(upload(h->mu, mus.data(), sizeof(double) * M));
+        std::vector<double> lone(SGPR_MAX_SPECIES, 0.0);
+        for (int p = 0; p < M; ++p)
+            if (h->ind_lone[p]) lone[h->ind_sp[p]] += mus[p];
+        SGPR_TRY(upload(h->lone_mu, lone.data(), sizeof(double) * SGPR_MAX_SPECIES));
+    }
+    if (mean_w_h) {
+        h->mean_w.assign(mean_w_h, mean_w_h + S);
+        h->mean_w.resize(SGPR_MAX_SPECIES, 0.0);
+        SGPR_TRY(upload(h->mean_w_d, h->mean_w.data(), sizeof(double) * SGPR_MAX_SPECIES));
+    }
+    if (vscale_h) h->vscale.assign(vscale_h, vscale_h + S);
+    if (choli_h) {
+        // rows and columns permuted into the sorted inducing order
+        std::vector<double> c((size_t)M * M);
+        for (int a = 0; a < M; ++a)
+            for (int b = 0; b < M; ++b) c[(size_t)a * M + b] = choli_h[(size_t)a * M + h->ind_perm[b]];
+        SGPR_TRY(upload(h->choli, c.data(), sizeof(double) * (size_t)M * M));
+        h->has_choli = true;
+    }
+    (void)ind_first_h;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_model_desc* d, sgpr_handle* out) {
+    if (!d || !out) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available: libsgpr_b200 has no CPU fallback");
+        return SGPR_ERR_NO_DEVICE;
+    }
+    if (d->device < 0 || d->device >= ndev) {
+        set_error("device %d out of range (have %d)", d->device, ndev);
+        return SGPR_ERR_INVALID;
+    }
+    if (d->lmax < 0 || d->lmax > kMaxL || d->nmax < 0 || d->nmax + 1 > kMaxNB) {
+        set_error("unsupported lmax=%d (max %d) / nmax=%d (max %d)", d->lmax, kMaxL, d->nmax, kMaxNB - 1);
+        return SGPR_ERR_INVALID;
+    }
+    if (d->n_species < 1 || d->n_species > SGPR_MAX_SPECIES) {
+        set_error("n_species=%d not in 1..%d", d->n_species, SGPR_MAX_SPECIES);
+        return SGPR_ERR_INVALID;
+    }
+    if (!(d->rc > 0) || !(d->xi > 0) || d->M < 0) {
+        set_error("invalid rc/xi/M");
+        return SGPR_ERR_INVALID;
+    }
+    SGPR_CUDA(cudaSetDevice(d->device));
+    sgpr_context* h = new sgpr_context();
+    h->device = d->device;
+    cudaDeviceProp prop;
+    SGPR_CUDA(cudaGetDeviceProperties(&prop, d->device));
+    h->sm_count = prop.multiProcessorCount;
+    SGPR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) SGPR_CUDA(cudaEventCreate(&h->ev[i]));
+    SGPR_TRY(upload_harm_coef());
+
+    DescParams& dp = h->dp;
+    const int S = d->n_species;
+    h->S = S;
+    dp.lmax = d->lmax;
+    dp.nb = d->nmax + 1;
+    dp.L2 = (d->lmax + 1) * (d->lmax + 1);
+    dp.S = S;
+    dp.A = S * dp.nb;
+    dp.ncomp = dp.nb * dp.L2;
+    dp.csize = S * dp.ncomp;
+    const int L = d->lmax + 1;
+    dp.D = dp.A * (dp.A + 1) / 2 * L;
+    dp.ldp = (dp.D + 15) & ~15;
+    dp.normalize = d->normalize ? 1 : 0;
+    dp.rc = d->rc;
+    if (dp.A > 255) {
+        set_error("S*(nmax+1) = %d exceeds 255", dp.A);
+        delete h;
+        return SGPR_ERR_INVALID;
+    }
+    for (int i = 0; i < 128; ++i) h->z_to_species[i] = -1;
+    for (int s = 0; s < SGPR_MAX_SPECIES; ++s) {
+        dp.radii[s] = 1.0;
+        dp.central_enabled[s] = 0;
+        h->species_Z[s] = -1;
+    }
+    for (int s = 0; s < S; ++s) {
+        const int z = d->species_Z[s];
+        if (z < 0 || z >= 128 || h->z_to_species[z] >= 0 || !(d->radii[s] > 0)) {
+            set_error("bad species table entry %d (Z=%d, radius=%g)", s, z, d->radii[s]);
+            delete h;
+            return SGPR_ERR_INVALID;
+        }
+        h->species_Z[s] = z;
+        h->z_to_species[z] = s;
+        dp.radii[s] = d->radii[s];
+        dp.central_enabled[s] = d->central_enabled[s] ? 1 : 0;
+    }
+    h->xi = d->xi;
+    h->xi_int = (d->xi == std::floor(d->xi) && d->xi >= 1 && d->xi <= 64) ? (int)d->xi : -1;
+    SGPR_TRY(upload(h->ztab, h->z_to_species, sizeof(int) * 128));
+    SGPR_TRY(h->errflag.ensure(sizeof(int) * 4));
+
+    // packed-entry tables
+    {
+        std::vector<unsigned> ptab(dp.D);
+        std::vector<double> nnlk(dp.D);
+        for (int a = 0; a < dp.A; ++a)
+            for (int b = a; b < dp.A; ++b) {
+                const int tri = a * dp.A - (a * (a - 1)) / 2 + (b - a);
+                const int na = a % dp.nb, nbb = b % dp.nb;
+                for (int l = 0; l < L; ++l) {
+                    ptab[tri * L + l] = (unsigned)a | ((unsigned)b << 8) | ((unsigned)l << 16);
+                    nnlk[tri * L + l] = std::sqrt(anl(na, l) * anl(nbb, l)) * (a == b ? 1.0 : std::sqrt(2.0));
+                }
+            }
+        SGPR_TRY(upload(h->ptab, ptab.data(), sizeof(unsigned) * dp.D));
+        SGPR_TRY(upload(h->nnlk, nnlk.data(), sizeof(double) * dp.D));
+    }
+
+    // inducing set, grouped by central species
+    const int M = d->M;
+    h->M = M;
+    std::vector<int> sp_of(M);
+    for (int m = 0; m < M; ++m) {
+        const int z = d->ind_Z_h[m];
+        if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+            set_error("inducing LCE %d: species Z=%d not in the species table", m, z);
+            delete h;
+            return SGPR_ERR_SPECIES;
+        }
+        sp_of[m] = h->z_to_species[z];
+    }
+    h->ind_perm.resize(M);
+    for (int m = 0; m < M; ++m) h->ind_perm[m] = m;
+    std::stable_sort(h->ind_perm.begin(), h->ind_perm.end(), [&](int a, int b) { return sp_of[a] < sp_of[b]; });
+    for (int s = 0; s <= SGPR_MAX_SPECIES; ++s) h->m_first[s] = 0;
+    for (int m = 0; m < M; ++m) h->m_first[sp_of[m] + 1]++;
+    for (int s = 0; s < SGPR_MAX_SPECIES; ++s) h->m_first[s + 1] += h->m_first[s];
+    int maxMs = 0;
+    for (int s = 0; s < S; ++s) maxMs = std::max(maxMs, h->m_first[s + 1] - h->m_first[s]);
+    h->ld_zt = std::max(16, (maxMs + 15) & ~15);
+    h->ldg = h->ld_zt;
+    h->ind_sp.resize(M);
+    h->ind_lone.resize(M);
+    std::vector<int> row_of(M);
+    for (int p = 0; p < M; ++p) {
+        const int m = h->ind_perm[p];
+        row_of[m] = p;
+        h->ind_sp[p] = sp_of[m];
+        h->ind_lone[p] = (d->ind_first_h[m + 1] == d->ind_first_h[m]) ? 1 : 0;
+    }
+    SGPR_TRY(upload(h->ind_perm_d, h->ind_perm.data(), sizeof(int) * M));
+    {
+        std::vector<unsigned char> on(SGPR_MAX_SPECIES, 0);
+        for (int s = 0; s < S; ++s) on[s] = (dp.central_enabled[s] && h->m_first[s + 1] > h->m_first[s]) ? 1 : 0;
+        SGPR_TRY(upload(h->sp_on, on.data(), SGPR_MAX_SPECIES));
+    }
+    // environments -> device, evaluate Z_hat with the atom kernels
+    SGPR_TRY(h->zhat.ensure(sizeof(double) * ((size_t)M + 1) * dp.ldp));
+    SGPR_CUDA(cudaMemset(h->zhat.p, 0, sizeof(double) * ((size_t)M + 1) * dp.ldp));
+    if (M > 0) {
+        const int64_t nnz = d->ind_first_h[M];
+        std::vector<unsigned char> esp((size_t)nnz + 1);
+        for (int64_t k = 0; k < nnz; ++k) {
+            const int z = d->ind_b_h[k];
+            if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+                set_error("inducing neighbour species Z=%d not in the species table", z);
+                delete h;
+                return SGPR_ERR_SPECIES;
+            }
+            esp[k] = (unsigned char)h->z_to_species[z];
+        }
+        std::vector<long long> first(M + 1);
+        for (int m = 0; m <= M; ++m) first[m] = d->ind_first_h[m];
+        DevBuf b_first, b_r, b_sp, b_row;
+        SGPR_TRY(upload(b_first, first.data(), sizeof(long long) * (M + 1)));
+        SGPR_TRY(upload(b_r, d->ind_r_h, sizeof(double) * 3 * nnz));
+        SGPR_TRY(upload(b_sp, esp.data(), nnz));
+        SGPR_TRY(upload(b_row, row_of.data(), sizeof(int) * M));
+        int st = descriptor_forward_env(h, M, b_first.as<long long>(), b_r.as<double>(), b_sp.as<unsigned char>(),
+                                        b_row.as<int>(), h->zhat.as<double>(), 0);
+        if (st == SGPR_OK && cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("inducing descriptor kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = SGPR_ERR_CUDA;
+        }
+        b_first.release();
+        b_r.release();
+        b_sp.release();
+        b_row.release();
+        if (st != SGPR_OK) {
+            delete h;
+            return st;
+        }
+    }
+    // transposed copies per species for the back projection
+    SGPR_TRY(h->zhat_t.ensure(sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
+    SGPR_CUDA(cudaMemset(h->zhat_t.p, 0, sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
+    for (int s = 0; s < S; ++s) {
+        h->zt_off[s] = (size_t)s * dp.D * h->ld_zt;
+        const int Ms = h->m_first[s + 1] - h->m_first[s];
+        if (Ms == 0) continue;
+        dim3 grid((dp.D + 31) / 32, (h->ld_zt + 31) / 32), block(32, 8);
+        transpose_zhat_kernel<<<grid, block>>>(dp.D, dp.ldp, h->m_first[s], Ms, h->ld_zt, h->zhat.as<double>(),
+                                               h->zhat_t.as<double>() + h->zt_off[s]);
+    }
+    SGPR_CUDA(cudaDeviceSynchronize());
+    {   // caller's order copies for the lone-lone kernel term
+        std::vector<int> sp_orig(M + 1);
+        std::vector<unsigned char> lone_orig(M + 1);
+        for (int p = 0; p < M; ++p) {
+            sp_orig[h->ind_perm[p]] = h->ind_sp[p];
+            lone_orig[h->ind_perm[p]] = h->ind_lone[p];
+        }
+        SGPR_TRY(upload(h->ind_sp_d, sp_orig.data(), sizeof(int) * M));
+        SGPR_TRY(upload(h->ind_lone_d, lone_orig.data(), M));
+    }
+    std::vector<double> zeros(SGPR_MAX_SPECIES, 0.0);
+    int st = upload_weights(h, d->mu_h, d->mean_w_h ? d->mean_w_h : zeros.data(), d->choli_h, d->vscale_h, nullptr);
+    if (st != SGPR_OK) {
+        delete h;
+        return st;
+    }
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->stats.d_packed = dp.D;
+    h->stats.d_full = dp.A * dp.A * L;
+    *out = h;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&h->zhat, &h->zhat_t, &h->mu, &h->lone_mu, &h->choli, &h->ptab, &h->nnlk, &h->ztab, &h->errflag,
+                      &h->ind_perm_d, &h->sp_on, &h->ind_sp_d, &h->ind_lone_d, &h->mean_w_d, &h->cnt, &h->cstart,
+                      &h->rstart, &h->keyrank, &h->atoms, &h->order, &h->rowof, &h->active_list, &h->nl_cnt,
+                      &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
+                      &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
+                      &h->rowmap};
+    for (DevBuf* b : bufs) b->release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < 6; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_handle h, const double* mu_h, const double* mean_w_h, const double* choli_h,
+                                const double* vscale_h) {
+    if (!h) {
+        set_error("null handle");
+        return SGPR_ERR_INVALID;
+    }
+    SGPR_CUDA(cudaSetDevice(h->device));
+    SGPR_CUDA(cudaDeviceSynchronize());
+    return upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr);
+}
+
+// =====================================================================================
+// pipeline
+// =====================================================================================
+static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                       const int32_t* pbc_h, cudaStream_t st, Geom* g) {
+    // geometry -> cell sort -> neighbour list -> descriptors (rows in species-major order)
+    if (N < 0 || N > 0x7fffff00ll) {
+        set_error("bad atom count");
+        return SGPR_ERR_INVALID;
+    }
+    h->stats.n_atoms = N;
+    h->stats.kernel_launches = 0;
+    h->stats.gemm_flops = 0.0;
+    h->last_N = N;
+    SGPR_TRY(build_geometry(h, N, pos_d, cell_h, pbc_h, st, g));
+    h->last_geom = *g;
+    if (h->timing) cudaEventRecord(h->ev[0], st);
+    SGPR_TRY(cell_sort(h, N, pos_d, Z_d, *g, st));
+    h->active_all = true;
+    h->n_active = N;
+    // species row ranges (first row of each species block) come back with the pair count
+    int rf[SGPR_MAX_SPECIES + 1];
+    const int nkeys = g->ncell * h->S;
+    const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
+    SGPR_CUDA(cudaMemcpy2DAsync(rf, sizeof(int), rstartT, sizeof(int) * g->ncell, sizeof(int), h->S + 1,
+                                cudaMemcpyDeviceToHost, st));
+    int64_t n_pairs = 0;
+    SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs));  // synchronises the stream
+    for (int s = 0; s <= h->S; ++s) h->row_first[s] = rf[s];
+    h->stats.n_active = h->n_active;
+    h->stats.n_pairs = n_pairs;
+    if (h->timing) cudaEventRecord(h->ev[1], st);
+    SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)N + 1) * h->dp.ldp));
+    SGPR_TRY(descriptor_forward_atoms(h, *g, st));
+    if (h->timing) cudaEventRecord(h->ev[2], st);
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                            const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
+                            double* W_d, double* beta_d, uint8_t* owned_d) {
+    if (!h || !cell_h || !pbc_h || !E_d || !F_d || !W_d || (N > 0 && (!pos_d || !Z_d))) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    if (world != 1 || rank != 0) {
+        set_error("atom sharding (world=%d) is not available in this build", world);
+        return SGPR_ERR_INVALID;
+    }
+    if (beta_d) {
+        set_error("covloss output is not available in this build");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    Geom g;
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
+    const int grid_g = 2 * h->sm_count;
+    const int nblk_b = h->sm_count * 8;
+    const int nblk_x = 64;
+    SGPR_TRY(h->gmat.ensure(sizeof(double) * ((size_t)N + 1) * h->ldg));
+    SGPR_TRY(h->gvec.ensure(sizeof(double) * ((size_t)N + 1) * h->dp.ldp));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)h->S * grid_g + nblk_x)));
+    SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
+    SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
+    SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)h->S * grid_g + nblk_x), st));
+    SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
+    SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+    SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, st));
+    SGPR_TRY(gemm_back_projection(h, st));
+    if (h->timing) cudaEventRecord(h->ev[3], st);
+    SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
+    if (N > 0) {
+        atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, nullptr, h->atoms.as<AtomRec>(),
+                                                  h->nl_first.as<long long>(), nullptr, h->mean_w_d.as<double>(),
+                                                  h->lone_mu.as<double>(),
+                                                  h->epart.as<double>() + (size_t)h->S * grid_g);
+        scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
+                                                                      nullptr, F_d, owned_d);
+    }
+    final_reduce_kernel<<<1, 256, 0, st>>>(h->S * grid_g, h->epart.as<double>(), nblk_x,
+                                           h->epart.as<double>() + (size_t)h->S * grid_g, nblk_b,
+                                           h->wpart.as<double>(), E_d, W_d);
+    h->stats.kernel_launches += 3;
+    SGPR_CUDA(cudaGetLastError());
+    if (h->timing) {
+        cudaEventRecord(h->ev[4], st);
+        SGPR_CUDA(cudaEventSynchronize(h->ev[4]));
+        cudaEventElapsedTime(&h->stats.ms_nl, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&h->stats.ms_desc, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&h->stats.ms_gemm, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&h->stats.ms_force, h->ev[3], h->ev[4]);
+        cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[4]);
+    }
+    return SGPR_OK;
+}
+
+static int ensure_pinned(sgpr_context* h, size_t bytes) {
+    if (bytes <= h->pinned_bytes) return SGPR_OK;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr;
+    h->pinned_bytes = 0;
+    SGPR_CUDA(cudaMallocHost(&h->pinned, bytes + bytes / 4));
+    h->pinned_bytes = bytes + bytes / 4;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_handle h, int64_t N, const double* pos_h, const int32_t* Z_h,
+                                 const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world, double* E_h,
+                                 double* F_h, double* W_h, double* beta_h, uint8_t* owned_h) {
+    if (!h || !E_h || !F_h || !W_h || (N > 0 && (!pos_h || !Z_h))) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    SGPR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->own_stream;
+    const size_t nb_pos = sizeof(double) * 3 * (size_t)N, nb_z = sizeof(int32_t) * (size_t)N;
+    const size_t nb_out = sizeof(double) * (3 * (size_t)N + 16);
+    SGPR_TRY(ensure_pinned(h, nb_pos + nb_z + nb_out + (size_t)N + 64));
+    char* pin = (char*)h->pinned;
+    double* pin_pos = (double*)pin;
+    double* pin_out = (double*)(pin + nb_pos);
+    int32_t* pin_z = (int32_t*)(pin + nb_pos + nb_out);
+    uint8_t* pin_own = (uint8_t*)(pin + nb_pos + nb_out + nb_z);
+    SGPR_TRY(h->stage_pos.ensure(nb_pos + 8));
+    SGPR_TRY(h->stage_z.ensure(nb_z + 8));
+    SGPR_TRY(h->stage_out.ensure(nb_out + (size_t)N + 64));
+    memcpy(pin_pos, pos_h, nb_pos);
+    memcpy(pin_z, Z_h, nb_z);
+    SGPR_CUDA(cudaMemcpyAsync(h->stage_pos.p, pin_pos, nb_pos, cudaMemcpyHostToDevice, st));
+    SGPR_CUDA(cudaMemcpyAsync(h->stage_z.p, pin_z, nb_z, cudaMemcpyHostToDevice, st));
+    double* out_d = h->stage_out.as<double>();  // [E(1) pad(6) W(9) F(3N)]
+    uint8_t* own_d = owned_h ? (uint8_t*)(out_d + 16 + 3 * (size_t)N) : nullptr;
+    SGPR_TRY(sgpr_predict(h, N, h->stage_pos.as<double>(), h->stage_z.as<int32_t>(), cell_h, pbc_h, rank, world, st,
+                          out_d, out_d + 16, out_d + 7, nullptr, own_d));
+    SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
+    if (owned_h) SGPR_CUDA(cudaMemcpyAsync(pin_own, own_d, (size_t)N, cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    E_h[0] = pin_out[0];
+    memcpy(W_h, pin_out + 7, sizeof(double) * 9);
+    memcpy(F_h, pin_out + 16, nb_pos);
+    if (owned_h) memcpy(owned_h, pin_own, (size_t)N);
+    (void)beta_h;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_kernel_forward(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                                   const double* cell_h, const int32_t* pbc_h, void* stream, double* K_d) {
+    if (!h || !K_d) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    Geom g;
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
+    const int grid_g = 2 * h->sm_count;
+    SGPR_TRY(h->gmat.ensure(sizeof(double) * ((size_t)N + 1) * h->ldg));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)h->S * grid_g + 64)));
+    SGPR_TRY(h->rowmap.ensure(sizeof(int) * ((size_t)N + 1)));
+    SGPR_CUDA(cudaMemsetAsync(K_d, 0, sizeof(double) * (size_t)N * h->M, st));
+    if (N > 0 && h->M > 0) {
+        row_to_orig_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(),
+                                                                   h->rowof.as<int>() + (N + 1), h->rowmap.as<int>());
+        SGPR_TRY(gemm_kernel_matrix(h, K_d, h->M, h->rowmap.as<int>(), st));
+        // lone-lone term, in the caller's inducing order
+        bool any = false;
+        for (int p = 0; p < h->M; ++p) any |= h->ind_lone[p] != 0;
+        if (any) {
+            lone_k_kernel<<<h->sm_count, 128, 0, st>>>((int)h->n_active, nullptr, h->atoms.as<AtomRec>(),
+                                                       h->nl_first.as<long long>(), h->M, h->ind_sp_d.as<int>(),
+                                                       h->ind_lone_d.as<unsigned char>(), K_d);
+        }
+        h->stats.kernel_launches += 2;
+    }
+    SGPR_CUDA(cudaGetLastError());
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_handle h, const double* gK_d, void* stream, double* gpos_d, double* gcell_h) {
+    (void)h; (void)gK_d; (void)stream; (void)gpos_d; (void)gcell_h;
+    set_error("sgpr_kernel_backward is not available in this build");
+    return SGPR_ERR_INVALID;
+}
+
+// =====================================================================================
+// parity hooks
+// =====================================================================================
+extern "C" __attribute__((visibility("default"))) int sgpr_neighbors(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                              const int32_t* pbc_h, void* stream, int64_t* first_d, int32_t* j_d, int8_t* S_d,
+                              int64_t capacity, int64_t* nnz_h) {
+    if (!h || !first_d || !nnz_h) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    Geom g;
+    h->stats.kernel_launches = 0;
+    h->last_N = N;
+    SGPR_TRY(build_geometry(h, N, pos_d, cell_h, pbc_h, st, &g));
+    SGPR_TRY(cell_sort(h, N, pos_d, Z_d, g, st));
+    h->active_all = true;
+    h->n_active = N;
+    int64_t n_pairs = 0;
+    SGPR_TRY(neighbor_build(h, N, g, st, &n_pairs));
+    *nnz_h = n_pairs;
+    // counts in caller order -> exclusive scan -> export
+    SGPR_TRY(h->misc.ensure(sizeof(long long) * ((size_t)N + 2)));
+    long long* cnt = h->misc.as<long long>();
+    nl_count_orig_kernel<<<(int)((N + 1 + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(),
+                                                                     h->nl_first.as<long long>(), cnt);
+    SGPR_TRY(scan_exclusive_ll(h, cnt, (long long*)first_d, (int)N + 1, st));
+    if (n_pairs <= capacity && N > 0 && j_d && S_d) {
+        nl_export_kernel<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->nl_pairs.as<PairRec>(),
+                                                                      h->nl_first.as<long long>(), (const long long*)first_d,
+                                                                      j_d, S_d);
+    }
+    SGPR_CUDA(cudaGetLastError());
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_descriptors(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                                const int32_t* pbc_h, void* stream, double* P_d) {
+    if (!h || !P_d) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    Geom g;
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
+    // source row of caller atom i: rowof[cell index of i]
+    SGPR_TRY(h->rowmap.ensure(sizeof(int) * 2 * ((size_t)N + 1)));
+    if (N > 0) {
+        orig_to_row_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(),
+                                                                   h->rowof.as<int>() + (N + 1), h->rowmap.as<int>());
+        SGPR_TRY(unpack_descriptors(h, N, h->phat.as<double>(), h->rowmap.as<int>(), P_d, st));
+    }
+    SGPR_CUDA(cudaGetLastError());
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_inducing_descriptors(sgpr_handle h, void* stream, double* Zhat_d) {
+    if (!h || !Zhat_d) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    if (h->M == 0) return SGPR_OK;
+    // source row of caller's inducing m = its sorted position
+    std::vector<int> src(h->M);
+    for (int p = 0; p < h->M; ++p) src[h->ind_perm[p]] = p;
+    SGPR_TRY(h->rowmap.ensure(sizeof(int) * ((size_t)h->M + 1)));
+    SGPR_CUDA(cudaMemcpyAsync(h->rowmap.p, src.data(), sizeof(int) * h->M, cudaMemcpyHostToDevice, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    SGPR_TRY(unpack_descriptors(h, h->M, h->zhat.as<double>(), h->rowmap.as<int>(), Zhat_d, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_get_stats(sgpr_handle h, sgpr_stats* out) {
+    if (!h || !out) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    *out = h->stats;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_enable_timing(sgpr_handle h, int32_t on) {
+    if (!h) {
+        set_error("null handle");
+        return SGPR_ERR_INVALID;
+    }
+    h->timing = on != 0;
+    return SGPR_OK;
+}

@@ -1,0 +1,566 @@
+// Per-atom descriptor kernels.
+//
+// forward : neighbour displacements -> radial x solid-harmonic expansion c[s,n,lm] ->
+//           power spectrum p[s1,s2,n1,n2,l] -> normalised, packed row q_hat
+//           (reference: SeSoap.forward / UniversalSoap.forward, descriptor/sesoap.py:161-260,
+//            descriptor/soap.py:765-851; Ylm.forward descriptor/ylm.py:113-190;
+//            displacements descriptor/atoms.py:365-368).
+// backward: g = dE/dq_hat -> dE/dc -> per-neighbour dE/dr_ij -> forces + pair virial
+//           (what torch.autograd does in calculator/active.py:587-611; analytic form
+//            as in sesoap.py:204-246 and ylm.py:191-222).
+//
+// One warp per environment.  Forward is two-phase per chunk of 32 neighbours: lanes
+// first own one neighbour each (radial + harmonics into shared memory), then own
+// components (n,lm) and accumulate over the chunk, so no cross-lane reduction is needed.
+// Backward keeps lanes on neighbours; the per-atom coefficients dE/dc live in shared
+// memory and are broadcast-read.
+//
+// Packed descriptor: the power spectrum is symmetric under (s1,n1)<->(s2,n2)
+// (descriptor/sesoap.py:195-203), so only pairs a<=b of a=(s,n) are stored, off-diagonal
+// entries scaled by sqrt(2): dot products and norms of packed rows equal those of the
+// reference's full [S,S,n,n,L] layout.
+#include "sgpr_internal.cuh"
+
+namespace sgpr {
+
+__constant__ HarmCoef c_harm;
+__constant__ unsigned char c_l_of_lm[(kMaxL + 1) * (kMaxL + 1)];
+
+int upload_harm_coef() {
+    HarmCoef hc;
+    fill_harm_coef(hc);
+    SGPR_CUDA(cudaMemcpyToSymbol(c_harm, &hc, sizeof(hc)));
+    unsigned char l_of[(kMaxL + 1) * (kMaxL + 1)];
+    for (int l = 0; l <= kMaxL; ++l)
+        for (int k = l * l; k < (l + 1) * (l + 1); ++k) l_of[k] = (unsigned char)l;
+    SGPR_CUDA(cudaMemcpyToSymbol(c_l_of_lm, l_of, sizeof(l_of)));
+    return SGPR_OK;
+}
+
+namespace {
+
+constexpr double kEps = 2.220446049250313e-16;  // torch.finfo(float64).eps, sesoap.py:249
+
+struct EnvSrc {
+    // atoms mode
+    const AtomRec* atoms;
+    const PairRec* pairs;
+    const long long* nl_first;
+    const int* active;   // env -> cell-order index (nullptr: identity)
+    // explicit-environment mode (inducing LCEs)
+    const long long* env_first;
+    const double* env_r;
+    const unsigned char* env_sp;
+};
+
+template <bool ENV>
+struct Nbr {
+    // displacement r_ij (as the reference computes it) and species of neighbour k
+    __device__ static __forceinline__ void load(const EnvSrc& src, const Geom& g, const AtomRec& ai, long long k,
+                                                double& rx, double& ry, double& rz, int& sp, int& j) {
+        if (ENV) {
+            rx = src.env_r[3 * k];
+            ry = src.env_r[3 * k + 1];
+            rz = src.env_r[3 * k + 2];
+            sp = src.env_sp[k];
+            j = -1;
+        } else {
+            const PairRec pr = src.pairs[k];
+            const AtomRec aj = src.atoms[pr.j];
+            j = pr.j;
+            sp = pr.sp;
+            const double S0 = (double)(pr.sb[0] - meta_w(aj.meta, 0) + meta_w(ai.meta, 0));
+            const double S1 = (double)(pr.sb[1] - meta_w(aj.meta, 1) + meta_w(ai.meta, 1));
+            const double S2 = (double)(pr.sb[2] - meta_w(aj.meta, 2) + meta_w(ai.meta, 2));
+            // r = xyz[n] - xyz[a] + (off[...,None]*lll).sum(dim=1)   (descriptor/atoms.py:366-368)
+            rx = __dadd_rn(__dadd_rn(aj.x, -ai.x), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[0]), __dmul_rn(S1, g.cell[3])), __dmul_rn(S2, g.cell[6])));
+            ry = __dadd_rn(__dadd_rn(aj.y, -ai.y), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[1]), __dmul_rn(S1, g.cell[4])), __dmul_rn(S2, g.cell[7])));
+            rz = __dadd_rn(__dadd_rn(aj.z, -ai.z), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[2]), __dmul_rn(S1, g.cell[5])), __dmul_rn(S2, g.cell[8])));
+        }
+    }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// packed-entry table word: a | b << 8 | l << 16
+__device__ __forceinline__ double pspec_entry(const DescParams& dp, const double* c_s, unsigned w, double scale) {
+    const int a = w & 0xff, b = (w >> 8) & 0xff, l = (w >> 16) & 0xff;
+    const double* ca = c_s + a * dp.L2 + l * l;
+    const double* cb = c_s + b * dp.L2 + l * l;
+    double s = 0.0;
+    for (int k = 0; k < 2 * l + 1; ++k) s += ca[k] * cb[k];
+    return s * scale;
+}
+
+// ---------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------
+template <int LMAX, int CPL, bool ENV>
+__global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
+                                                           const int* __restrict__ row_of,
+                                                           const unsigned* __restrict__ ptab,
+                                                           const double* __restrict__ nnlk, double* __restrict__ phat,
+                                                           double* __restrict__ cbuf, double* __restrict__ pnorm,
+                                                           unsigned char* __restrict__ sflag, int per_warp_doubles,
+                                                           int stride) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* c_s = smem + (size_t)warp * per_warp_doubles;
+    double* buf = c_s + ((dp.csize + 1) & ~1);
+    int* sp_s = reinterpret_cast<int*>(buf + 32 * stride);
+    // component ownership: comp = lane + 32 t  ->  (n, lm)
+    int offn[CPL], offy[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        const int comp = lane + 32 * t;
+        const int n = comp / dp.L2;
+        offn[t] = n;
+        offy[t] = dp.nb + (comp - n * dp.L2);
+    }
+    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
+        long long beg, end;
+        AtomRec ai;
+        int c = env;
+        if (ENV) {
+            beg = src.env_first[env];
+            end = src.env_first[env + 1];
+            ai.x = ai.y = ai.z = 0.0;
+            ai.meta = 0;
+        } else {
+            c = src.active ? src.active[env] : env;
+            ai = src.atoms[c];
+            beg = src.nl_first[env];
+            end = src.nl_first[env + 1];
+        }
+        for (int t = lane; t < dp.csize; t += 32) c_s[t] = 0.0;
+        // pass 0: does any neighbour sit (almost) on the z axis?   ylm.py:10-23
+        bool hit = false;
+        for (long long k = beg + lane; k < end; k += 32) {
+            double rx, ry, rz;
+            int sp, j;
+            Nbr<ENV>::load(src, g, ai, k, rx, ry, rz, sp, j);
+            const double u = dp.radii[sp];
+            hit |= near_z_axis(rx / u, ry / u, rz / u);
+        }
+        const bool flag = __any_sync(0xffffffffu, hit);
+        __syncwarp();
+        int cur_s = -1;
+        double acc[CPL];
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
+        for (long long k0 = beg; k0 < end; k0 += 32) {
+            const long long k = k0 + lane;
+            if (k < end) {
+                double rx, ry, rz;
+                int sp, j;
+                Nbr<ENV>::load(src, g, ai, k, rx, ry, rz, sp, j);
+                const double u = dp.radii[sp];
+                const double x = rx / u, y = ry / u, z = rz / u;
+                const double d2 = x * x + y * y + z * z;
+                const double d = sqrt(d2);
+                double R, Rpd;
+                radial(d, u, dp.rc, R, Rpd);
+                double* my = buf + lane * stride;
+                double fn = R;
+                for (int n = 0; n < dp.nb; ++n) {
+                    my[n] = fn;
+                    fn *= d2;
+                }
+                double ys = y, zs = z;
+                if (flag) {
+                    ys = y - kTinyAngle * z;
+                    zs = kTinyAngle * y + z;
+                }
+                double* yo = my + dp.nb;
+                solid_harmonics<LMAX, false>(c_harm, dp.lmax, x, ys, zs,
+                                             [&](int idx, double Y, double, double, double) { yo[idx] = Y; });
+                sp_s[lane] = sp;
+            }
+            __syncwarp();
+            const int cnt = (int)min((long long)32, end - k0);
+            for (int jj = 0; jj < cnt; ++jj) {
+                const int s = sp_s[jj];
+                if (s != cur_s) {
+                    if (cur_s >= 0) {
+#pragma unroll
+                        for (int t = 0; t < CPL; ++t) {
+                            const int comp = lane + 32 * t;
+                            if (comp < dp.ncomp) c_s[cur_s * dp.ncomp + comp] += acc[t];
+                            acc[t] = 0.0;
+                        }
+                    }
+                    cur_s = s;
+                }
+                const double* row = buf + jj * stride;
+#pragma unroll
+                for (int t = 0; t < CPL; ++t)
+                    if (lane + 32 * t < dp.ncomp) acc[t] += row[offn[t]] * row[offy[t]];
+            }
+            __syncwarp();
+        }
+        if (cur_s >= 0) {
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int comp = lane + 32 * t;
+                if (comp < dp.ncomp) c_s[cur_s * dp.ncomp + comp] += acc[t];
+            }
+        }
+        __syncwarp();
+        // power spectrum, norm over ALL blocks (sesoap.py:249-251), packed row out
+        double ss = 0.0;
+        for (int e = lane; e < dp.D; e += 32) {
+            const double q = pspec_entry(dp, c_s, ptab[e], nnlk[e]);
+            ss += q * q;
+        }
+        ss = warp_sum(ss);
+        const double P = dp.normalize ? (sqrt(ss) + kEps) : 1.0;
+        const size_t row = (size_t)row_of[ENV ? env : c] * dp.ldp;
+        for (int e = lane; e < dp.ldp; e += 32)
+            phat[row + e] = (e < dp.D) ? pspec_entry(dp, c_s, ptab[e], nnlk[e]) / P : 0.0;
+        if (cbuf) {
+            for (int t = lane; t < dp.csize; t += 32) cbuf[(size_t)env * dp.csize + t] = c_s[t];
+            if (lane == 0) {
+                pnorm[env] = P;
+                sflag[env] = flag ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// backward: forces + virial
+// ---------------------------------------------------------------------------------
+struct BackOut {
+    double* fcell;               // [N,3] forces in cell order (atomically accumulated)
+    double* wpart;               // [gridDim.x, 9] per-block virial partials
+    const unsigned char* owned;  // by cell-order index, nullptr = all owned
+    const unsigned char* sp_on;  // [S] species has usable inducing points
+};
+
+template <int LMAX, int NB>
+__global__ void __launch_bounds__(256) desc_backward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
+                                                            const int* __restrict__ row_of,
+                                                            const unsigned* __restrict__ ptab,
+                                                            const double* __restrict__ nnlk,
+                                                            const double* __restrict__ phat,
+                                                            const double* __restrict__ gvec,
+                                                            const double* __restrict__ cbuf,
+                                                            const double* __restrict__ pnorm,
+                                                            const unsigned char* __restrict__ sflag, BackOut out,
+                                                            int per_warp_doubles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double wred[8][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* T_s = smem + (size_t)warp * per_warp_doubles;   // [D]   dE/dq * kappa*nnl * (1 + [a==b])
+    double* c_s = T_s + ((dp.D + 1) & ~1);                  // [csize]
+    double* D_s = c_s + ((dp.csize + 1) & ~1);              // [csize] dE/dc
+    const int L = dp.lmax + 1;
+    double Wacc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Wacc[q] = 0.0;
+
+    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
+        const int c = src.active ? src.active[env] : env;
+        const AtomRec ai = src.atoms[c];
+        const int si = meta_species(ai.meta);
+        const long long beg = src.nl_first[env], end = src.nl_first[env + 1];
+        if (end == beg || !out.sp_on[si]) continue;   // warp-uniform
+        const size_t row = (size_t)row_of[c] * dp.ldp;
+        const double P = pnorm[env];
+        const bool flag = sflag[env] != 0;
+        double pg = 0.0;
+        if (dp.normalize) {
+            for (int e = lane; e < dp.D; e += 32) pg += phat[row + e] * gvec[row + e];
+            pg = warp_sum(pg);
+        }
+        for (int e = lane; e < dp.D; e += 32) {
+            const unsigned w = ptab[e];
+            const double gq = gvec[row + e];
+            const double dq = dp.normalize ? (gq - phat[row + e] * pg) / P : gq;
+            T_s[e] = dq * nnlk[e] * (((w & 0xff) == ((w >> 8) & 0xff)) ? 2.0 : 1.0);
+        }
+        for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
+        __syncwarp();
+        // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm]
+        for (int o = lane; o < dp.csize; o += 32) {
+            const int a = o / dp.L2, lm = o - a * dp.L2;
+            const int l = c_l_of_lm[lm];
+            double s = 0.0;
+            for (int b = 0; b < dp.A; ++b) {
+                const int lo = min(a, b), hi = max(a, b);
+                const int tri = lo * dp.A - (lo * (lo - 1)) / 2 + (hi - lo);
+                s += T_s[tri * L + l] * c_s[b * dp.L2 + lm];
+            }
+            D_s[o] = s;
+        }
+        __syncwarp();
+        double Fx = 0.0, Fy = 0.0, Fz = 0.0;
+        const bool own_i = out.owned ? (out.owned[c] != 0) : true;
+        for (long long k = beg + lane; k < end; k += 32) {
+            double rx, ry, rz;
+            int sp, j;
+            Nbr<false>::load(src, g, ai, k, rx, ry, rz, sp, j);
+            const double u = dp.radii[sp];
+            const double x = rx / u, y = ry / u, z = rz / u;
+            const double d2 = x * x + y * y + z * z;
+            const double d = sqrt(d2);
+            double R, Rpd;
+            radial(d, u, dp.rc, R, Rpd);
+            double f[NB], hh[NB], Tn[NB];
+            {
+                double pw = 1.0;  // d2^(n-1)
+                f[0] = R;
+                hh[0] = Rpd;
+                Tn[0] = 0.0;
+#pragma unroll
+                for (int n = 1; n < NB; ++n) {
+                    f[n] = f[n - 1] * d2;
+                    hh[n] = Rpd * (pw * d2) + 2.0 * n * R * pw;
+                    pw *= d2;
+                    Tn[n] = 0.0;
+                }
+            }
+            double ys = y, zs = z;
+            if (flag) {
+                ys = y - kTinyAngle * z;
+                zs = kTinyAngle * y + z;
+            }
+            const double* Dj = D_s + sp * dp.ncomp;
+            double gx = 0.0, gy = 0.0, gz = 0.0;
+            solid_harmonics<LMAX, true>(c_harm, dp.lmax, x, ys, zs,
+                                        [&](int idx, double Y, double dYx, double dYy, double dYz) {
+                                            double B = 0.0;
+#pragma unroll
+                                            for (int n = 0; n < NB; ++n) {
+                                                if (n < dp.nb) {
+                                                    const double dc = Dj[n * dp.L2 + idx];
+                                                    B += dc * f[n];
+                                                    Tn[n] += dc * Y;
+                                                }
+                                            }
+                                            gx += B * dYx;
+                                            gy += B * dYy;
+                                            gz += B * dYz;
+                                        });
+            if (flag) {  // transpose of the shear, ylm.py:212-220
+                const double t = gy;
+                gy = t + kTinyAngle * gz;
+                gz = -kTinyAngle * t + gz;
+            }
+            double rad = 0.0;
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+                if (n < dp.nb) rad += Tn[n] * hh[n];
+            const double Gx = (rad * x + gx) / u, Gy = (rad * y + gy) / u, Gz = (rad * z + gz) / u;
+            if (own_i) {
+                Fx += Gx;
+                Fy += Gy;
+                Fz += Gz;
+                Wacc[0] += rx * Gx; Wacc[1] += rx * Gy; Wacc[2] += rx * Gz;
+                Wacc[3] += ry * Gx; Wacc[4] += ry * Gy; Wacc[5] += ry * Gz;
+                Wacc[6] += rz * Gx; Wacc[7] += rz * Gy; Wacc[8] += rz * Gz;
+            }
+            if (!out.owned || out.owned[j]) {
+                atomicAdd(out.fcell + 3 * (size_t)j, -Gx);
+                atomicAdd(out.fcell + 3 * (size_t)j + 1, -Gy);
+                atomicAdd(out.fcell + 3 * (size_t)j + 2, -Gz);
+            }
+        }
+        Fx = warp_sum(Fx);
+        Fy = warp_sum(Fy);
+        Fz = warp_sum(Fz);
+        if (lane == 0 && own_i) {
+            atomicAdd(out.fcell + 3 * (size_t)c, Fx);
+            atomicAdd(out.fcell + 3 * (size_t)c + 1, Fy);
+            atomicAdd(out.fcell + 3 * (size_t)c + 2, Fz);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Wacc[q] = warp_sum(Wacc[q]);
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) wred[warp][q] = Wacc[q];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += wred[w][threadIdx.x];
+        out.wpart[blockIdx.x * 9 + threadIdx.x] = s;
+    }
+}
+
+// packed row -> the reference's dense block layout [S,S,nb,nb,L]
+__global__ void unpack_kernel(DescParams dp, long long rows, const double* __restrict__ packed,
+                              const int* __restrict__ src_row, double* __restrict__ full) {
+    const int L = dp.lmax + 1;
+    const long long dfull = (long long)dp.A * dp.A * L;
+    const long long total = rows * dfull;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / dfull;
+        int o = (int)(t - r * dfull);
+        const int l = o % L; o /= L;
+        const int n2 = o % dp.nb; o /= dp.nb;
+        const int n1 = o % dp.nb; o /= dp.nb;
+        const int s2 = o % dp.S;
+        const int s1 = o / dp.S;
+        const int a = s1 * dp.nb + n1, b = s2 * dp.nb + n2;
+        const int lo = min(a, b), hi = max(a, b);
+        const int tri = lo * dp.A - (lo * (lo - 1)) / 2 + (hi - lo);
+        const double v = packed[(size_t)(src_row ? src_row[r] : r) * dp.ldp + tri * L + l];
+        full[t] = (a == b) ? v : v * 0.70710678118654752440;
+    }
+}
+
+struct Launch {
+    int warps;
+    size_t smem;
+    int per_warp;
+};
+
+Launch plan_forward(const DescParams& dp, int stride) {
+    int per_warp = ((dp.csize + 1) & ~1) + 32 * stride + 16;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
+    return {warps, (size_t)warps * per_warp * 8, per_warp};
+}
+Launch plan_backward(const DescParams& dp) {
+    int per_warp = ((dp.D + 1) & ~1) + 2 * ((dp.csize + 1) & ~1);
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
+    return {warps, (size_t)warps * per_warp * 8, per_warp};
+}
+
+template <int LMAX, int CPL, bool ENV>
+int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const int* row_of, double* phat,
+                   double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
+    const DescParams& dp = h->dp;
+    int stride = dp.nb + dp.L2;
+    if ((stride & 1) == 0) stride += 1;  // odd stride: lanes writing their own row hit distinct banks
+    Launch L = plan_forward(dp, stride);
+    if ((size_t)L.per_warp * 8 > 200 * 1024) {
+        set_error("descriptor too large for shared memory (S=%d nmax=%d lmax=%d)", dp.S, dp.nb - 1, dp.lmax);
+        return SGPR_ERR_INVALID;
+    }
+    auto kern = desc_forward_kernel<LMAX, CPL, ENV>;
+    SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    int grid = (n_env + L.warps - 1) / L.warps;
+    const int maxgrid = h->sm_count * 16;
+    if (grid > maxgrid) grid = maxgrid;
+    if (grid < 1) grid = 1;
+    kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, row_of, h->ptab.as<unsigned>(), h->nnlk.as<double>(), phat,
+                                             cbuf, pnorm, sflag, L.per_warp, stride);
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
+template <bool ENV>
+int dispatch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const int* row_of, double* phat,
+                     double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
+    const int lmax = h->dp.lmax, ncomp = h->dp.ncomp;
+    const int cpl = (ncomp + 31) / 32;
+#define FWD(LM, CP) return launch_forward<LM, CP, ENV>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st)
+    if (lmax <= 3 && cpl <= 2) FWD(3, 2);
+    if (lmax <= 3 && cpl <= 6) FWD(3, 6);
+    if (lmax <= 6 && cpl <= 8) FWD(6, 8);
+    if (lmax <= 6 && cpl <= 14) FWD(6, 14);
+    if (lmax <= 6 && cpl <= 19) FWD(6, 19);
+    if (lmax <= 8 && cpl <= 16) FWD(8, 16);
+    if (lmax <= 8 && cpl <= 31) FWD(8, 31);
+#undef FWD
+    set_error("unsupported descriptor size lmax=%d nmax=%d", lmax, h->dp.nb - 1);
+    return SGPR_ERR_INVALID;
+}
+
+template <int LMAX, int NB>
+int launch_backward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const BackOut& out, int grid,
+                    cudaStream_t st) {
+    const DescParams& dp = h->dp;
+    Launch L = plan_backward(dp);
+    if ((size_t)L.per_warp * 8 > 200 * 1024) {
+        set_error("descriptor too large for shared memory (S=%d nmax=%d lmax=%d)", dp.S, dp.nb - 1, dp.lmax);
+        return SGPR_ERR_INVALID;
+    }
+    auto kern = desc_backward_kernel<LMAX, NB>;
+    SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, h->rowof.as<int>() + (h->last_N + 1),
+                                             h->ptab.as<unsigned>(), h->nnlk.as<double>(), h->phat.as<double>(),
+                                             h->gvec.as<double>(), h->cbuf.as<double>(), h->pnorm.as<double>(),
+                                             h->sflag.as<unsigned char>(), out, L.per_warp);
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
+}  // namespace
+
+int descriptor_forward_env(sgpr_context* h, int M, const long long* env_first_d, const double* env_r_d,
+                           const unsigned char* env_sp_d, const int* row_of_d, double* phat_d, cudaStream_t st) {
+    EnvSrc src{};
+    src.env_first = env_first_d;
+    src.env_r = env_r_d;
+    src.env_sp = env_sp_d;
+    Geom g{};
+    return dispatch_forward<true>(h, g, M, src, row_of_d, phat_d, nullptr, nullptr, nullptr, st);
+}
+
+int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st) {
+    const int na = (int)h->n_active;
+    const DescParams& dp = h->dp;
+    SGPR_TRY(h->cbuf.ensure(sizeof(double) * ((size_t)na * dp.csize + 1)));
+    SGPR_TRY(h->pnorm.ensure(sizeof(double) * ((size_t)na + 1)));
+    SGPR_TRY(h->sflag.ensure((size_t)na + 1));
+    if (na == 0) return SGPR_OK;
+    EnvSrc src{};
+    src.atoms = h->atoms.as<AtomRec>();
+    src.pairs = h->nl_pairs.as<PairRec>();
+    src.nl_first = h->nl_first.as<long long>();
+    src.active = h->active_all ? nullptr : h->active_list.as<int>();
+    return dispatch_forward<false>(h, g, na, src, h->rowof.as<int>() + (h->last_N + 1), h->phat.as<double>(),
+                                   h->cbuf.as<double>(), h->pnorm.as<double>(), h->sflag.as<unsigned char>(), st);
+}
+
+int backward_grid(sgpr_context* h) { return h->sm_count * 8; }
+
+int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st) {
+    const int na = (int)h->n_active;
+    if (na == 0) return SGPR_OK;
+    EnvSrc src{};
+    src.atoms = h->atoms.as<AtomRec>();
+    src.pairs = h->nl_pairs.as<PairRec>();
+    src.nl_first = h->nl_first.as<long long>();
+    src.active = h->active_all ? nullptr : h->active_list.as<int>();
+    BackOut out{};
+    out.fcell = h->fcell.as<double>();
+    out.wpart = h->wpart.as<double>();
+    out.owned = owned_d;
+    out.sp_on = h->sp_on.as<unsigned char>();
+    const int grid = backward_grid(h);
+    const int lmax = h->dp.lmax, nb = h->dp.nb;
+#define BWD(LM, NBB) return launch_backward<LM, NBB>(h, g, na, src, out, grid, st)
+    if (lmax <= 3 && nb <= 4) BWD(3, 4);
+    if (lmax <= 3 && nb <= 8) BWD(3, 8);
+    if (lmax <= 6 && nb <= 6) BWD(6, 6);
+    if (lmax <= 6 && nb <= 9) BWD(6, 9);
+    if (lmax <= 6 && nb <= 12) BWD(6, 12);
+    if (lmax <= 8 && nb <= 12) BWD(8, 12);
+#undef BWD
+    set_error("unsupported descriptor size lmax=%d nmax=%d", lmax, nb - 1);
+    return SGPR_ERR_INVALID;
+}
+
+int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, const int* src_row_d, double* full_d,
+                       cudaStream_t st) {
+    if (rows == 0) return SGPR_OK;
+    unpack_kernel<<<h->sm_count * 4, 256, 0, st>>>(h->dp, rows, packed_d, src_row_d, full_d);
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
+}  // namespace sgpr

@@ -1,0 +1,509 @@
+// Cell-list neighbour search.
+//
+// Semantics restated from the reference's call site descriptor/atoms.py:348-368
+// (ASE NeighborList(N*[rc/2], skin=0, self_interaction=False, bothways=True)):
+//   pair (i, j, S) kept  iff  sqrt(|x_j - x_i + S.cell|^2) < rc  (strict), both
+//   directions, (i == j, S == 0) dropped, periodic images of the same atom kept,
+//   S relative to the positions as given.
+// The distance is evaluated from the caller's (unwrapped) positions in the reference's
+// operation order (r = (x_j - x_i) + sum_k S_k cell_k, no FMA contraction), so the
+// accept/reject decision is the same floating-point comparison the reference makes.
+//
+// Layout: atoms are counting-sorted by key = bin*S + species ("cell order"); a bin's
+// atoms are one contiguous run, ordered by species then by original index
+// (deterministic).  Descriptor rows use a second, species-major order ("row order") so
+// that the kernel GEMM sees one contiguous row block per central species.
+#include <cub/device/device_scan.cuh>
+#include <math.h>
+
+#include "sgpr_internal.cuh"
+
+namespace sgpr {
+
+// ---------------------------------------------------------------------------------
+// geometry (host)
+// ---------------------------------------------------------------------------------
+static void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static double norm3(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+
+// Replace zero lattice vectors by unit vectors orthogonal to the others (what ASE's
+// Atoms.get_cell(complete=True) hands to the neighbour list).
+static void complete_cell(double* c) {
+    bool missing[3];
+    int nmiss = 0;
+    for (int i = 0; i < 3; ++i) {
+        missing[i] = (c[3 * i] == 0.0 && c[3 * i + 1] == 0.0 && c[3 * i + 2] == 0.0);
+        nmiss += missing[i];
+    }
+    if (nmiss == 3) {
+        for (int i = 0; i < 9; ++i) c[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    } else if (nmiss == 2) {
+        int p = !missing[0] ? 0 : (!missing[1] ? 1 : 2);
+        double v[3] = {c[3 * p], c[3 * p + 1], c[3 * p + 2]};
+        double n = norm3(v);
+        for (int k = 0; k < 3; ++k) v[k] /= n;
+        int m = 0;
+        for (int k = 1; k < 3; ++k)
+            if (fabs(v[k]) < fabs(v[m])) m = k;
+        double t[3] = {0, 0, 0};
+        t[m] = 1.0;
+        double e1[3], e2[3];
+        cross3(v, t, e1);
+        n = norm3(e1);
+        for (int k = 0; k < 3; ++k) e1[k] /= n;
+        cross3(v, e1, e2);
+        int q = 0;
+        for (int i = 0; i < 3; ++i)
+            if (missing[i]) {
+                const double* e = (q++ == 0) ? e1 : e2;
+                for (int k = 0; k < 3; ++k) c[3 * i + k] = e[k];
+            }
+    } else if (nmiss == 1) {
+        int i = missing[0] ? 0 : (missing[1] ? 1 : 2);
+        double e[3];
+        cross3(&c[3 * ((i + 1) % 3)], &c[3 * ((i + 2) % 3)], e);
+        double n = norm3(e);
+        for (int k = 0; k < 3; ++k) c[3 * i + k] = e[k] / n;
+    }
+}
+
+__global__ void frac_minmax_kernel(int64_t N, const double* __restrict__ pos, Geom g, double* __restrict__ part) {
+    // per-block min/max of the fractional coordinates (non-periodic axes need a bounding box)
+    __shared__ double smin[3][256], smax[3][256];
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        for (int c = 0; c < 3; ++c) {
+            double f = x * g.inv[c] + y * g.inv[3 + c] + z * g.inv[6 + c];
+            mn[c] = fmin(mn[c], f);
+            mx[c] = fmax(mx[c], f);
+        }
+    }
+    for (int c = 0; c < 3; ++c) {
+        smin[c][threadIdx.x] = mn[c];
+        smax[c][threadIdx.x] = mx[c];
+    }
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int c = 0; c < 3; ++c) {
+                smin[c][threadIdx.x] = fmin(smin[c][threadIdx.x], smin[c][threadIdx.x + s]);
+                smax[c][threadIdx.x] = fmax(smax[c][threadIdx.x], smax[c][threadIdx.x + s]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 3; ++c) {
+            part[blockIdx.x * 6 + c] = smin[c][0];
+            part[blockIdx.x * 6 + 3 + c] = smax[c][0];
+        }
+}
+
+int build_geometry(sgpr_context* h, int64_t N, const double* pos_d, const double* cell_h, const int32_t* pbc_h,
+                   cudaStream_t st, Geom* g) {
+    for (int i = 0; i < 9; ++i) g->cell[i] = cell_h[i];
+    for (int c = 0; c < 3; ++c) g->pbc[c] = pbc_h[c] ? 1 : 0;
+    complete_cell(g->cell);
+    const double* a = g->cell;
+    double bc[3], ca[3], ab[3];
+    cross3(a + 3, a + 6, bc);
+    cross3(a + 6, a + 0, ca);
+    cross3(a + 0, a + 3, ab);
+    double vol = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2];
+    if (!(fabs(vol) > 1e-12)) {
+        set_error("singular cell (volume %g)", vol);
+        return SGPR_ERR_GEOMETRY;
+    }
+    // inverse: columns are the reciprocal vectors b_c = (a_{c+1} x a_{c+2}) / vol
+    const double* rec[3] = {bc, ca, ab};
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < 3; ++k) g->inv[k * 3 + c] = rec[c][k] / vol;
+    g->rc = h->dp.rc;
+    double hface[3];
+    for (int c = 0; c < 3; ++c) hface[c] = fabs(vol) / norm3(rec[c]);
+    bool open = !(g->pbc[0] && g->pbc[1] && g->pbc[2]);
+    double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    if (open && N > 0) {
+        int nblk = 64;
+        SGPR_TRY(h->misc.ensure(sizeof(double) * 6 * nblk));
+        frac_minmax_kernel<<<nblk, 256, 0, st>>>(N, pos_d, *g, h->misc.as<double>());
+        std::vector<double> part(6 * nblk);
+        SGPR_CUDA(cudaMemcpyAsync(part.data(), h->misc.p, sizeof(double) * 6 * nblk, cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaStreamSynchronize(st));
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = 1e300;
+            hi[c] = -1e300;
+            for (int b = 0; b < nblk; ++b) {
+                lo[c] = fmin(lo[c], part[b * 6 + c]);
+                hi[c] = fmax(hi[c], part[b * 6 + 3 + c]);
+            }
+        }
+    }
+    const double rcs = g->rc * (1.0 + 1e-7);
+    for (int c = 0; c < 3; ++c) {
+        if (g->pbc[c]) {
+            int nb = (int)floor(hface[c] / rcs);
+            if (nb < 1) nb = 1;
+            g->nb[c] = nb;
+            g->reach[c] = (int)ceil(rcs / (hface[c] / nb));
+            g->flo[c] = 0.0;
+            g->fscale[c] = (double)nb;
+        } else {
+            double ext = (hi[c] - lo[c]) * hface[c];
+            int nb = (int)floor(ext / rcs);
+            if (nb < 1) nb = 1;
+            g->nb[c] = nb;
+            g->reach[c] = 1;
+            g->flo[c] = lo[c];
+            g->fscale[c] = (hi[c] > lo[c]) ? nb / (hi[c] - lo[c]) : 0.0;
+        }
+    }
+    // keep the cell table small relative to the number of atoms (larger bins stay correct)
+    const double limit = fmax(4096.0, 4.0 * (double)N);
+    for (;;) {
+        double nc = (double)g->nb[0] * g->nb[1] * g->nb[2];
+        if (nc <= limit) break;
+        int c = 0;
+        for (int k = 1; k < 3; ++k)
+            if (g->nb[k] > g->nb[c]) c = k;
+        int nb = (g->nb[c] + 1) / 2;
+        if (g->pbc[c]) {
+            g->fscale[c] = (double)nb;
+            g->reach[c] = (int)ceil(rcs / (hface[c] / nb));
+        } else {
+            g->fscale[c] *= (double)nb / g->nb[c];
+        }
+        g->nb[c] = nb;
+    }
+    g->ncell = g->nb[0] * g->nb[1] * g->nb[2];
+    return SGPR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// counting sort into cell order
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void frac_bin(const Geom& g, double x, double y, double z, int* bin3, int* w3) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double f = x * g.inv[c] + y * g.inv[3 + c] + z * g.inv[6 + c];
+        int w = 0;
+        if (g.pbc[c]) {
+            double fl = floor(f);
+            w = (int)fl;
+            f -= fl;
+        } else {
+            f -= g.flo[c];
+        }
+        int b = (int)(f * g.fscale[c]);
+        b = max(0, min(g.nb[c] - 1, b));
+        bin3[c] = b;
+        w3[c] = w;
+    }
+}
+
+__global__ void bin_count_kernel(int64_t N, const double* __restrict__ pos, const int32_t* __restrict__ Z,
+                                 const int* __restrict__ ztab, Geom g, int S, int* __restrict__ cnt,
+                                 int* __restrict__ key_out, int* __restrict__ rank_out, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int z = Z[i];
+    int s = (z >= 0 && z < 128) ? ztab[z] : -1;
+    if (s < 0) {
+        atomicExch(&err[0], 1);
+        atomicExch(&err[1], z);
+        s = 0;
+    }
+    int b[3], w[3];
+    frac_bin(g, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], b, w);
+    if (abs(w[0]) > 120 || abs(w[1]) > 120 || abs(w[2]) > 120) atomicExch(&err[0], 2);
+    int bin = (b[0] * g.nb[1] + b[1]) * g.nb[2] + b[2];
+    int key = bin * S + s;
+    key_out[i] = key;
+    rank_out[i] = atomicAdd(&cnt[key], 1);
+}
+
+__global__ void transpose_cnt_kernel(int ncell, int S, const int* __restrict__ cnt, int* __restrict__ cntT) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncell * S) return;
+    int bin = k / S, s = k - bin * S;
+    cntT[s * ncell + bin] = cnt[k];
+}
+
+__global__ void scatter_order_kernel(int64_t N, const int* __restrict__ key, const int* __restrict__ rank,
+                                     const int* __restrict__ cstart, int* __restrict__ order) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    order[cstart[key[i]] + rank[i]] = (int)i;
+}
+
+// one thread per key: sort the (short) run by original index -> deterministic cell order
+__global__ void sort_runs_kernel(int nkeys, const int* __restrict__ cstart, int* __restrict__ order) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    int b = cstart[k], e = cstart[k + 1];
+    for (int i = b + 1; i < e; ++i) {
+        int v = order[i];
+        int j = i - 1;
+        while (j >= b && order[j] > v) {
+            order[j + 1] = order[j];
+            --j;
+        }
+        order[j + 1] = v;
+    }
+}
+
+__global__ void gather_atoms_kernel(int64_t N, const double* __restrict__ pos, const int* __restrict__ key,
+                                    const int* __restrict__ order, const int* __restrict__ cstart,
+                                    const int* __restrict__ rstartT, Geom g, int S, AtomRec* __restrict__ atoms,
+                                    int* __restrict__ abin, int* __restrict__ rowof) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    int i = order[c];
+    int k = key[i];
+    int bin = k / S, s = k - bin * S;
+    double x = pos[3 * (int64_t)i], y = pos[3 * (int64_t)i + 1], z = pos[3 * (int64_t)i + 2];
+    int b[3], w[3];
+    frac_bin(g, x, y, z, b, w);
+    AtomRec r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    r.meta = (unsigned long long)(unsigned int)i | ((unsigned long long)s << 32) |
+             ((unsigned long long)(w[0] + 128) << 40) | ((unsigned long long)(w[1] + 128) << 48) |
+             ((unsigned long long)(w[2] + 128) << 56);
+    atoms[c] = r;
+    abin[c] = bin;
+    rowof[c] = rstartT[s * g.ncell + bin] + (int)(c - cstart[k]);
+}
+
+static int scan_exclusive_int(sgpr_context* h, const int* in, int* out, int n, cudaStream_t st) {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st);
+    SGPR_TRY(h->scan_tmp.ensure(tmp));
+    SGPR_CUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp, in, out, n, st));
+    return SGPR_OK;
+}
+
+int scan_exclusive_ll(sgpr_context* h, const long long* in, long long* out, int n, cudaStream_t st) {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st);
+    SGPR_TRY(h->scan_tmp.ensure(tmp));
+    SGPR_CUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp, in, out, n, st));
+    return SGPR_OK;
+}
+
+// Workspace layout after cell_sort (all int32 unless noted):
+//   cnt     [nkeys+1]   atoms per key (last entry 0 so the exclusive scan yields the total)
+//   cstart  [nkeys+1]   first cell-order index of each key
+//   rstart  [2*(nkeys+1)]  transposed counts, then their scan: first row of (species, bin)
+//   keyrank [2N]        key per original atom, arbitrary rank within key
+//   order   [N]         original index of cell-order atom c
+//   atoms   [N] AtomRec ; rowof [2N]: abin[c], rowof[c]
+//   misc    [16] ints   err flag(2) ...
+int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const Geom& g, cudaStream_t st) {
+    const int S = h->S;
+    const int nkeys = g.ncell * S;
+    SGPR_TRY(h->cnt.ensure(sizeof(int) * (nkeys + 1)));
+    SGPR_TRY(h->cstart.ensure(sizeof(int) * (nkeys + 1)));
+    SGPR_TRY(h->rstart.ensure(sizeof(int) * 2 * (nkeys + 1)));
+    SGPR_TRY(h->keyrank.ensure(sizeof(int) * 2 * (N + 1)));
+    SGPR_TRY(h->order.ensure(sizeof(int) * (N + 1)));
+    SGPR_TRY(h->atoms.ensure(sizeof(AtomRec) * (N + 1)));
+    SGPR_TRY(h->rowof.ensure(sizeof(int) * 2 * (N + 1)));
+    int* cnt = h->cnt.as<int>();
+    int* cstart = h->cstart.as<int>();
+    int* cntT = h->rstart.as<int>();
+    int* rstartT = cntT + (nkeys + 1);
+    int* key = h->keyrank.as<int>();
+    int* rank = key + (N + 1);
+    int* err = h->errflag.as<int>();
+    SGPR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (nkeys + 1), st));
+    SGPR_CUDA(cudaMemsetAsync(cntT, 0, sizeof(int) * (nkeys + 1), st));
+    SGPR_CUDA(cudaMemsetAsync(err, 0, sizeof(int) * 4, st));
+    const int T = 256;
+    const int nblkN = (int)((N + T - 1) / T);
+    const int nblkK = (nkeys + T - 1) / T;
+    if (N > 0)
+        bin_count_kernel<<<nblkN, T, 0, st>>>(N, pos_d, Z_d, h->ztab.as<int>(), g, S, cnt, key, rank, err);
+    transpose_cnt_kernel<<<nblkK, T, 0, st>>>(g.ncell, S, cnt, cntT);
+    SGPR_TRY(scan_exclusive_int(h, cnt, cstart, nkeys + 1, st));
+    SGPR_TRY(scan_exclusive_int(h, cntT, rstartT, nkeys + 1, st));
+    if (N > 0) {
+        scatter_order_kernel<<<nblkN, T, 0, st>>>(N, key, rank, cstart, h->order.as<int>());
+        sort_runs_kernel<<<nblkK, T, 0, st>>>(nkeys, cstart, h->order.as<int>());
+        gather_atoms_kernel<<<nblkN, T, 0, st>>>(N, pos_d, key, h->order.as<int>(), cstart, rstartT, g, S,
+                                                 h->atoms.as<AtomRec>(), h->rowof.as<int>(),
+                                                 h->rowof.as<int>() + (N + 1));
+    }
+    h->stats.kernel_launches += 7;
+    SGPR_CUDA(cudaGetLastError());
+    return SGPR_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// neighbour search: one warp per atom, lanes over the candidates of a bin run
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_test(const Geom& g, const AtomRec& ai, const AtomRec& aj, int sx, int sy, int sz,
+                                          bool same) {
+    // image shift relative to the positions as given:  S = S_bin - w_j + w_i
+    const int S0 = sx - meta_w(aj.meta, 0) + meta_w(ai.meta, 0);
+    const int S1 = sy - meta_w(aj.meta, 1) + meta_w(ai.meta, 1);
+    const int S2 = sz - meta_w(aj.meta, 2) + meta_w(ai.meta, 2);
+    if (same && S0 == 0 && S1 == 0 && S2 == 0) return false;
+    // r = (x_j - x_i) + ((S0*c0 + S1*c1) + S2*c2), rounded like the reference (no FMA)
+    double r[3];
+    const double xj[3] = {aj.x, aj.y, aj.z}, xi[3] = {ai.x, ai.y, ai.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double sh = __dadd_rn(__dadd_rn(__dmul_rn((double)S0, g.cell[k]), __dmul_rn((double)S1, g.cell[3 + k])),
+                              __dmul_rn((double)S2, g.cell[6 + k]));
+        r[k] = __dadd_rn(__dadd_rn(xj[k], -xi[k]), sh);
+    }
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])), __dmul_rn(r[2], r[2]));
+    return __dsqrt_rn(d2) < g.rc;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) neighbor_kernel(int n_active, const int* __restrict__ active,
+                                                       const AtomRec* __restrict__ atoms, const int* __restrict__ abin,
+                                                       const int* __restrict__ cstart, Geom g, int S,
+                                                       int* __restrict__ nl_cnt, const long long* __restrict__ nl_first,
+                                                       PairRec* __restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_active) return;
+    const int c = active ? active[wid] : wid;
+    const AtomRec ai = atoms[c];
+    int bin = abin[c];
+    const int bz = bin % g.nb[2];
+    bin /= g.nb[2];
+    const int by = bin % g.nb[1];
+    const int bx = bin / g.nb[1];
+    int count[kMaxSpecies];
+    long long base[kMaxSpecies];
+#pragma unroll
+    for (int s = 0; s < kMaxSpecies; ++s) count[s] = 0;
+    if (FILL) {
+        long long o = nl_first[wid];
+#pragma unroll
+        for (int s = 0; s < kMaxSpecies; ++s) {
+            base[s] = o;
+            if (s < S) o += nl_cnt[(long long)wid * S + s];
+        }
+    }
+    for (int dx = -g.reach[0]; dx <= g.reach[0]; ++dx) {
+        int nx = bx + dx, sx = 0;
+        if (g.pbc[0]) {
+            sx = (nx >= 0) ? nx / g.nb[0] : -((-nx + g.nb[0] - 1) / g.nb[0]);
+            nx -= sx * g.nb[0];
+        } else if (nx < 0 || nx >= g.nb[0]) continue;
+        for (int dy = -g.reach[1]; dy <= g.reach[1]; ++dy) {
+            int ny = by + dy, sy = 0;
+            if (g.pbc[1]) {
+                sy = (ny >= 0) ? ny / g.nb[1] : -((-ny + g.nb[1] - 1) / g.nb[1]);
+                ny -= sy * g.nb[1];
+            } else if (ny < 0 || ny >= g.nb[1]) continue;
+            for (int dz = -g.reach[2]; dz <= g.reach[2]; ++dz) {
+                int nz = bz + dz, sz = 0;
+                if (g.pbc[2]) {
+                    sz = (nz >= 0) ? nz / g.nb[2] : -((-nz + g.nb[2] - 1) / g.nb[2]);
+                    nz -= sz * g.nb[2];
+                } else if (nz < 0 || nz >= g.nb[2]) continue;
+                const int b2 = (nx * g.nb[1] + ny) * g.nb[2] + nz;
+                const int beg = cstart[b2 * S], end = cstart[b2 * S + S];
+                for (int p0 = beg; p0 < end; p0 += 32) {
+                    const int p = p0 + lane;
+                    bool acc = false;
+                    int sp = 0;
+                    if (p < end) {
+                        const AtomRec aj = atoms[p];
+                        sp = meta_species(aj.meta);
+                        acc = pair_test(g, ai, aj, sx, sy, sz, p == c);
+                    }
+#pragma unroll
+                    for (int s = 0; s < kMaxSpecies; ++s) {
+                        if (s < S) {
+                            const unsigned m = __ballot_sync(0xffffffffu, acc && sp == s);
+                            if (FILL) {
+                                if (acc && sp == s) {
+                                    PairRec pr;
+                                    pr.j = p;
+                                    pr.sb[0] = (signed char)sx;
+                                    pr.sb[1] = (signed char)sy;
+                                    pr.sb[2] = (signed char)sz;
+                                    pr.sp = (unsigned char)sp;
+                                    pairs[base[s] + count[s] + __popc(m & ((1u << lane) - 1u))] = pr;
+                                }
+                            }
+                            count[s] += __popc(m);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!FILL && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kMaxSpecies; ++s)
+            if (s < S) nl_cnt[(long long)wid * S + s] = count[s];
+    }
+}
+
+__global__ void row_total_kernel(int n, int S, const int* __restrict__ nl_cnt, long long* __restrict__ tot) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    long long t = 0;
+    if (i < n)
+        for (int s = 0; s < S; ++s) t += nl_cnt[(long long)i * S + s];
+    tot[i] = t;
+}
+
+// Builds the CSR neighbour list of the active atoms (h->n_active entries of active_list,
+// or all atoms in cell order when h->active_all):
+//   nl_cnt [n_active, S], nl_first [n_active+1] (int64), nl_pairs [n_pairs] PairRec,
+//   rows ordered by neighbour species, then bin traversal order, then cell order.
+int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs) {
+    const int S = h->S;
+    const int na = (int)h->n_active;
+    const int* active = h->active_all ? nullptr : h->active_list.as<int>();
+    SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)na * S + 1)));
+    SGPR_TRY(h->nl_first.ensure(sizeof(long long) * 2 * ((size_t)na + 1)));
+    long long* first = h->nl_first.as<long long>();
+    long long* tot = first + (na + 1);
+    *n_pairs = 0;
+    if (na == 0) return SGPR_OK;
+    const int T = 256;
+    const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
+    const AtomRec* atoms = h->atoms.as<AtomRec>();
+    const int* abin = h->rowof.as<int>();
+    neighbor_kernel<false><<<nblk, T, 0, st>>>(na, active, atoms, abin, h->cstart.as<int>(), g, S, h->nl_cnt.as<int>(),
+                                               nullptr, nullptr);
+    row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
+    SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
+    long long total = 0;
+    SGPR_CUDA(cudaMemcpyAsync(&total, first + na, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    int err[4] = {0, 0, 0, 0};
+    SGPR_CUDA(cudaMemcpyAsync(err, h->errflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    if (err[0] == 1) {
+        set_error("atomic number %d is not in the handle's species table", err[1]);
+        return SGPR_ERR_SPECIES;
+    }
+    if (err[0] == 2) {
+        set_error("an atom lies more than 120 cells outside the unit cell; wrap positions first");
+        return SGPR_ERR_GEOMETRY;
+    }
+    SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
+    neighbor_kernel<true><<<nblk, T, 0, st>>>(na, active, atoms, abin, h->cstart.as<int>(), g, S, h->nl_cnt.as<int>(),
+                                              first, h->nl_pairs.as<PairRec>());
+    h->stats.kernel_launches += 4;
+    SGPR_CUDA(cudaGetLastError());
+    *n_pairs = total;
+    return SGPR_OK;
+}
+
+}  // namespace sgpr

@@ -1,0 +1,173 @@
+// Internal declarations shared by the translation units of libsgpr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sgpr_b200.h"
+#include "sgpr_math.cuh"
+
+namespace sgpr {
+
+// ----------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define SGPR_CUDA(call)                                                                    \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            sgpr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return SGPR_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+#define SGPR_TRY(call)                \
+    do {                              \
+        int _s = (call);              \
+        if (_s != SGPR_OK) return _s; \
+    } while (0)
+
+// ----------------------------------------------------------------------------------
+// device-side views
+// ----------------------------------------------------------------------------------
+
+// Atom record in cell order: position as given by the caller (NOT wrapped) + meta word.
+//   meta bits  0..31 original index | 32..39 species index | 40..47 w0+128 | 48..55 w1+128
+//              | 56..63 w2+128      (w = floor(frac) on periodic axes: wrap shift)
+struct __align__(32) AtomRec {
+    double x, y, z;
+    unsigned long long meta;
+};
+__host__ __device__ inline int meta_orig(unsigned long long m) { return (int)(m & 0xffffffffull); }
+__host__ __device__ inline int meta_species(unsigned long long m) { return (int)((m >> 32) & 0xff); }
+__host__ __device__ inline int meta_w(unsigned long long m, int c) { return (int)((m >> (40 + 8 * c)) & 0xff) - 128; }
+
+// Neighbour pair record (8 bytes): cell-order index of j, bin-level image shift
+// (relative to WRAPPED positions) and species of j.
+struct __align__(8) PairRec {
+    int j;
+    signed char sb[3];
+    unsigned char sp;
+};
+
+struct Geom {
+    double cell[9];   // rows = lattice vectors (completed on non-periodic axes)
+    double inv[9];    // frac_c = sum_k pos_k * inv[k*3+c]
+    double flo[3];    // non-periodic axes: lower bound of frac coordinate
+    double fscale[3]; // bin = floor((frac - flo) * fscale)
+    int pbc[3];
+    int nb[3];        // bins per axis
+    int reach[3];     // stencil reach per axis
+    int ncell;
+    double rc;
+};
+
+// Everything the descriptor kernels need to know about the model (passed by value).
+struct DescParams {
+    int lmax, nb;           // nb = nmax+1
+    int L2;                 // (lmax+1)^2
+    int S;                  // species
+    int A;                  // S*nb
+    int ncomp;              // nb*L2  (components per species)
+    int csize;              // S*nb*L2
+    int D;                  // packed descriptor length = A(A+1)/2*(lmax+1)
+    int ldp;                // leading dimension of packed descriptor rows (doubles)
+    int normalize;
+    double rc;
+    double radii[kMaxSpecies];
+    int central_enabled[kMaxSpecies];
+};
+
+// host-side mirror of a grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need);  // returns sgpr_status
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace sgpr
+
+// ----------------------------------------------------------------------------------
+// the handle
+// ----------------------------------------------------------------------------------
+struct sgpr_context {
+    int device = 0;
+    int sm_count = 148;
+    // ---- model (host copies)
+    sgpr::DescParams dp;
+    double xi = 4.0;
+    int xi_int = 4;                          // xi when it is a small positive integer, else -1
+    int S = 0;
+    int species_Z[SGPR_MAX_SPECIES];
+    int z_to_species[128];                   // atomic number -> species index or -1
+    int M = 0;
+    int m_first[SGPR_MAX_SPECIES + 1];       // inducing LCEs grouped by central species (sorted order)
+    int ld_zt = 0;                           // leading dim of the transposed Z_hat blocks
+    int ldg = 0;                             // leading dim of G
+    size_t zt_off[SGPR_MAX_SPECIES];         // offset (doubles) of species s inside zhat_t
+    std::vector<int> ind_perm;               // sorted position -> caller's inducing index
+    std::vector<int> ind_sp;                 // species of sorted inducing p
+    std::vector<unsigned char> ind_lone;     // sorted inducing p has no neighbours
+    std::vector<double> mean_w, vscale, mu_host;
+    bool has_choli = false;
+    // ---- model (device)
+    sgpr::DevBuf zhat;        // [M, ldp]  packed normalised descriptors, rows grouped by species
+    sgpr::DevBuf zhat_t;      // [S][D, ld_zt]  per-species transposes
+    sgpr::DevBuf mu;          // [M] sorted order
+    sgpr::DevBuf lone_mu;     // [S] sum of mu over neighbour-less inducing LCEs of species s
+    sgpr::DevBuf mean_w_d;    // [S]
+    sgpr::DevBuf choli;       // [M, M], columns in sorted order
+    sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
+    sgpr::DevBuf ztab;        // [128] atomic number -> species
+    sgpr::DevBuf ind_perm_d;  // [M]
+    sgpr::DevBuf ind_sp_d, ind_lone_d;  // [M] caller's order (lone-lone kernel term)
+    sgpr::DevBuf sp_on;       // [S] species has usable inducing points and is enabled as a centre
+    sgpr::DevBuf errflag;     // [4] ints
+    // ---- per-call workspaces (grow-only)
+    sgpr::DevBuf cnt, cstart, rstart, keyrank, atoms, order, rowof, active_list, rowmap;
+    sgpr::DevBuf nl_cnt, nl_first, nl_pairs, scan_tmp;
+    sgpr::DevBuf phat, cbuf, pnorm, sflag, gmat, gvec, epart, wpart, fcell, misc;
+    sgpr::DevBuf stage_pos, stage_z, stage_out;  // device staging for the host API
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    // ---- state of the current / last call
+    int64_t last_N = 0;
+    int64_t n_active = 0;
+    bool active_all = true;
+    int row_first[SGPR_MAX_SPECIES + 1];     // first descriptor row of each central species
+    sgpr::Geom last_geom;
+    sgpr_stats stats;
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace sgpr {
+
+// ---- nl.cu ------------------------------------------------------------------------
+int build_geometry(sgpr_context* h, int64_t N, const double* pos_d, const double* cell_h, const int32_t* pbc_h,
+                   cudaStream_t st, Geom* g);
+int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const Geom& g, cudaStream_t st);
+int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs);
+int scan_exclusive_ll(sgpr_context* h, const long long* in, long long* out, int n, cudaStream_t st);
+
+// ---- descriptor.cu ----------------------------------------------------------------
+int upload_harm_coef();
+int descriptor_forward_env(sgpr_context* h, int M, const long long* env_first_d, const double* env_r_d,
+                           const unsigned char* env_sp_d, const int* row_of_d, double* phat_d, cudaStream_t st);
+int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st);
+int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st);
+int backward_grid(sgpr_context* h);
+int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, const int* src_row_d, double* full_d,
+                       cudaStream_t st);
+
+// ---- gemm.cu ----------------------------------------------------------------------
+int gemm_grid_size(sgpr_context* h);
+int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, cudaStream_t st);
+int gemm_back_projection(sgpr_context* h, cudaStream_t st);
+
+}  // namespace sgpr

@@ -1,0 +1,275 @@
+"""ctypes binding of libsgpr_b200.so (include/sgpr_b200.h) + a thin engine object.
+
+PyTorch is used only for device memory and streams.  No CPU fallback: a missing
+library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int8, c_int32, c_int64, c_uint8, c_void_p
+
+import numpy as np
+
+from .model import MAX_SPECIES, SgprModel
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsgpr_b200.so")
+
+
+class sgpr_model_desc(ctypes.Structure):
+    _fields_ = [
+        ("lmax", c_int32), ("nmax", c_int32), ("xi", c_double), ("rc", c_double), ("normalize", c_int32),
+        ("n_species", c_int32), ("species_Z", c_int32 * MAX_SPECIES), ("radii", c_double * MAX_SPECIES),
+        ("central_enabled", c_int32 * MAX_SPECIES), ("M", c_int32), ("ind_first_h", c_void_p), ("ind_r_h", c_void_p),
+        ("ind_b_h", c_void_p), ("ind_Z_h", c_void_p), ("mu_h", c_void_p), ("mean_w_h", c_void_p),
+        ("choli_h", c_void_p), ("vscale_h", c_void_p), ("device", c_int32),
+    ]
+
+
+class sgpr_stats(ctypes.Structure):
+    _fields_ = [
+        ("n_atoms", c_int64), ("n_active", c_int64), ("n_pairs", c_int64), ("d_packed", c_int32), ("d_full", c_int32),
+        ("kernel_launches", c_int64), ("gemm_flops", c_double), ("ms_nl", c_float), ("ms_desc", c_float),
+        ("ms_gemm", c_float), ("ms_force", c_float), ("ms_total", c_float),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)       -- every symbol include/sgpr_b200.h declares
+    "sgpr_create": (c_int32, [POINTER(sgpr_model_desc), POINTER(c_void_p)]),
+    "sgpr_destroy": (None, [c_void_p]),
+    "sgpr_last_error": (c_char_p, []),
+    "sgpr_abi_version": (c_int32, []),
+    "sgpr_set_weights": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_predict": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_predict_host": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_kernel_forward": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_kernel_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_neighbors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
+    "sgpr_descriptors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_inducing_descriptors": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "sgpr_get_stats": (c_int32, [c_void_p, POINTER(sgpr_stats)]),
+    "sgpr_enable_timing": (c_int32, [c_void_p, c_int32]),
+}
+
+
+def load_library(path=None):
+    """dlopen libsgpr_b200.so and declare every exported symbol.  Raises if missing."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(autoforce_b200 has no CPU fallback)")
+    import torch  # noqa: F401  (loads libcudart.so.12 into the process before our dlopen)
+
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sgpr_abi_version() != 1:
+        raise RuntimeError("libsgpr_b200.so: ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _check(lib, status):
+    if status != 0:
+        msg = lib.sgpr_last_error().decode(errors="replace")
+        raise RuntimeError(f"libsgpr_b200 error {status}: {msg}")
+
+
+def _ptr(a):
+    return c_void_p(a.ctypes.data)
+
+
+class SgprEngine:
+    """One handle on one CUDA device.  Host-side mirror of the C ABI."""
+
+    def __init__(self, model: SgprModel, species=None, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: autoforce_b200 has no CPU fallback")
+        self.lib = load_library()
+        self.model = model
+        self.device = int(device)
+        self.species = sorted(set(model.species()) | set(int(z) for z in (species or [])))
+        if len(self.species) > MAX_SPECIES:
+            raise ValueError(f"at most {MAX_SPECIES} species are supported, got {self.species}")
+        self._h = c_void_p()
+        d = sgpr_model_desc()
+        d.lmax, d.nmax, d.xi, d.rc = model.lmax, model.nmax, float(model.xi), float(model.rc)
+        d.normalize = 1 if model.normalize else 0
+        d.n_species = len(self.species)
+        mean_w = np.zeros(MAX_SPECIES)
+        vscale = np.full(MAX_SPECIES, np.inf)
+        for s, z in enumerate(self.species):
+            d.species_Z[s] = z
+            d.radii[s] = model.unit_of(z)
+            d.central_enabled[s] = 0 if z in model.a_not else 1
+            mean_w[s] = model.mean_w.get(z, 0.0)
+            vscale[s] = model.vscale.get(z, np.inf)
+        d.M = model.M
+        self._keep = (model.ind_first, model.ind_r, model.ind_b, model.ind_Z, model.mu, mean_w, vscale, model.choli)
+        d.ind_first_h, d.ind_r_h, d.ind_b_h = _ptr(model.ind_first), _ptr(model.ind_r), _ptr(model.ind_b)
+        d.ind_Z_h, d.mu_h, d.mean_w_h, d.vscale_h = _ptr(model.ind_Z), _ptr(model.mu), _ptr(mean_w), _ptr(vscale)
+        d.choli_h = _ptr(model.choli) if model.choli is not None else None
+        d.device = self.device
+        _check(self.lib, self.lib.sgpr_create(ctypes.byref(d), ctypes.byref(self._h)))
+        self.d_full = len(self.species) ** 2 * (model.nmax + 1) ** 2 * (model.lmax + 1)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.sgpr_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _geom(cell, pbc):
+        cell_h = np.ascontiguousarray(np.asarray(cell, dtype=np.float64).reshape(9))
+        pbc_h = np.ascontiguousarray(np.broadcast_to(np.asarray(pbc), (3,)).astype(np.int32))
+        return cell_h, pbc_h
+
+    def _dev(self, pos, numbers):
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        pos_t = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float64)).to(dev) if not torch.is_tensor(pos) else pos.to(dev, torch.float64).contiguous()
+        z_t = torch.as_tensor(np.ascontiguousarray(numbers, dtype=np.int32)).to(dev) if not torch.is_tensor(numbers) else numbers.to(dev, torch.int32).contiguous()
+        return pos_t.reshape(-1, 3), z_t.reshape(-1)
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ hot path
+    def predict(self, pos, numbers, cell, pbc, rank=0, world=1):
+        """Host numpy in, host numpy out (H2D/D2H inside): E, F[N,3], W[3,3], owned[N]."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        Z = np.ascontiguousarray(numbers, dtype=np.int32).reshape(-1)
+        N = len(Z)
+        cell_h, pbc_h = self._geom(cell, pbc)
+        E = np.zeros(1)
+        F = np.zeros((N, 3))
+        W = np.zeros(9)
+        owned = np.zeros(N, dtype=np.uint8)
+        _check(self.lib, self.lib.sgpr_predict_host(self._h, N, _ptr(pos), _ptr(Z), _ptr(cell_h), _ptr(pbc_h), rank, world,
+                                                    _ptr(E), _ptr(F), _ptr(W), None, _ptr(owned)))
+        return float(E[0]), F, W.reshape(3, 3), owned.astype(bool)
+
+    def predict_device(self, pos_t, z_t, cell, pbc, rank=0, world=1, out=None):
+        """Device tensors in, device tensors out, on torch's current stream."""
+        import torch
+
+        N = z_t.numel()
+        cell_h, pbc_h = self._geom(cell, pbc)
+        if out is None:
+            dev = pos_t.device
+            out = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty((N, 3), dtype=torch.float64, device=dev),
+                   torch.empty(9, dtype=torch.float64, device=dev))
+        E, F, W = out
+        _check(self.lib, self.lib.sgpr_predict(self._h, N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()), _ptr(cell_h),
+                                               _ptr(pbc_h), rank, world, self._stream(), c_void_p(E.data_ptr()),
+                                               c_void_p(F.data_ptr()), c_void_p(W.data_ptr()), None, None))
+        return E, F, W
+
+    def kernel_matrix(self, pos, numbers, cell, pbc):
+        import torch
+
+        pos_t, z_t = self._dev(pos, numbers)
+        N = z_t.numel()
+        cell_h, pbc_h = self._geom(cell, pbc)
+        K = torch.empty((N, self.model.M), dtype=torch.float64, device=pos_t.device)
+        _check(self.lib, self.lib.sgpr_kernel_forward(self._h, N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()),
+                                                      _ptr(cell_h), _ptr(pbc_h), self._stream(), c_void_p(K.data_ptr())))
+        return K
+
+    # ------------------------------------------------------------------ parity hooks
+    def neighbors(self, pos, numbers, cell, pbc):
+        """CSR (first[N+1], j[nnz], S[nnz,3]) in the caller's atom order."""
+        import torch
+
+        pos_t, z_t = self._dev(pos, numbers)
+        N = z_t.numel()
+        cell_h, pbc_h = self._geom(cell, pbc)
+        first = torch.empty(N + 1, dtype=torch.int64, device=pos_t.device)
+        nnz = c_int64(0)
+        cap = max(1, 128 * N)
+        for _ in range(2):
+            j = torch.empty(cap, dtype=torch.int32, device=pos_t.device)
+            S = torch.empty((cap, 3), dtype=torch.int8, device=pos_t.device)
+            _check(self.lib, self.lib.sgpr_neighbors(self._h, N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()), _ptr(cell_h),
+                                                     _ptr(pbc_h), self._stream(), c_void_p(first.data_ptr()),
+                                                     c_void_p(j.data_ptr()), c_void_p(S.data_ptr()), cap, ctypes.byref(nnz)))
+            if nnz.value <= cap:
+                break
+            cap = nnz.value
+        n = nnz.value
+        return first.cpu().numpy(), j[:n].cpu().numpy(), S[:n].cpu().numpy()
+
+    def descriptors(self, pos, numbers, cell, pbc):
+        """[N, S, S, nmax+1, nmax+1, lmax+1] normalised descriptors (reference layout)."""
+        import torch
+
+        pos_t, z_t = self._dev(pos, numbers)
+        N = z_t.numel()
+        cell_h, pbc_h = self._geom(cell, pbc)
+        P = torch.empty((N, self.d_full), dtype=torch.float64, device=pos_t.device)
+        _check(self.lib, self.lib.sgpr_descriptors(self._h, N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()), _ptr(cell_h),
+                                                   _ptr(pbc_h), self._stream(), c_void_p(P.data_ptr())))
+        S, n, L = len(self.species), self.model.nmax + 1, self.model.lmax + 1
+        return P.cpu().numpy().reshape(N, S, S, n, n, L)
+
+    def inducing_descriptors(self):
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        Zh = torch.empty((self.model.M, self.d_full), dtype=torch.float64, device=dev)
+        _check(self.lib, self.lib.sgpr_inducing_descriptors(self._h, self._stream(), c_void_p(Zh.data_ptr())))
+        S, n, L = len(self.species), self.model.nmax + 1, self.model.lmax + 1
+        return Zh.cpu().numpy().reshape(self.model.M, S, S, n, n, L)
+
+    # ------------------------------------------------------------------ misc
+    def set_weights(self, mu=None, mean_w=None, choli=None, vscale=None):
+        def arr(x, n):
+            if x is None:
+                return None, None
+            a = np.ascontiguousarray(x, dtype=np.float64)
+            assert a.size == n
+            return a, _ptr(a)
+
+        M = self.model.M
+        mw = None if mean_w is None else np.array([mean_w.get(z, 0.0) for z in self.species])
+        vs = None if vscale is None else np.array([vscale.get(z, np.inf) for z in self.species])
+        a1, p1 = arr(mu, M)
+        a2, p2 = arr(mw, len(self.species))
+        a3, p3 = arr(choli, M * M)
+        a4, p4 = arr(vs, len(self.species))
+        _check(self.lib, self.lib.sgpr_set_weights(self._h, p1, p2, p3, p4))
+
+    def enable_timing(self, on=True):
+        _check(self.lib, self.lib.sgpr_enable_timing(self._h, 1 if on else 0))
+
+    def stats(self):
+        s = sgpr_stats()
+        _check(self.lib, self.lib.sgpr_get_stats(self._h, ctypes.byref(s)))
+        return {k: getattr(s, k) for k, _ in sgpr_stats._fields_}

@@ -1,0 +1,179 @@
+/* sgpr_b200.h -- C ABI of the B200-native SGPR prediction path (libsgpr_b200.so).
+ *
+ * Drop-in boundary for AutoForce's prediction hot path.  The
+ * reference is pure Python (no FFI of its own); each entry point below names the
+ * reference interface whose work it replaces (paths relative to the reference repo,
+ * theforce v2021.09).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is suffixed _h (host memory) or _d (device
+ *     memory on the handle's CUDA device);
+ *   - every function returns 0 on success, a negative sgpr_status on failure; the
+ *     message of the last failure on the calling thread is sgpr_last_error();
+ *   - never throws, never exits; one handle per CUDA device, not re-entrant;
+ *   - all device work of a call is enqueued on the caller-supplied `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).  Calls that
+ *     return host results synchronise that stream before returning;
+ *   - float64 everywhere (the reference sets torch's default dtype to float64,
+ *     theforce/__init__.py:13); atomic numbers are int32, indices int32/int64 as noted.
+ */
+#ifndef SGPR_B200_H
+#define SGPR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPR_ABI_VERSION 1
+#define SGPR_MAX_SPECIES 8
+
+typedef struct sgpr_context* sgpr_handle;
+
+typedef enum {
+    SGPR_OK = 0,
+    SGPR_ERR_INVALID = -1,      /* bad argument / unsupported hyper-parameter        */
+    SGPR_ERR_CUDA = -2,         /* CUDA runtime error (message has the details)      */
+    SGPR_ERR_SPECIES = -3,      /* atomic number not in the handle's species table   */
+    SGPR_ERR_GEOMETRY = -4,     /* singular cell / atom too far outside the cell     */
+    SGPR_ERR_NOMEM = -5,
+    SGPR_ERR_NO_DEVICE = -6     /* no CUDA device: there is NO CPU fallback          */
+} sgpr_status;
+
+/* Frozen model = kernel hyper-parameters + inducing set + weights.
+ * Replaces what ActiveCalculator reads from PosteriorPotential on the hot path
+ * (regression/gppotential.py:453-478, 548-649):
+ *   model.gp.kern.kernels[0].{exponent, cutoff, descriptor.{nmax, ylm.lmax, radii|unit,
+ *   normalize}, _a},  model.X (LocalsData of Local: number, _r, _b),  model.mu,
+ *   model.choli,  model.mean.weights/_weights,  model._vscale.
+ * SeSoapKernel (similarity/sesoap.py:10-24, descriptor/sesoap.py:102-260) and
+ * UniversalSoapKernel (similarity/universal.py:52-122, descriptor/soap.py:715-851) differ
+ * only in the per-species length unit:  radii[s] = radii(Z_s)  resp.  = unit for all s.
+ * All pointers are HOST pointers; the library copies what it needs. */
+typedef struct {
+    int32_t lmax;                 /* ylm.lmax,  <= 8                                  */
+    int32_t nmax;                 /* radial order, nmax + 1 <= 12                     */
+    double  xi;                   /* kernel exponent (universal.py:67,121)            */
+    double  rc;                   /* cutoff of PolyCut(rc, n=2) (cutoff.py:33-44)     */
+    int32_t normalize;            /* descriptor.normalize (sesoap.py:249-251)         */
+    int32_t n_species;            /* size of the dense species table, <= 8            */
+    int32_t species_Z[SGPR_MAX_SPECIES];     /* sorted atomic numbers; must cover every
+                                     species of the inducing set AND of the structures */
+    double  radii[SGPR_MAX_SPECIES];         /* length unit of neighbour species s     */
+    int32_t central_enabled[SGPR_MAX_SPECIES]; /* 0 = species excluded as a centre
+                                     (`a`/`a_not`, universal.py:44-49,85,101)          */
+    int32_t M;                    /* number of inducing LCEs                          */
+    const int64_t* ind_first_h;   /* [M+1] CSR offsets into ind_r / ind_b             */
+    const double*  ind_r_h;       /* [nnz,3]  Local._r  (descriptor/atoms.py:36-52)   */
+    const int32_t* ind_b_h;       /* [nnz]    Local._b  (atomic numbers)              */
+    const int32_t* ind_Z_h;       /* [M]      Local.number                            */
+    const double*  mu_h;          /* [M]      model.mu                                */
+    const double*  mean_w_h;      /* [n_species] weights[Z]+_weights[Z]; 0 where the
+                                     mean has no entry (gppotential.py:219-227)        */
+    const double*  choli_h;       /* [M,M] row-major model.choli, or NULL             */
+    const double*  vscale_h;      /* [n_species] model._vscale[Z] (inf where unseen,
+                                     calculator/active.py:797-803), or NULL            */
+    int32_t device;               /* CUDA device ordinal                              */
+} sgpr_model_desc;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+
+/* Build a handle: uploads the model and evaluates the inducing descriptors Z_hat on the
+ * device with the same kernels used for atoms.  Replaces the per-LCE cache
+ * `kern.precalculate(loc)` -> loc.kern_0_value (similarity/universal.py:100-107). */
+int sgpr_create(const sgpr_model_desc* desc, sgpr_handle* out);
+void sgpr_destroy(sgpr_handle h);
+const char* sgpr_last_error(void);
+int sgpr_abi_version(void);
+
+/* New weights after the reference's trainer refitted the model (make_munu,
+ * regression/gppotential.py:548-601).  Any pointer may be NULL (= keep). */
+int sgpr_set_weights(sgpr_handle h, const double* mu_h, const double* mean_w_h,
+                     const double* choli_h, const double* vscale_h);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+
+/* One ActiveCalculator.calculate() in prediction mode (calculator/active.py:425-611):
+ * neighbour list (descriptor/atoms.py:348-363,402), descriptors (sesoap.py:161-260),
+ * kernel vs the inducing set (similarity.py:17-43, universal.py:109-122),
+ * E = sum(K mu) + mean (active.py:548-570), F = -dE/dxyz and the pair virial
+ * (active.py:587-611).  Device-resident inputs and outputs.
+ *   pos_d  [N,3]   positions (need not be wrapped into the cell)
+ *   Z_d    [N]     atomic numbers
+ *   cell_h [9]     row-major lattice vectors (zero rows allowed on non-periodic axes)
+ *   pbc_h  [3]
+ *   rank, world    atom sharding: this call evaluates the local energies of its share
+ *                  of the atoms (contiguous range in the internal cell order) and the
+ *                  forces on exactly those atoms; (0,1) = everything.
+ *   E_d    [1]     sum of owned local energies + (rank 0 only) the mean
+ *   F_d    [N,3]   forces on owned atoms, 0 elsewhere
+ *   W_d    [9]     un-normalised pair virial sum_i r_ij (x) dE_i/dr_ij of owned
+ *                  environments, index [a*3+b] = r_a g_b; stress = (W/V).flat[[0,4,8,5,2,1]]
+ *   beta_d [N]     covloss (active.py:781-804) of owned atoms, or NULL to skip
+ *   owned_d[N]     1 where this rank owns the atom (uint8), or NULL */
+int sgpr_predict(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                 const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world,
+                 void* stream, double* E_d, double* F_d, double* W_d, double* beta_d,
+                 uint8_t* owned_d);
+
+/* Same with HOST buffers: what the calculator calls once per MD step.  Stages through
+ * pinned memory; H2D of positions and D2H of E/F/W(/beta) are inside the call. */
+int sgpr_predict_host(sgpr_handle h, int64_t N, const double* pos_h, const int32_t* Z_h,
+                      const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world,
+                      double* E_h, double* F_h, double* W_h, double* beta_h, uint8_t* owned_h);
+
+/* Kernel matrix cov = model.gp.kern(atoms, model.X)  (calculator/active.py:464,
+ * regression/gppotential.py:47-50,63-64; similarity/similarity.py:17-31).
+ *   K_d [N,M] row-major, atoms and inducing LCEs in the caller's order. */
+int sgpr_kernel_forward(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                        const double* cell_h, const int32_t* pbc_h, void* stream, double* K_d);
+
+/* Vector-Jacobian product of the last sgpr_kernel_forward: given gK = dL/dcov [N,M]
+ * returns dL/dxyz [N,3] and dL/dcell [9] -- what torch.autograd.grad(E, xyz / lll) does
+ * in the reference (calculator/active.py:587-599, gppotential.py:905-911). */
+int sgpr_kernel_backward(sgpr_handle h, const double* gK_d, void* stream, double* gpos_d,
+                         double* gcell_h);
+
+/* ---- parity hooks (used by tests; same kernels as the hot path) --------------------- */
+
+/* Neighbour list as ASE's NeighborList(N*[rc/2], skin=0, self_interaction=False,
+ * bothways=True) returns it through get_neighbors(a) (descriptor/atoms.py:348-366):
+ * CSR over atoms in the caller's order, offsets relative to the given positions.
+ *   first_d [N+1] int64;  j_d [capacity] int32;  S_d [capacity,3] int8
+ *   *nnz_h receives the number of pairs; if it exceeds `capacity` nothing is written to
+ *   j_d/S_d and the call still returns SGPR_OK (call again with a larger buffer). */
+int sgpr_neighbors(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                   const double* cell_h, const int32_t* pbc_h, void* stream,
+                   int64_t* first_d, int32_t* j_d, int8_t* S_d, int64_t capacity, int64_t* nnz_h);
+
+/* Normalised descriptors of all atoms in the reference's dense block layout
+ * p[s1,s2,n1,n2,l] (descriptor/sesoap.py:195-203,248-258; block [s1,s2] <-> sparse
+ * index (Z_s2, Z_s1)):  P_d [N, S*S*(nmax+1)^2*(lmax+1)]. */
+int sgpr_descriptors(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                     const double* cell_h, const int32_t* pbc_h, void* stream, double* P_d);
+
+/* Same layout for the inducing LCEs (loc.kern_0_value): Zhat_d [M, S*S*(nmax+1)^2*(lmax+1)]. */
+int sgpr_inducing_descriptors(sgpr_handle h, void* stream, double* Zhat_d);
+
+/* ---- introspection ------------------------------------------------------------------ */
+
+typedef struct {
+    int64_t n_atoms;          /* atoms of the last call                                */
+    int64_t n_active;         /* environments evaluated (owned + halo)                 */
+    int64_t n_pairs;          /* neighbour pairs of the evaluated environments         */
+    int32_t d_packed;         /* packed descriptor length used by the GEMMs            */
+    int32_t d_full;           /* S*S*(nmax+1)^2*(lmax+1)                               */
+    int64_t kernel_launches;  /* CUDA kernels launched by the last hot-path call        */
+    double  gemm_flops;       /* flops executed by the two kernel GEMMs, last call     */
+    float   ms_nl, ms_desc, ms_gemm, ms_force, ms_total; /* device time per stage of the
+                                 last call (CUDA events), valid if timing was enabled  */
+} sgpr_stats;
+
+int sgpr_get_stats(sgpr_handle h, sgpr_stats* out);
+int sgpr_enable_timing(sgpr_handle h, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGPR_B200_H */

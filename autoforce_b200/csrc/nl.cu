@@ -339,7 +339,7 @@ int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_
                                                  h->atoms.as<AtomRec>(), h->rowof.as<int>(),
                                                  h->rowof.as<int>() + (N + 1));
     }
-    h->stats.kernel_launches += 7;
+    h->stats.kernel_launches += 9;  // 5 own kernels + 2 cub scans (2 kernels each)
     SGPR_CUDA(cudaGetLastError());
     return SGPR_OK;
 }
@@ -500,7 +500,7 @@ int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, i
     SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
     neighbor_kernel<true><<<nblk, T, 0, st>>>(na, active, atoms, abin, h->cstart.as<int>(), g, S, h->nl_cnt.as<int>(),
                                               first, h->nl_pairs.as<PairRec>());
-    h->stats.kernel_launches += 4;
+    h->stats.kernel_launches += 5;  // count, row totals, cub scan (2), fill
     SGPR_CUDA(cudaGetLastError());
     *n_pairs = total;
     return SGPR_OK;

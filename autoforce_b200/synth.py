@@ -34,20 +34,26 @@ def cut_environments(pos, cell, pbc, numbers, rc, indices, first, J, S):
     return envs
 
 
-def synth_model(Zs, M, seed, lmax=3, nmax=3, xi=4, rc=6.0, kind="sesoap", src_rep=5, mu_scale=0.1, with_choli=False):
+def synth_model(Zs, M, seed, lmax=3, nmax=3, xi=4, rc=6.0, kind="sesoap", src_rep=5, mu_scale=0.1, with_choli=False,
+                neighbors_fn=None):
     """Frozen model: M inducing LCEs drawn per-species-balanced from fcc(src_rep, Zs, 0.15, seed+100),
-    mu ~ N(0,1)*mu_scale, mean weight -3.0 per species, choli = 0.5 I, vscale = 1."""
-    from .engine import SgprEngine
-
+    mu ~ N(0,1)*mu_scale, mean weight -3.0 per species, choli = 0.5 I, vscale = 1.
+    ``neighbors_fn(pos, cell, pbc, rc) -> (first, j, S)`` overrides the GPU neighbour hook
+    (the CPU arm of bench.py passes the oracle's, so that it needs no GPU)."""
     rng = np.random.default_rng(seed)
     pos, cell, numbers = fcc(src_rep, Zs, 0.15, seed + 100)
     base = dict(lmax=lmax, nmax=nmax, xi=float(xi), rc=float(rc), kind=kind, radii={1: 0.5} if kind == "sesoap" else {},
                 default_radius=1.0 if kind == "sesoap" else rc / 6)
-    probe = SgprEngine(SgprModel.from_envs([], **base), species=sorted(set(int(z) for z in Zs)))
-    try:
-        first, J, S = probe.neighbors(pos, numbers, cell, True)
-    finally:
-        probe.close()
+    if neighbors_fn is not None:
+        first, J, S = neighbors_fn(pos, cell, True, rc)
+    else:
+        from .engine import SgprEngine
+
+        probe = SgprEngine(SgprModel.from_envs([], **base), species=sorted(set(int(z) for z in Zs)))
+        try:
+            first, J, S = probe.neighbors(pos, numbers, cell, True)
+        finally:
+            probe.close()
     sel = []
     Zs = sorted(set(int(z) for z in Zs))
     for k, z in enumerate(Zs):

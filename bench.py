@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/sec of SGPR E+F+stress prediction (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+A step = one full evaluation (neighbour list -> descriptors -> kernel GEMMs -> energy,
+forces, virial) of one synthetic structure.  Workload (default c3, the configuration the
+metric's target is quoted on): 4-species Li/P/S/O-like 97,556-atom fcc-derived solid,
+random-init frozen model with M = 2000 inducing LCEs, SeSoap lmax=3 nmax=3 rc=6.
+Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "atom-steps/sec (E+F+stress) SGPR MD prediction"
+UNIT = "atom-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="atoms in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variants", type=int, default=4, help="pre-generated perturbed position sets cycled over the steps")
+    return ap.parse_args()
+
+
+def workload_inputs(name, variants):
+    from autoforce_b200 import synth
+
+    w = synth.WORKLOADS[name]
+    pos, cell, numbers = synth.fcc(w["rep"], w["Zs"], 0.1, 0)
+    rng = np.random.default_rng(123)
+    # every step sees perturbed positions, N(0, 0.03 A); generated before timing
+    pos_variants = [pos + rng.normal(0, 0.03, pos.shape) for _ in range(max(1, variants))]
+    return w, pos_variants, cell, numbers
+
+
+def config_of(name, w, N, M, world):
+    return {
+        "workload": f"{name}: fcc-derived {N}-atom {'/'.join(str(z) for z in w['Zs'])} solid, frozen random-init SGPR model "
+                    f"M={M}, SeSoap lmax={w['lmax']} nmax={w['nmax']} rc={w['rc']}, xi=4",
+        "atoms": N, "inducing": M, "species": len(w["Zs"]),
+        "parallelism": f"atoms sharded over {world} GPU(s); positions replicated; all-reduce of E + 3x3 virial only",
+        "cache": "working set (pair list + descriptor/gradient matrices, >500 MB at c3) exceeds the 126 MB L2; positions change every step",
+    }
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dgemm_peak_tflops():
+    """FP64 GEMM peak of this GPU measured in-run (cuBLAS DGEMM 8192^3, best of 5):
+    MEASURED_PEAKS.json only lists bf16, and the kernel GEMMs run on the FP64 pipe."""
+    import torch
+
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def cpu_arm(args, world, rank):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the
+    Python reference itself cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    from autoforce_b200 import synth
+    from oracle.cpu_bench import CpuBench
+
+    w, pos_variants, cell, numbers = workload_inputs(args.workload, args.variants)
+    from oracle.sgpr_oracle import neighbor_list
+
+    model = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], neighbors_fn=neighbor_list)
+    procs = min(os.cpu_count() or 1, 64)
+    sample = args.cpu_sample or 32 * procs
+    cb = CpuBench(model, pos_variants, cell, numbers, sample, procs)
+    value, sec = cb.run(args.steps, args.warmup)
+    cb.close()
+    N = len(numbers)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_of(args.workload, w, N, model.M, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{cb.sample} of {N} atoms per step (full neighbour environments, all {model.M} inducing LCEs), "
+                                   f"{procs} worker processes; oracle/sgpr_oracle.py (vectorised numpy restatement of the reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        cpu_arm(args, world, rank)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import autoforce_b200 as ab
+    from autoforce_b200 import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, pos_variants, cell, numbers = workload_inputs(args.workload, args.variants)
+    N = len(numbers)
+    model = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"])
+    eng = ab.SgprEngine(model, species=w["Zs"], device=local_rank)
+    pbc = True
+    pos_d = [torch.as_tensor(p, device=dev) for p in pos_variants]
+    z_d = torch.as_tensor(numbers.astype(np.int32), device=dev)
+    out = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty((N, 3), dtype=torch.float64, device=dev),
+           torch.empty(9, dtype=torch.float64, device=dev))
+    ew = torch.zeros(10, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(it):
+        E, F, W = eng.predict_device(pos_d[it % len(pos_d)], z_d, cell, pbc, rank=rank, world=world, out=out)
+        if world > 1:  # the only collective of the path: 10 doubles
+            ew[0:1].copy_(E)
+            ew[1:].copy_(W)
+            dist.all_reduce(ew)
+
+    def step_host(it):
+        E, F, W, owned = eng.predict(pos_variants[it % len(pos_variants)], numbers, cell, pbc, rank=rank, world=world)
+        if world > 1:
+            t = torch.tensor([E] + list(W.reshape(-1)), dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            E = float(t[0].item())
+        return E
+
+    def timed(fn, steps, warmup):
+        for it in range(warmup):
+            fn(it)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for it in range(steps):
+            fn(it)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item())
+
+    # ---- device-resident leg (value) with per-stage CUDA-event timing inside the library
+    eng.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "launches": 0}
+
+    def step_device_acc(it):
+        step_device(it)
+        s = eng.stats()
+        if it >= 0:
+            for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total"):
+                stage[k] += s[k]
+            stage["gemm_flops"] += s["gemm_flops"]
+            stage["launches"] += s["kernel_launches"]
+            stage["n_active"] = s["n_active"]
+            stage["n_pairs"] = s["n_pairs"]
+
+    for it in range(args.warmup):
+        step_device(it)
+    for k in list(stage):
+        stage[k] = 0 if k == "launches" else 0.0
+    sampler.start()
+    ms_dev, wall_dev = timed(step_device_acc, args.steps, 0)
+    clocks = sampler.stop()
+    eng.enable_timing(False)
+    # ---- end-to-end leg: host buffers through the public host API (H2D + D2H inside)
+    ms_e2e, wall_e2e = timed(step_host, args.steps, args.warmup)
+
+    if rank == 0:
+        K = args.steps
+        value = N * K / (ms_dev * 1e-3)
+        e2e = N * K / (wall_e2e * 1e-3)
+        gemm_s = stage["ms_gemm"] * 1e-3
+        achieved = stage["gemm_flops"] / gemm_s / 1e12 if gemm_s > 0 else None
+        try:
+            peak = dgemm_peak_tflops()
+            peak_src = "measured in-run: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has no FP64 entry)"
+        except Exception as ex:  # pragma: no cover
+            peak, peak_src = 40.0, f"nominal B200 FP64 (in-run DGEMM failed: {ex})"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get("gemm_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_of(args.workload, w, N, model.M, world),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": wall_e2e / K,
+                    "h2d_bytes_per_step": int(N * 24 + N * 4), "d2h_bytes_per_step": int(N * 24 + 16 * 8 + N)},
+            "gpu_launches": int(stage["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA kernel-matrix GEMM + back projection)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "flops_per_step": stage["gemm_flops"] / K, "gemm_ms_per_step": stage["ms_gemm"] / K},
+            "stages_ms_per_step": {k[3:]: stage[k] / K for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total")},
+            "pairs": int(stage.get("n_pairs", 0)), "active_envs_rank0": int(stage.get("n_active", 0)),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle.cpu_bench import CpuBench
+
+                procs = min(os.cpu_count() or 1, 64)
+                sample = args.cpu_sample or 16 * procs
+                cb = CpuBench(model, pos_variants, cell, numbers, sample, procs)
+                v, sec = cb.run(2, 1)
+                cb.close()
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                                        "sample": f"{cb.sample} of {N} atoms x 2 steps (full environments, all {model.M} inducing LCEs), "
+                                                  f"{procs} processes, oracle/sgpr_oracle.py"}
+            except Exception as ex:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -108,7 +108,7 @@ def face_distances(cell):
     return 1.0 / np.linalg.norm(inv, axis=0)
 
 
-def neighbor_list(pos, cell, pbc, rc):
+def neighbor_list(pos, cell, pbc, rc, centers=None):
     """All (i, j, S) with |pos[j] - pos[i] + S@cell| < rc  (strict), both ways,
     (i==j, S==0) excluded, images of the same atom (and of i itself) kept.
 
@@ -119,7 +119,8 @@ def neighbor_list(pos, cell, pbc, rc):
 
     Returns CSR (first[N+1] int64, j[nnz] int64, S[nnz,3] int64) with each row
     sorted lexicographically by (j, S0, S1, S2) (ASE's order is implementation
-    defined; comparisons are done on sorted rows).
+    defined; comparisons are done on sorted rows).  ``centers`` restricts the rows
+    that are filled to a subset of atoms (the other rows stay empty).
     """
     from scipy.spatial import cKDTree
 
@@ -139,7 +140,8 @@ def neighbor_list(pos, cell, pbc, rc):
             rng.append(range(-k, k + 1))
         else:
             rng.append(range(0, 1))
-    tree = cKDTree(pos)
+    cidx = np.arange(n) if centers is None else np.asarray(centers, dtype=np.int64)
+    tree = cKDTree(pos[cidx])
     I, J, S = [], [], []
     margin = rc / h
     for s in itertools.product(*rng):
@@ -157,6 +159,7 @@ def neighbor_list(pos, cell, pbc, rc):
         ii = np.concatenate([np.asarray(l, np.int64) for l in lists] or [np.zeros(0, np.int64)])
         if len(ii) == 0:
             continue
+        ii = cidx[ii]
         dv = pos[jj] - pos[ii] + (s.astype(float)[:, None] * cell).sum(axis=0)
         d = np.sqrt((dv * dv).sum(axis=1))
         m = d < rc
@@ -490,7 +493,7 @@ def kernel_from_descriptors(model, P, Zc, lone_c, Zh, lone_m):
 # --------------------------------------------------------------------------
 # a7-a9: energy / forces / stress / covloss  (calculator/active.py:548-611,781-804)
 # --------------------------------------------------------------------------
-def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk=256, atoms=None):
+def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk=256, atoms=None, nl=None, Zh=None):
     """Full restatement of ``ActiveCalculator.calculate`` in prediction mode.
 
     returns dict(energy, forces[N,3], stress[6] (xx,yy,zz,yz,xz,xy), virial[3,3],
@@ -504,8 +507,8 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
     cell = np.asarray(cell, dtype=float).reshape(3, 3)
     N = len(pos)
     species = model.species_table(extra=numbers)
-    first, J, S = neighbor_list(pos, cell, pbc, model.rc)
-    Zh, lone_m = inducing_descriptors(model, species, chunk)
+    first, J, S = neighbor_list(pos, cell, pbc, model.rc, centers=atoms) if nl is None else nl
+    Zh, lone_m = inducing_descriptors(model, species, chunk) if Zh is None else Zh
     idx_all = np.arange(N) if atoms is None else np.asarray(atoms, dtype=np.int64)
     F = np.zeros((N, 3))
     W = np.zeros((3, 3))

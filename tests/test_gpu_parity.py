@@ -1,0 +1,161 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against
+(a) the golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+(b) the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): neighbour lists bit-exact; energies within 1e-6 eV/atom,
+forces within 1e-5 eV/A, stress within 1e-6 eV/A^3 of the reference's float64 path.
+Everything on this path computes in float64, so the asserts below are far tighter.
+"""
+import numpy as np
+import pytest
+
+from golden_util import golden_cases, golden_radii, load_golden, oracle_model
+from oracle import sgpr_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL_E_PER_ATOM = 1e-9   # north_star: 1e-6 eV/atom
+TOL_F = 1e-8            # north_star: 1e-5 eV/A
+TOL_S = 1e-9            # north_star: 1e-6 eV/A^3
+
+
+def model_from_golden(g, big=False):
+    import autoforce_b200 as ab
+
+    k = g["meta"]["kernel"]
+    radii, default = golden_radii(g["meta"])
+    return ab.SgprModel(
+        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind=k["kind"], radii=radii, default_radius=default,
+        a_not=tuple(k.get("a_not", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
+        mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
+        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()})
+
+
+def sorted_rows(first, J, S):
+    I = np.repeat(np.arange(len(first) - 1), np.diff(first))
+    order = np.lexsort((S[:, 2], S[:, 1], S[:, 0], J, I))
+    return I[order], J[order].astype(np.int64), S[order].astype(np.int64)
+
+
+def stress_of(W, cell):
+    vol = abs(np.linalg.det(np.asarray(cell, dtype=float).reshape(3, 3))) or -2.0
+    return (W / vol).reshape(-1)[[0, 4, 8, 5, 2, 1]]
+
+
+@pytest.fixture(params=golden_cases())
+def case(request):
+    import autoforce_b200 as ab
+
+    g = load_golden(request.param)
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    yield g, eng
+    eng.close()
+
+
+def test_neighbor_list_bit_exact(case):
+    g, eng = case
+    first, J, S = eng.neighbors(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    assert len(J) == len(g["nl_j"])
+    a, b = sorted_rows(first, J, S), sorted_rows(g["nl_first"], g["nl_j"], g["nl_S"])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_descriptors_match_reference_cache(case):
+    g, eng = case
+    species = np.array(g["meta"]["species"])
+    Zh = eng.inducing_descriptors()
+    keep = ~np.isin(g["ind_Z"], np.array(g["meta"]["kernel"].get("a_not", []), dtype=np.int64))
+    ref = g["ind_desc"].reshape(Zh.shape)
+    assert np.abs(Zh[keep] - ref[keep]).max() < 1e-13
+    Zo, _ = o.inducing_descriptors(oracle_model(g), species)
+    assert np.abs(Zh - Zo).max() < 1e-13
+    P = eng.descriptors(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    excluded = set(g["meta"]["kernel"].get("a_not", []))
+    for key in [k for k in g if k.startswith("desc_")]:
+        a = int(key.split("_")[1])
+        if int(g["numbers"][a]) in excluded:
+            continue
+        assert np.abs(P[a] - g[key].reshape(P[a].shape)).max() < 1e-13
+
+
+def test_kernel_matrix(case):
+    g, eng = case
+    K = eng.kernel_matrix(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"]).cpu().numpy()
+    assert K.shape == g["K"].shape
+    assert np.abs(K - g["K"]).max() < 1e-12
+
+
+def test_energy_forces_stress(case):
+    g, eng = case
+    N = len(g["numbers"])
+    E, F, W, owned = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    assert owned.all()
+    assert abs(E - float(g["energy"])) / N < TOL_E_PER_ATOM
+    assert np.abs(F - g["forces"]).max() < TOL_F
+    assert np.abs(stress_of(W, g["cell"]) - g["stress"]).max() < TOL_S
+    # same through the oracle (independent derivative formulation)
+    ref = o.predict(oracle_model(g), g["pos"], g["cell"], g["meta"]["pbc"], g["numbers"])
+    assert abs(E - ref["energy"]) / N < TOL_E_PER_ATOM
+    assert np.abs(F - ref["forces"]).max() < TOL_F
+    assert np.abs(W - ref["virial"]).max() < 1e-8
+    # weights x1000 through sgpr_set_weights: same K, amplified E/F/stress (relative bars)
+    eng.set_weights(mu=g["mu_big"])
+    E, F, W, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    assert abs(E - float(g["energy_big"])) / N < 1e-9 * max(1.0, abs(float(g["energy_big"])) / N)
+    assert np.abs(F - g["forces_big"]).max() < 1e-10 * max(1.0, np.abs(g["forces_big"]).max())
+    assert np.abs(stress_of(W, g["cell"]) - g["stress_big"]).max() < 1e-10 * max(1.0, np.abs(g["stress_big"]).max())
+
+
+def test_device_pointer_api_matches_host_api(case):
+    import torch
+
+    g, eng = case
+    E0, F0, W0, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    pos_t = torch.as_tensor(g["pos"], device="cuda")
+    z_t = torch.as_tensor(g["numbers"].astype(np.int32), device="cuda")
+    E, F, W = eng.predict_device(pos_t, z_t, g["cell"], g["meta"]["pbc"])
+    torch.cuda.synchronize()
+    assert float(E.cpu()[0]) == E0  # deterministic reductions: bit-identical energy
+    assert np.abs(F.cpu().numpy() - F0).max() < 1e-12
+    assert np.array_equal(W.cpu().numpy().reshape(3, 3), W0)
+
+
+def test_calculator_results_mirror_reference(case):
+    import autoforce_b200 as ab
+
+    g, eng = case
+
+    class A:  # anything with positions / cell / pbc / numbers
+        positions, cell, pbc, numbers = g["pos"], g["cell"], g["meta"]["pbc"], g["numbers"]
+
+    calc = ab.B200Calculator(model_from_golden(g))
+    res = calc.calculate(A())
+    assert res["energy"].shape == () and res["energy"].dtype == np.float64      # active.py:572
+    assert res["stress"].shape == (6,)                                             # active.py:574
+    assert abs(float(res["energy"]) - float(g["energy"])) / len(g["numbers"]) < TOL_E_PER_ATOM
+    assert np.abs(res["forces"] - g["forces"]).max() < TOL_F
+    assert np.abs(res["stress"] - g["stress"]).max() < TOL_S
+    assert float(res["free_energy"]) == float(res["energy"])                      # active.py:527
+
+
+def test_unknown_species_is_an_error():
+    import autoforce_b200 as ab
+
+    g = load_golden("cu108_sesoap")
+    eng = ab.SgprEngine(model_from_golden(g))
+    numbers = g["numbers"].copy()
+    numbers[3] = 47
+    with pytest.raises(RuntimeError, match="species"):
+        eng.predict(g["pos"], numbers, g["cell"], True)
+    eng.close()
+
+
+def test_empty_structure():
+    import autoforce_b200 as ab
+
+    g = load_golden("cu108_sesoap")
+    eng = ab.SgprEngine(model_from_golden(g))
+    E, F, W, owned = eng.predict(np.zeros((0, 3)), np.zeros(0, np.int32), g["cell"], True)
+    assert E == 0.0 and F.shape == (0, 3) and np.all(W == 0)
+    eng.close()

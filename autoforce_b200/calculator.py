@@ -81,6 +81,25 @@ class B200Calculator(_AseCalculator):
             self._engine = SgprEngine(self.model, species=sorted(need), device=dev)
         return self._engine
 
+    def _reduce(self, dist, E, W, F, device_index):
+        """The path's only exchange step: all-reduce of 10 doubles (energy + 3x3 virial),
+        replacing the reference's all_reduce(energy), all_reduce(forces [N,3]) and
+        all_reduce(cellgrad) (calculator/active.py:562,601-602).  Forces are owner-computed;
+        ``gather_forces=True`` additionally sums them so that every rank sees all forces."""
+        import torch
+
+        backend = dist.get_backend(self.process_group)
+        dev = torch.device("cuda", device_index) if backend == "nccl" else torch.device("cpu")
+        ew = torch.tensor([E] + list(np.asarray(W).reshape(-1)), dtype=torch.float64, device=dev)
+        dist.all_reduce(ew, group=self.process_group)
+        ew = ew.cpu().numpy()
+        E, W = float(ew[0]), ew[1:].reshape(3, 3)
+        if self.gather_forces:
+            ft = torch.as_tensor(np.ascontiguousarray(F), device=dev)
+            dist.all_reduce(ft, group=self.process_group)
+            F = ft.cpu().numpy()
+        return E, W, F
+
     # ------------------------------------------------------------------ the call
     def calculate(self, atoms=None, properties=("energy",), system_changes=_all_changes):
         if atoms is not None:
@@ -94,17 +113,7 @@ class B200Calculator(_AseCalculator):
         dist, rank, world = self._dist()
         E, F, W, owned = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world)
         if world > 1:
-            import torch
-
-            dev = torch.device("cuda", eng.device)
-            ew = torch.tensor([E] + list(W.reshape(-1)), dtype=torch.float64, device=dev)
-            dist.all_reduce(ew, group=self.process_group)  # 10 doubles: energy + 3x3 virial
-            ew = ew.cpu().numpy()
-            E, W = float(ew[0]), ew[1:].reshape(3, 3)
-            if self.gather_forces:  # reference-conformant: every rank sees all forces (active.py:601)
-                ft = torch.as_tensor(F, device=dev)
-                dist.all_reduce(ft, group=self.process_group)
-                F = ft.cpu().numpy()
+            E, W, F = self._reduce(dist, E, W, F, getattr(eng, "device", 0))
         vol = abs(np.linalg.det(cell))
         if vol == 0.0:
             vol = -2.0  # calculator/active.py:606-609

@@ -444,7 +444,7 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->rstart, &h->keyrank, &h->atoms, &h->order, &h->rowof, &h->active_list, &h->nl_cnt,
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
-                      &h->rowmap};
+                      &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -468,7 +468,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
 // pipeline
 // =====================================================================================
 static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
-                       const int32_t* pbc_h, cudaStream_t st, Geom* g) {
+                       const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1) {
     // geometry -> cell sort -> neighbour list -> descriptors (rows in species-major order)
     if (N < 0 || N > 0x7fffff00ll) {
         set_error("bad atom count");
@@ -482,21 +482,16 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     h->last_geom = *g;
     if (h->timing) cudaEventRecord(h->ev[0], st);
     SGPR_TRY(cell_sort(h, N, pos_d, Z_d, *g, st));
-    h->active_all = true;
-    h->n_active = N;
-    // species row ranges (first row of each species block) come back with the pair count
-    int rf[SGPR_MAX_SPECIES + 1];
-    const int nkeys = g->ncell * h->S;
-    const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
-    SGPR_CUDA(cudaMemcpy2DAsync(rf, sizeof(int), rstartT, sizeof(int) * g->ncell, sizeof(int), h->S + 1,
-                                cudaMemcpyDeviceToHost, st));
+    // neighbour list (+ halo when sharded); species row ranges come back with the pair count
     int64_t n_pairs = 0;
-    SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs));  // synchronises the stream
-    for (int s = 0; s <= h->S; ++s) h->row_first[s] = rf[s];
+    if (world == 1)
+        SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs));  // synchronises the stream
+    else
+        SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs));
     h->stats.n_active = h->n_active;
     h->stats.n_pairs = n_pairs;
     if (h->timing) cudaEventRecord(h->ev[1], st);
-    SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)N + 1) * h->dp.ldp));
+    SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)h->n_active + 1) * h->dp.ldp));
     SGPR_TRY(descriptor_forward_atoms(h, *g, st));
     if (h->timing) cudaEventRecord(h->ev[2], st);
     return SGPR_OK;
@@ -509,8 +504,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
         set_error("null argument");
         return SGPR_ERR_INVALID;
     }
-    if (world != 1 || rank != 0) {
-        set_error("atom sharding (world=%d) is not available in this build", world);
+    if (world < 1 || rank < 0 || rank >= world) {
+        set_error("bad rank/world (%d/%d)", rank, world);
         return SGPR_ERR_INVALID;
     }
     if (beta_d) {
@@ -520,12 +515,15 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
-    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world));
+    const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
+    const int* active = h->active_all ? nullptr : h->active_list.as<int>();
     const int grid_g = 2 * h->sm_count;
     const int nblk_b = h->sm_count * 8;
     const int nblk_x = 64;
-    SGPR_TRY(h->gmat.ensure(sizeof(double) * ((size_t)N + 1) * h->ldg));
-    SGPR_TRY(h->gvec.ensure(sizeof(double) * ((size_t)N + 1) * h->dp.ldp));
+    const size_t nrows = (size_t)h->n_active + 1;
+    SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
+    SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
     SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)h->S * grid_g + nblk_x)));
     SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
     SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
@@ -535,14 +533,14 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, st));
     SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
-    SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
+    SGPR_TRY(descriptor_backward_atoms(h, g, owned, st));
     if (N > 0) {
-        atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, nullptr, h->atoms.as<AtomRec>(),
-                                                  h->nl_first.as<long long>(), nullptr, h->mean_w_d.as<double>(),
+        atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, active, h->atoms.as<AtomRec>(),
+                                                  h->nl_first.as<long long>(), owned, h->mean_w_d.as<double>(),
                                                   h->lone_mu.as<double>(),
                                                   h->epart.as<double>() + (size_t)h->S * grid_g);
         scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
-                                                                      nullptr, F_d, owned_d);
+                                                                      owned, F_d, owned_d);
     }
     final_reduce_kernel<<<1, 256, 0, st>>>(h->S * grid_g, h->epart.as<double>(), nblk_x,
                                            h->epart.as<double>() + (size_t)h->S * grid_g, nblk_b,

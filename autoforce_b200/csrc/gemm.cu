@@ -41,6 +41,7 @@ struct GemmArgs {
     double xi;
     int xi_int;        // xi if it is a small positive integer, else -1
     double* epart;     // [gridDim.x] per-CTA energy partial
+    const unsigned char* row_owned;  // [M] count this row's energy (atom sharding), nullptr = all
     // epilogue 2 (back projection)
     double* C;         // [M, ldc]
     int ldc;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_kernel(GemmArgs g) {
         for (int i = 0; i < 4; ++i) {
             const int r = row0 + wm * 32 + i * 8 + gid;
             if (r >= g.M) continue;
+            const double ew = (EPI == 1 && g.row_owned) ? (g.row_owned[r] ? 1.0 : 0.0) : 1.0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = col0 + wn * 32 + j * 8 + 2 * tig;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_kernel(GemmArgs g) {
                             const double pw = powm1(k, g.xi, g.xi_int);
                             const double m = g.mu[cc];
                             gv = g.xi * m * pw;
-                            e_acc += m * pw * k;
+                            e_acc += ew * (m * pw * k);
                             if (g.Kmat) {
                                 const size_t kr = g.row_map ? (size_t)g.row_map[r] : (size_t)r;
                                 g.Kmat[kr * g.ldk + g.col_map[cc]] = pw * k;
@@ -249,6 +251,7 @@ int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_ma
         a.xi = h->xi;
         a.xi_int = h->xi_int;
         a.epart = h->epart.as<double>() + (size_t)s * grid;
+        a.row_owned = h->active_all ? nullptr : h->row_owned.as<unsigned char>() + r0;
         SGPR_TRY(launch_gemm<1>(h, a, st, grid));
         h->stats.gemm_flops += 2.0 * a.M * (double)a.N * a.K;
     }

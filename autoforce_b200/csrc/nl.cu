@@ -368,14 +368,15 @@ __device__ __forceinline__ bool pair_test(const Geom& g, const AtomRec& ai, cons
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(256) neighbor_kernel(int n_active, const int* __restrict__ active,
+__global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, const int* __restrict__ active,
                                                        const AtomRec* __restrict__ atoms, const int* __restrict__ abin,
                                                        const int* __restrict__ cstart, Geom g, int S,
                                                        int* __restrict__ nl_cnt, const long long* __restrict__ nl_first,
-                                                       PairRec* __restrict__ pairs) {
+                                                       PairRec* __restrict__ pairs, unsigned char* __restrict__ mark) {
     const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= n_active) return;
+    int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_env) return;
+    wid += env0;  // index into the active list / the neighbour-list rows
     const int c = active ? active[wid] : wid;
     const AtomRec ai = atoms[c];
     int bin = abin[c];
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int n_active, const int* 
                         const AtomRec aj = atoms[p];
                         sp = meta_species(aj.meta);
                         acc = pair_test(g, ai, aj, sx, sy, sz, p == c);
+                        if (!FILL && mark && acc) mark[p] = 1;  // atoms whose environment the owner needs (halo)
                     }
 #pragma unroll
                     for (int s = 0; s < kMaxSpecies; ++s) {
@@ -462,33 +464,18 @@ __global__ void row_total_kernel(int n, int S, const int* __restrict__ nl_cnt, l
     tot[i] = t;
 }
 
-// Builds the CSR neighbour list of the active atoms (h->n_active entries of active_list,
-// or all atoms in cell order when h->active_all):
-//   nl_cnt [n_active, S], nl_first [n_active+1] (int64), nl_pairs [n_pairs] PairRec,
-//   rows ordered by neighbour species, then bin traversal order, then cell order.
-int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs) {
-    const int S = h->S;
-    const int na = (int)h->n_active;
-    const int* active = h->active_all ? nullptr : h->active_list.as<int>();
-    SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)na * S + 1)));
-    SGPR_TRY(h->nl_first.ensure(sizeof(long long) * 2 * ((size_t)na + 1)));
-    long long* first = h->nl_first.as<long long>();
-    long long* tot = first + (na + 1);
-    *n_pairs = 0;
-    if (na == 0) return SGPR_OK;
+static int launch_count(sgpr_context* h, int env0, int n_env, const Geom& g, unsigned char* mark, cudaStream_t st) {
+    if (n_env <= 0) return SGPR_OK;
     const int T = 256;
-    const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
-    const AtomRec* atoms = h->atoms.as<AtomRec>();
-    const int* abin = h->rowof.as<int>();
-    neighbor_kernel<false><<<nblk, T, 0, st>>>(na, active, atoms, abin, h->cstart.as<int>(), g, S, h->nl_cnt.as<int>(),
-                                               nullptr, nullptr);
-    row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
-    SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
-    long long total = 0;
-    SGPR_CUDA(cudaMemcpyAsync(&total, first + na, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    int err[4] = {0, 0, 0, 0};
-    SGPR_CUDA(cudaMemcpyAsync(err, h->errflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaStreamSynchronize(st));
+    const int nblk = (int)(((int64_t)n_env * 32 + T - 1) / T);
+    neighbor_kernel<false><<<nblk, T, 0, st>>>(env0, n_env, h->active_all ? nullptr : h->active_list.as<int>(),
+                                               h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->S,
+                                               h->nl_cnt.as<int>(), nullptr, nullptr, mark);
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
+static int check_err_flags(const int* err) {
     if (err[0] == 1) {
         set_error("atomic number %d is not in the handle's species table", err[1]);
         return SGPR_ERR_SPECIES;
@@ -497,13 +484,161 @@ int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, i
         set_error("an atom lies more than 120 cells outside the unit cell; wrap positions first");
         return SGPR_ERR_GEOMETRY;
     }
+    return SGPR_OK;
+}
+
+// row totals -> exclusive scan -> (sync: pair count, error flags, species row ranges) -> fill
+static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int* row_first_src, int row_first_pitch,
+                     int64_t* n_pairs) {
+    const int S = h->S;
+    const int na = (int)h->n_active;
+    SGPR_TRY(h->nl_first.ensure(sizeof(long long) * 2 * ((size_t)na + 1)));
+    long long* first = h->nl_first.as<long long>();
+    long long* tot = first + (na + 1);
+    const int T = 256;
+    row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
+    SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
+    long long total = 0;
+    int err[4] = {0, 0, 0, 0};
+    int rf[SGPR_MAX_SPECIES + 1];
+    SGPR_CUDA(cudaMemcpyAsync(&total, first + na, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaMemcpyAsync(err, h->errflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaMemcpy2DAsync(rf, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
+                                cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    SGPR_TRY(check_err_flags(err));
+    for (int s = 0; s <= S; ++s) h->row_first[s] = rf[s];
     SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
-    neighbor_kernel<true><<<nblk, T, 0, st>>>(na, active, atoms, abin, h->cstart.as<int>(), g, S, h->nl_cnt.as<int>(),
-                                              first, h->nl_pairs.as<PairRec>());
-    h->stats.kernel_launches += 5;  // count, row totals, cub scan (2), fill
+    if (na > 0) {
+        const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
+        neighbor_kernel<true><<<nblk, T, 0, st>>>(0, na, h->active_all ? nullptr : h->active_list.as<int>(),
+                                                  h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, S,
+                                                  h->nl_cnt.as<int>(), first, h->nl_pairs.as<PairRec>(), nullptr);
+    }
+    h->stats.kernel_launches += 4;  // row totals, cub scan (2), fill
     SGPR_CUDA(cudaGetLastError());
     *n_pairs = total;
     return SGPR_OK;
+}
+
+// Neighbour list of ALL atoms (single-GPU path): rows in cell order, descriptor rows from the
+// species-major scan of cell_sort.  Output: nl_cnt [N,S], nl_first [N+1] (int64), nl_pairs,
+// rows ordered by neighbour species, then bin traversal order, then cell order; h->row_first.
+int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs) {
+    h->active_all = true;
+    h->n_active = N;
+    SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * h->S + 1)));
+    SGPR_TRY(launch_count(h, 0, (int)N, g, nullptr, st));
+    const int nkeys = g.ncell * h->S;
+    const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
+    return nl_finish(h, g, st, rstartT, (int)sizeof(int) * g.ncell, n_pairs);
+}
+
+// ---------------------------------------------------------------------------------
+// atom sharding
+// ---------------------------------------------------------------------------------
+__global__ void shard_init_kernel(int64_t N, int c0, int c1, unsigned char* __restrict__ owned,
+                                  unsigned char* __restrict__ mark, int* __restrict__ active, int* __restrict__ rowof) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const bool own = (c >= c0 && c < c1);
+    owned[c] = own ? 1 : 0;
+    mark[c] = 0;
+    rowof[c] = -1;
+    if (own) active[c - c0] = (int)c;
+}
+__global__ void halo_flag_kernel(int64_t N, const unsigned char* __restrict__ owned, const unsigned char* __restrict__ mark,
+                                 int* __restrict__ flag) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > N) return;
+    flag[c] = (c < N && mark[c] && !owned[c]) ? 1 : 0;
+}
+__global__ void halo_scatter_kernel(int64_t N, const int* __restrict__ flag, const int* __restrict__ pos, int n_own,
+                                    int* __restrict__ active) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    if (flag[c]) active[n_own + pos[c]] = (int)c;
+}
+__global__ void species_flag_kernel(int na, const int* __restrict__ active, const AtomRec* __restrict__ atoms, int s,
+                                    int* __restrict__ flag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > na) return;
+    flag[k] = (k < na && meta_species(atoms[active[k]].meta) == s) ? 1 : 0;
+}
+__global__ void species_rows_kernel(int na, const int* __restrict__ active, const AtomRec* __restrict__ atoms, int s,
+                                    const int* __restrict__ flag, const int* __restrict__ pos,
+                                    int* __restrict__ row_first_d, const unsigned char* __restrict__ owned,
+                                    int* __restrict__ rowof, unsigned char* __restrict__ row_owned) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > na) return;
+    const int base = row_first_d[s];
+    if (k == na) {
+        row_first_d[s + 1] = base + pos[na];  // read by the launch for species s+1 (stream order)
+        return;
+    }
+    if (flag[k]) {
+        const int c = active[k];
+        const int row = base + pos[k];
+        rowof[c] = row;
+        row_owned[row] = owned[c];
+    }
+}
+
+// Owned range of the cell order + exact one-cutoff halo (atoms that have an owned atom as a
+// neighbour).  Active list = owned ++ halo; rows are species-major over the active list.
+int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
+                           int64_t* n_pairs) {
+    const int S = h->S;
+    const int c0 = (int)((N * rank) / world), c1 = (int)((N * (rank + 1)) / world);
+    const int n_own = c1 - c0;
+    h->active_all = false;
+    h->n_owned = n_own;
+    SGPR_TRY(h->owned.ensure(2 * ((size_t)N + 1)));
+    SGPR_TRY(h->active_list.ensure(sizeof(int) * ((size_t)N + 1)));
+    SGPR_TRY(h->shard_tmp.ensure(sizeof(int) * (2 * ((size_t)N + 2) + SGPR_MAX_SPECIES + 2)));
+    SGPR_TRY(h->row_owned.ensure((size_t)N + 1));
+    SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * S + 1)));
+    unsigned char* owned = h->owned.as<unsigned char>();
+    unsigned char* mark = owned + (N + 1);
+    int* active = h->active_list.as<int>();
+    int* flag = h->shard_tmp.as<int>();
+    int* pos = flag + (N + 2);
+    int* row_first_d = pos + (N + 2);
+    int* rowof = h->rowof.as<int>() + (N + 1);
+    const int T = 256;
+    const int nblkN = (int)((N + 1 + T - 1) / T);
+    shard_init_kernel<<<nblkN, T, 0, st>>>(N, c0, c1, owned, mark, active, rowof);
+    h->n_active = n_own;
+    SGPR_TRY(launch_count(h, 0, n_own, g, mark, st));
+    halo_flag_kernel<<<nblkN, T, 0, st>>>(N, owned, mark, flag);
+    {
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, flag, pos, (int)N + 1, st);
+        SGPR_TRY(h->scan_tmp.ensure(tmp));
+        SGPR_CUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp, flag, pos, (int)N + 1, st));
+    }
+    halo_scatter_kernel<<<nblkN, T, 0, st>>>(N, flag, pos, n_own, active);
+    int n_halo = 0;
+    SGPR_CUDA(cudaMemcpyAsync(&n_halo, pos + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    const int na = n_own + n_halo;
+    h->n_active = na;
+    SGPR_TRY(launch_count(h, n_own, n_halo, g, nullptr, st));
+    // species-major rows over the active list
+    SGPR_CUDA(cudaMemsetAsync(row_first_d, 0, sizeof(int) * (SGPR_MAX_SPECIES + 1), st));
+    const int nblkA = (na + 1 + T - 1) / T;
+    for (int s = 0; s < S; ++s) {
+        species_flag_kernel<<<nblkA, T, 0, st>>>(na, active, h->atoms.as<AtomRec>(), s, flag);
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, flag, pos, na + 1, st);
+        SGPR_TRY(h->scan_tmp.ensure(tmp));
+        SGPR_CUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp, flag, pos, na + 1, st));
+        species_rows_kernel<<<nblkA, T, 0, st>>>(na, active, h->atoms.as<AtomRec>(), s, flag, pos, row_first_d, owned,
+                                                 rowof, h->row_owned.as<unsigned char>());
+    }
+    h->stats.kernel_launches += 5 + 4 * S;
+    SGPR_CUDA(cudaGetLastError());
+    return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs);
 }
 
 }  // namespace sgpr

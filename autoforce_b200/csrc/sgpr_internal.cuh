@@ -130,6 +130,7 @@ struct sgpr_context {
     // ---- per-call workspaces (grow-only)
     sgpr::DevBuf cnt, cstart, rstart, keyrank, atoms, order, rowof, active_list, rowmap;
     sgpr::DevBuf nl_cnt, nl_first, nl_pairs, scan_tmp;
+    sgpr::DevBuf owned, shard_tmp, row_owned;    // atom sharding: owned/mark masks, scans, per-row ownership
     sgpr::DevBuf phat, cbuf, pnorm, sflag, gmat, gvec, epart, wpart, fcell, misc;
     sgpr::DevBuf stage_pos, stage_z, stage_out;  // device staging for the host API
     void* pinned = nullptr;
@@ -138,6 +139,7 @@ struct sgpr_context {
     // ---- state of the current / last call
     int64_t last_N = 0;
     int64_t n_active = 0;
+    int64_t n_owned = 0;
     bool active_all = true;
     int row_first[SGPR_MAX_SPECIES + 1];     // first descriptor row of each central species
     sgpr::Geom last_geom;
@@ -153,6 +155,8 @@ int build_geometry(sgpr_context* h, int64_t N, const double* pos_d, const double
                    cudaStream_t st, Geom* g);
 int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const Geom& g, cudaStream_t st);
 int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs);
+int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
+                           int64_t* n_pairs);
 int scan_exclusive_ll(sgpr_context* h, const long long* in, long long* out, int n, cudaStream_t st);
 
 // ---- descriptor.cu ----------------------------------------------------------------

@@ -136,3 +136,20 @@ def test_c3_sampled_rows_match_oracle(c3):
     Zh, lone_m = o.inducing_descriptors(om, species)
     Ko, _, _ = o.kernel_from_descriptors(om, P, numbers[sample].astype(np.int64), ~mask.any(axis=1), Zh, lone_m)
     assert np.abs(Ks - Ko).max() < 1e-12
+
+
+def test_c3_sharded_over_8_ranks_matches_unsharded(c3):
+    model, pos, cell, numbers, eng = c3
+    E0, F0, W0, _ = eng.predict(pos, numbers, cell, True)
+    E, F, W = 0.0, np.zeros_like(F0), np.zeros_like(W0)
+    n_active = []
+    for rank in range(8):
+        e, f, w, owned = eng.predict(pos, numbers, cell, True, rank=rank, world=8)
+        assert abs(int(owned.sum()) - len(pos) / 8) <= 1
+        n_active.append(eng.stats()["n_active"])
+        E, F, W = E + e, F + f, W + w
+    assert abs(E - E0) / len(pos) < 1e-12
+    assert np.abs(F - F0).max() < 1e-10
+    assert np.abs(W - W0).max() < 1e-7
+    # halo = one cutoff on each side of an x-slab: redundant work stays bounded
+    assert max(n_active) < 2.6 * len(pos) / 8

@@ -159,3 +159,25 @@ def test_empty_structure():
     E, F, W, owned = eng.predict(np.zeros((0, 3)), np.zeros(0, np.int32), g["cell"], True)
     assert E == 0.0 and F.shape == (0, 3) and np.all(W == 0)
     eng.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_atom_sharding_sums_to_single_rank_result(case, world):
+    """every rank evaluates its owned environments + the one-cutoff halo and
+    returns E/W partial sums and the forces of its owned atoms; summing the ranks (what
+    the 10-double all-reduce does for E and W) must reproduce the unsharded result."""
+    g, eng = case
+    args = (g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    E0, F0, W0, own0 = eng.predict(*args)
+    E, F, W = 0.0, np.zeros_like(F0), np.zeros_like(W0)
+    count = np.zeros(len(F0), dtype=int)
+    for rank in range(world):
+        e, f, w, owned = eng.predict(*args, rank=rank, world=world)
+        assert np.all(f[~owned] == 0.0)
+        E, F, W = E + e, F + f, W + w
+        count += owned
+    assert np.all(count == 1)                       # disjoint and complete ownership
+    N = len(F0)
+    assert abs(E - E0) / N < 1e-12
+    assert np.abs(F - F0).max() < 1e-11
+    assert np.abs(W - W0).max() < 1e-10

@@ -82,6 +82,33 @@ __global__ void atom_terms_kernel(int64_t N, int n_active, const int* __restrict
     if (threadIdx.x == 0) part[blockIdx.x] = red[0];
 }
 
+// covloss (calculator/active.py:781-804): beta_i = sqrt(clamp(1 - c_i, 0)) * sqrt(vscale[Z_i])
+__global__ void beta_finish_kernel(int n_active, const int* __restrict__ active, const AtomRec* __restrict__ atoms,
+                                   const int* __restrict__ rowof, const long long* __restrict__ nl_first,
+                                   const unsigned char* __restrict__ owned, const unsigned char* __restrict__ sp_on,
+                                   const int* __restrict__ sp_enabled, const double* __restrict__ cpart, int n_part,
+                                   int part_ld, const double* __restrict__ clone, const double* __restrict__ vscale,
+                                   double* __restrict__ beta) {
+    for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n_active; env += gridDim.x * blockDim.x) {
+        const int c = active ? active[env] : env;
+        if (owned && !owned[c]) continue;
+        const unsigned long long meta = atoms[c].meta;
+        const int sp = meta_species(meta);
+        double cc = 0.0;
+        const bool lone = nl_first[env + 1] == nl_first[env];
+        if (lone) {
+            cc = clone[sp];
+        } else if (sp_on[sp]) {
+            const int row = rowof[c];
+            for (int p = 0; p < n_part; ++p) cc += cpart[(size_t)p * part_ld + row];
+        }
+        double b = sqrt(fmax(1.0 - cc, 0.0));
+        // the reference divides c by the self kernel k(x,x) = 0 for an excluded centre -> NaN (active.py:784-791)
+        if (!lone && !sp_enabled[sp]) b = nan("");
+        beta[meta_orig(meta)] = b * sqrt(vscale[sp]);
+    }
+}
+
 __global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ atoms, const double* __restrict__ fcell,
                                       const unsigned char* __restrict__ owned, double* __restrict__ F,
                                       unsigned char* __restrict__ owned_out) {
@@ -215,13 +242,30 @@ static int upload_weights(sgpr_context* h, const double* mu_h, const double* mea
         h->mean_w.resize(SGPR_MAX_SPECIES, 0.0);
         SGPR_TRY(upload(h->mean_w_d, h->mean_w.data(), sizeof(double) * SGPR_MAX_SPECIES));
     }
-    if (vscale_h) h->vscale.assign(vscale_h, vscale_h + S);
+    if (vscale_h) {
+        h->vscale.assign(vscale_h, vscale_h + S);
+        h->vscale.resize(SGPR_MAX_SPECIES, INFINITY);
+        SGPR_TRY(upload(h->vscale_d, h->vscale.data(), sizeof(double) * SGPR_MAX_SPECIES));
+    }
     if (choli_h) {
-        // rows and columns permuted into the sorted inducing order
-        std::vector<double> c((size_t)M * M);
-        for (int a = 0; a < M; ++a)
-            for (int b = 0; b < M; ++b) c[(size_t)a * M + b] = choli_h[(size_t)a * M + h->ind_perm[b]];
-        SGPR_TRY(upload(h->choli, c.data(), sizeof(double) * (size_t)M * M));
+        // per central species: choli[:, columns of that species] (sorted inducing order), rows
+        // zero-padded to ld_zt -> the B operand of the covloss GEMM (K contiguous)
+        std::vector<double> c((size_t)S * M * h->ld_zt, 0.0);
+        std::vector<double> clone(SGPR_MAX_SPECIES, 0.0);
+        for (int s = 0; s < S; ++s) {
+            const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
+            for (int k = 0; k < M; ++k) {
+                double lone_sum = 0.0;
+                for (int p = m0; p < m1; ++p) {
+                    const double v = choli_h[(size_t)k * M + h->ind_perm[p]];
+                    c[((size_t)s * M + k) * h->ld_zt + (p - m0)] = v;
+                    if (h->ind_lone[p]) lone_sum += v;
+                }
+                clone[s] += lone_sum * lone_sum;  // c of a neighbour-less atom (K row = lone indicator)
+            }
+        }
+        SGPR_TRY(upload(h->choli_t, c.data(), sizeof(double) * c.size()));
+        SGPR_TRY(upload(h->clone_d, clone.data(), sizeof(double) * SGPR_MAX_SPECIES));
         h->has_choli = true;
     }
     (void)ind_first_h;
@@ -273,8 +317,9 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     dp.L2 = (d->lmax + 1) * (d->lmax + 1);
     dp.S = S;
     dp.A = S * dp.nb;
+    dp.L2p = dp.L2 | 1;
     dp.ncomp = dp.nb * dp.L2;
-    dp.csize = S * dp.ncomp;
+    dp.csize = dp.A * dp.L2p;
     const int L = d->lmax + 1;
     dp.D = dp.A * (dp.A + 1) / 2 * L;
     dp.ldp = (dp.D + 15) & ~15;
@@ -422,8 +467,9 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         SGPR_TRY(upload(h->ind_sp_d, sp_orig.data(), sizeof(int) * M));
         SGPR_TRY(upload(h->ind_lone_d, lone_orig.data(), M));
     }
-    std::vector<double> zeros(SGPR_MAX_SPECIES, 0.0);
-    int st = upload_weights(h, d->mu_h, d->mean_w_h ? d->mean_w_h : zeros.data(), d->choli_h, d->vscale_h, nullptr);
+    std::vector<double> zeros(SGPR_MAX_SPECIES, 0.0), infs(SGPR_MAX_SPECIES, INFINITY);
+    int st = upload_weights(h, d->mu_h, d->mean_w_h ? d->mean_w_h : zeros.data(), d->choli_h,
+                            d->vscale_h ? d->vscale_h : infs.data(), nullptr);
     if (st != SGPR_OK) {
         delete h;
         return st;
@@ -439,12 +485,13 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&h->zhat, &h->zhat_t, &h->mu, &h->lone_mu, &h->choli, &h->ptab, &h->nnlk, &h->ztab, &h->errflag,
+    DevBuf* bufs[] = {&h->zhat, &h->zhat_t, &h->mu, &h->lone_mu, &h->ptab, &h->nnlk, &h->ztab, &h->errflag,
                       &h->ind_perm_d, &h->sp_on, &h->ind_sp_d, &h->ind_lone_d, &h->mean_w_d, &h->cnt, &h->cstart,
                       &h->rstart, &h->keyrank, &h->atoms, &h->order, &h->rowof, &h->active_list, &h->nl_cnt,
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
-                      &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned};
+                      &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
+                      &h->kcmat, &h->cpart};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -508,8 +555,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
         set_error("bad rank/world (%d/%d)", rank, world);
         return SGPR_ERR_INVALID;
     }
-    if (beta_d) {
-        set_error("covloss output is not available in this build");
+    if (beta_d && !h->has_choli) {
+        set_error("covloss requested but the model has no choli");
         return SGPR_ERR_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -518,19 +565,20 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world));
     const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
     const int* active = h->active_all ? nullptr : h->active_list.as<int>();
-    const int grid_g = 2 * h->sm_count;
-    const int nblk_b = h->sm_count * 8;
+    const int grid_g = gemm_grid_size(h);
+    const int nblk_b = backward_grid(h);
     const int nblk_x = 64;
     const size_t nrows = (size_t)h->n_active + 1;
     SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
     SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
-    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)h->S * grid_g + nblk_x)));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + nblk_x)));
     SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
     SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
-    SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)h->S * grid_g + nblk_x), st));
+    SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)grid_g + nblk_x), st));
     SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
     SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
-    SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, st));
+    if (beta_d) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
+    SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
     SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
     SGPR_TRY(descriptor_backward_atoms(h, g, owned, st));
@@ -538,23 +586,43 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
         atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, active, h->atoms.as<AtomRec>(),
                                                   h->nl_first.as<long long>(), owned, h->mean_w_d.as<double>(),
                                                   h->lone_mu.as<double>(),
-                                                  h->epart.as<double>() + (size_t)h->S * grid_g);
+                                                  h->epart.as<double>() + (size_t)grid_g);
         scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
                                                                       owned, F_d, owned_d);
     }
-    final_reduce_kernel<<<1, 256, 0, st>>>(h->S * grid_g, h->epart.as<double>(), nblk_x,
-                                           h->epart.as<double>() + (size_t)h->S * grid_g, nblk_b,
+    final_reduce_kernel<<<1, 256, 0, st>>>(grid_g, h->epart.as<double>(), nblk_x,
+                                           h->epart.as<double>() + (size_t)grid_g, nblk_b,
                                            h->wpart.as<double>(), E_d, W_d);
     h->stats.kernel_launches += 3;
     SGPR_CUDA(cudaGetLastError());
+    if (h->timing) cudaEventRecord(h->ev[4], st);
+    h->stats.covloss_flops = 0.0;
+    if (beta_d) {
+        const int n_part = gemm_covloss_parts(h);
+        SGPR_TRY(h->cpart.ensure(sizeof(double) * (size_t)n_part * nrows));
+        SGPR_CUDA(cudaMemsetAsync(beta_d, 0, sizeof(double) * (size_t)N, st));
+        SGPR_TRY(gemm_covloss(h, (int64_t)nrows, st));
+        if (h->n_active > 0) {
+            SGPR_TRY(h->misc.ensure(sizeof(int) * SGPR_MAX_SPECIES));
+            SGPR_CUDA(cudaMemcpyAsync(h->misc.p, h->dp.central_enabled, sizeof(int) * SGPR_MAX_SPECIES,
+                                      cudaMemcpyHostToDevice, st));
+            beta_finish_kernel<<<h->sm_count * 2, 256, 0, st>>>(
+                (int)h->n_active, active, h->atoms.as<AtomRec>(), h->rowof.as<int>() + (N + 1), h->nl_first.as<long long>(),
+                owned, h->sp_on.as<unsigned char>(), h->misc.as<int>(), h->cpart.as<double>(), n_part, (int)nrows,
+                h->clone_d.as<double>(), h->vscale_d.as<double>(), beta_d);
+            h->stats.kernel_launches += 1;
+        }
+        SGPR_CUDA(cudaGetLastError());
+    }
     if (h->timing) {
-        cudaEventRecord(h->ev[4], st);
-        SGPR_CUDA(cudaEventSynchronize(h->ev[4]));
+        cudaEventRecord(h->ev[5], st);
+        SGPR_CUDA(cudaEventSynchronize(h->ev[5]));
         cudaEventElapsedTime(&h->stats.ms_nl, h->ev[0], h->ev[1]);
         cudaEventElapsedTime(&h->stats.ms_desc, h->ev[1], h->ev[2]);
         cudaEventElapsedTime(&h->stats.ms_gemm, h->ev[2], h->ev[3]);
         cudaEventElapsedTime(&h->stats.ms_force, h->ev[3], h->ev[4]);
-        cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[4]);
+        cudaEventElapsedTime(&h->stats.ms_beta, h->ev[4], h->ev[5]);
+        cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[5]);
     }
     return SGPR_OK;
 }
@@ -579,7 +647,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_han
     SGPR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->own_stream;
     const size_t nb_pos = sizeof(double) * 3 * (size_t)N, nb_z = sizeof(int32_t) * (size_t)N;
-    const size_t nb_out = sizeof(double) * (3 * (size_t)N + 16);
+    const size_t nb_out = sizeof(double) * ((beta_h ? 4 : 3) * (size_t)N + 16);
     SGPR_TRY(ensure_pinned(h, nb_pos + nb_z + nb_out + (size_t)N + 64));
     char* pin = (char*)h->pinned;
     double* pin_pos = (double*)pin;
@@ -593,10 +661,11 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_han
     memcpy(pin_z, Z_h, nb_z);
     SGPR_CUDA(cudaMemcpyAsync(h->stage_pos.p, pin_pos, nb_pos, cudaMemcpyHostToDevice, st));
     SGPR_CUDA(cudaMemcpyAsync(h->stage_z.p, pin_z, nb_z, cudaMemcpyHostToDevice, st));
-    double* out_d = h->stage_out.as<double>();  // [E(1) pad(6) W(9) F(3N)]
-    uint8_t* own_d = owned_h ? (uint8_t*)(out_d + 16 + 3 * (size_t)N) : nullptr;
+    double* out_d = h->stage_out.as<double>();  // [E(1) pad(6) W(9) F(3N) beta(N)]
+    double* beta_d = beta_h ? out_d + 16 + 3 * (size_t)N : nullptr;
+    uint8_t* own_d = owned_h ? (uint8_t*)(out_d + 16 + (beta_h ? 4 : 3) * (size_t)N) : nullptr;
     SGPR_TRY(sgpr_predict(h, N, h->stage_pos.as<double>(), h->stage_z.as<int32_t>(), cell_h, pbc_h, rank, world, st,
-                          out_d, out_d + 16, out_d + 7, nullptr, own_d));
+                          out_d, out_d + 16, out_d + 7, beta_d, own_d));
     SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
     if (owned_h) SGPR_CUDA(cudaMemcpyAsync(pin_own, own_d, (size_t)N, cudaMemcpyDeviceToHost, st));
     SGPR_CUDA(cudaStreamSynchronize(st));
@@ -604,7 +673,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_han
     memcpy(W_h, pin_out + 7, sizeof(double) * 9);
     memcpy(F_h, pin_out + 16, nb_pos);
     if (owned_h) memcpy(owned_h, pin_own, (size_t)N);
-    (void)beta_h;
+    if (beta_h) memcpy(beta_h, pin_out + 16 + 3 * (size_t)N, sizeof(double) * (size_t)N);
     return SGPR_OK;
 }
 
@@ -618,15 +687,15 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_forward(sgpr_h
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
     SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
-    const int grid_g = 2 * h->sm_count;
+    const int grid_g = gemm_grid_size(h);
     SGPR_TRY(h->gmat.ensure(sizeof(double) * ((size_t)N + 1) * h->ldg));
-    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)h->S * grid_g + 64)));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + 64)));
     SGPR_TRY(h->rowmap.ensure(sizeof(int) * ((size_t)N + 1)));
     SGPR_CUDA(cudaMemsetAsync(K_d, 0, sizeof(double) * (size_t)N * h->M, st));
     if (N > 0 && h->M > 0) {
         row_to_orig_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(),
                                                                    h->rowof.as<int>() + (N + 1), h->rowmap.as<int>());
-        SGPR_TRY(gemm_kernel_matrix(h, K_d, h->M, h->rowmap.as<int>(), st));
+        SGPR_TRY(gemm_kernel_matrix(h, K_d, h->M, h->rowmap.as<int>(), false, st));
         // lone-lone term, in the caller's inducing order
         bool any = false;
         for (int p = 0; p < h->M; ++p) any |= h->ind_lone[p] != 0;

@@ -89,8 +89,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // packed-entry table word: a | b << 8 | l << 16
 __device__ __forceinline__ double pspec_entry(const DescParams& dp, const double* c_s, unsigned w, double scale) {
     const int a = w & 0xff, b = (w >> 8) & 0xff, l = (w >> 16) & 0xff;
-    const double* ca = c_s + a * dp.L2 + l * l;
-    const double* cb = c_s + b * dp.L2 + l * l;
+    const double* ca = c_s + a * dp.L2p + l * l;
+    const double* cb = c_s + b * dp.L2p + l * l;
     double s = 0.0;
     for (int k = 0; k < 2 * l + 1; ++k) s += ca[k] * cb[k];
     return s * scale;
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         offn[t] = n;
         offy[t] = dp.nb + (comp - n * dp.L2);
     }
+    const int sp_stride = dp.nb * dp.L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
     for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
         long long beg, end;
         AtomRec ai;
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
                     if (cur_s >= 0) {
 #pragma unroll
                         for (int t = 0; t < CPL; ++t) {
-                            const int comp = lane + 32 * t;
-                            if (comp < dp.ncomp) c_s[cur_s * dp.ncomp + comp] += acc[t];
+                            if (lane + 32 * t < dp.ncomp)
+                                c_s[cur_s * sp_stride + offn[t] * dp.L2p + (offy[t] - dp.nb)] += acc[t];
                             acc[t] = 0.0;
                         }
                     }
@@ -204,10 +205,8 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         }
         if (cur_s >= 0) {
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                const int comp = lane + 32 * t;
-                if (comp < dp.ncomp) c_s[cur_s * dp.ncomp + comp] += acc[t];
-            }
+            for (int t = 0; t < CPL; ++t)
+                if (lane + 32 * t < dp.ncomp) c_s[cur_s * sp_stride + offn[t] * dp.L2p + (offy[t] - dp.nb)] += acc[t];
         }
         __syncwarp();
         // power spectrum, norm over ALL blocks (sesoap.py:249-251), packed row out
@@ -243,7 +242,7 @@ struct BackOut {
 };
 
 template <int LMAX, int NB>
-__global__ void __launch_bounds__(256) desc_backward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
+__global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                             const int* __restrict__ row_of,
                                                             const unsigned* __restrict__ ptab,
                                                             const double* __restrict__ nnlk,
@@ -287,16 +286,16 @@ __global__ void __launch_bounds__(256) desc_backward_kernel(DescParams dp, Geom 
         for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
         __syncwarp();
         // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm]
-        for (int o = lane; o < dp.csize; o += 32) {
+        for (int o = lane; o < dp.A * dp.L2; o += 32) {
             const int a = o / dp.L2, lm = o - a * dp.L2;
             const int l = c_l_of_lm[lm];
             double s = 0.0;
             for (int b = 0; b < dp.A; ++b) {
                 const int lo = min(a, b), hi = max(a, b);
                 const int tri = lo * dp.A - (lo * (lo - 1)) / 2 + (hi - lo);
-                s += T_s[tri * L + l] * c_s[b * dp.L2 + lm];
+                s += T_s[tri * L + l] * c_s[b * dp.L2p + lm];
             }
-            D_s[o] = s;
+            D_s[a * dp.L2p + lm] = s;
         }
         __syncwarp();
         double Fx = 0.0, Fy = 0.0, Fz = 0.0;
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(256) desc_backward_kernel(DescParams dp, Geom 
                 ys = y - kTinyAngle * z;
                 zs = kTinyAngle * y + z;
             }
-            const double* Dj = D_s + sp * dp.ncomp;
+            const double* Dj = D_s + sp * dp.nb * dp.L2p;
             double gx = 0.0, gy = 0.0, gz = 0.0;
             solid_harmonics<LMAX, true>(c_harm, dp.lmax, x, ys, zs,
                                         [&](int idx, double Y, double dYx, double dYy, double dYz) {
@@ -338,7 +337,7 @@ __global__ void __launch_bounds__(256) desc_backward_kernel(DescParams dp, Geom 
 #pragma unroll
                                             for (int n = 0; n < NB; ++n) {
                                                 if (n < dp.nb) {
-                                                    const double dc = Dj[n * dp.L2 + idx];
+                                                    const double dc = Dj[n * dp.L2p + idx];
                                                     B += dc * f[n];
                                                     Tn[n] += dc * Y;
                                                 }
@@ -430,7 +429,7 @@ Launch plan_forward(const DescParams& dp, int stride) {
 }
 Launch plan_backward(const DescParams& dp) {
     int per_warp = ((dp.D + 1) & ~1) + 2 * ((dp.csize + 1) & ~1);
-    int warps = 8;
+    int warps = 4;
     while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
     return {warps, (size_t)warps * per_warp * 8, per_warp};
 }
@@ -525,7 +524,7 @@ int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st) {
                                    h->cbuf.as<double>(), h->pnorm.as<double>(), h->sflag.as<unsigned char>(), st);
 }
 
-int backward_grid(sgpr_context* h) { return h->sm_count * 8; }
+int backward_grid(sgpr_context* h) { return h->sm_count * 16; }
 
 int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st) {
     const int na = (int)h->n_active;

@@ -408,14 +408,25 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
                 sy = (ny >= 0) ? ny / g.nb[1] : -((-ny + g.nb[1] - 1) / g.nb[1]);
                 ny -= sy * g.nb[1];
             } else if (ny < 0 || ny >= g.nb[1]) continue;
-            for (int dz = -g.reach[2]; dz <= g.reach[2]; ++dz) {
-                int nz = bz + dz, sz = 0;
-                if (g.pbc[2]) {
-                    sz = (nz >= 0) ? nz / g.nb[2] : -((-nz + g.nb[2] - 1) / g.nb[2]);
-                    nz -= sz * g.nb[2];
-                } else if (nz < 0 || nz >= g.nb[2]) continue;
+            // z bins of this (x,y) column: contiguous in cell order -> one merged run when the
+            // stencil does not wrap (or leave the box) inside the column
+            const int zlo = bz - g.reach[2], zhi = bz + g.reach[2];
+            const bool merged = (zlo >= 0 && zhi < g.nb[2]);
+            for (int dz = merged ? 0 : -g.reach[2]; dz <= (merged ? 0 : g.reach[2]); ++dz) {
+                int nz = bz + dz, sz = 0, nz_last;
+                if (merged) {
+                    nz = zlo;
+                    nz_last = zhi;
+                } else {
+                    if (g.pbc[2]) {
+                        sz = (nz >= 0) ? nz / g.nb[2] : -((-nz + g.nb[2] - 1) / g.nb[2]);
+                        nz -= sz * g.nb[2];
+                    } else if (nz < 0 || nz >= g.nb[2]) continue;
+                    nz_last = nz;
+                }
                 const int b2 = (nx * g.nb[1] + ny) * g.nb[2] + nz;
-                const int beg = cstart[b2 * S], end = cstart[b2 * S + S];
+                const int b3 = (nx * g.nb[1] + ny) * g.nb[2] + nz_last;
+                const int beg = cstart[b2 * S], end = cstart[b3 * S + S];
                 for (int p0 = beg; p0 < end; p0 += 32) {
                     const int p = p0 + lane;
                     bool acc = false;

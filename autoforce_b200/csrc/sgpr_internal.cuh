@@ -68,10 +68,11 @@ struct Geom {
 struct DescParams {
     int lmax, nb;           // nb = nmax+1
     int L2;                 // (lmax+1)^2
+    int L2p;                // row stride of c[a][lm] (L2 made odd: conflict-free smem columns)
     int S;                  // species
     int A;                  // S*nb
     int ncomp;              // nb*L2  (components per species)
-    int csize;              // S*nb*L2
+    int csize;              // A*L2p  (padded expansion-coefficient block per atom)
     int D;                  // packed descriptor length = A(A+1)/2*(lmax+1)
     int ldp;                // leading dimension of packed descriptor rows (doubles)
     int normalize;
@@ -120,7 +121,10 @@ struct sgpr_context {
     sgpr::DevBuf mu;          // [M] sorted order
     sgpr::DevBuf lone_mu;     // [S] sum of mu over neighbour-less inducing LCEs of species s
     sgpr::DevBuf mean_w_d;    // [S]
-    sgpr::DevBuf choli;       // [M, M], columns in sorted order
+    sgpr::DevBuf choli_t;     // [S][M, ld_zt]: choli[:, columns of species s] (sorted order), zero padded
+    sgpr::DevBuf vscale_d;    // [S] model._vscale (inf where unseen)
+    sgpr::DevBuf clone_d;     // [S] c of a neighbour-less atom of species s
+    sgpr::DevBuf kcmat, cpart;  // covloss: K^xi [rows, ldg], per-row partial sums of squares
     sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
     sgpr::DevBuf ztab;        // [128] atomic number -> species
     sgpr::DevBuf ind_perm_d;  // [M]
@@ -171,7 +175,9 @@ int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, 
 
 // ---- gemm.cu ----------------------------------------------------------------------
 int gemm_grid_size(sgpr_context* h);
-int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, cudaStream_t st);
+int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st);
+int gemm_covloss_parts(sgpr_context* h);
+int gemm_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
 int gemm_back_projection(sgpr_context* h, cudaStream_t st);
 
 }  // namespace sgpr

@@ -33,8 +33,8 @@ class sgpr_model_desc(ctypes.Structure):
 class sgpr_stats(ctypes.Structure):
     _fields_ = [
         ("n_atoms", c_int64), ("n_active", c_int64), ("n_pairs", c_int64), ("d_packed", c_int32), ("d_full", c_int32),
-        ("kernel_launches", c_int64), ("gemm_flops", c_double), ("ms_nl", c_float), ("ms_desc", c_float),
-        ("ms_gemm", c_float), ("ms_force", c_float), ("ms_total", c_float),
+        ("kernel_launches", c_int64), ("gemm_flops", c_double), ("covloss_flops", c_double), ("ms_nl", c_float),
+        ("ms_desc", c_float), ("ms_gemm", c_float), ("ms_force", c_float), ("ms_beta", c_float), ("ms_total", c_float),
     ]
 
 
@@ -162,8 +162,9 @@ class SgprEngine:
         return c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ hot path
-    def predict(self, pos, numbers, cell, pbc, rank=0, world=1):
-        """Host numpy in, host numpy out (H2D/D2H inside): E, F[N,3], W[3,3], owned[N]."""
+    def predict(self, pos, numbers, cell, pbc, rank=0, world=1, want_beta=False):
+        """Host numpy in, host numpy out (H2D/D2H inside): E, F[N,3], W[3,3], owned[N]
+        (+ beta[N], the covloss of calculator/active.py:781-804, when want_beta)."""
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
         Z = np.ascontiguousarray(numbers, dtype=np.int32).reshape(-1)
         N = len(Z)
@@ -172,8 +173,11 @@ class SgprEngine:
         F = np.zeros((N, 3))
         W = np.zeros(9)
         owned = np.zeros(N, dtype=np.uint8)
+        beta = np.zeros(N) if want_beta else None
         _check(self.lib, self.lib.sgpr_predict_host(self._h, N, _ptr(pos), _ptr(Z), _ptr(cell_h), _ptr(pbc_h), rank, world,
-                                                    _ptr(E), _ptr(F), _ptr(W), None, _ptr(owned)))
+                                                    _ptr(E), _ptr(F), _ptr(W), _ptr(beta) if want_beta else None, _ptr(owned)))
+        if want_beta:
+            return float(E[0]), F, W.reshape(3, 3), owned.astype(bool), beta
         return float(E[0]), F, W.reshape(3, 3), owned.astype(bool)
 
     def predict_device(self, pos_t, z_t, cell, pbc, rank=0, world=1, out=None):

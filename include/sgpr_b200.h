@@ -166,8 +166,9 @@ typedef struct {
     int32_t d_full;           /* S*S*(nmax+1)^2*(lmax+1)                               */
     int64_t kernel_launches;  /* CUDA kernels launched by the last hot-path call        */
     double  gemm_flops;       /* flops executed by the two kernel GEMMs, last call     */
-    float   ms_nl, ms_desc, ms_gemm, ms_force, ms_total; /* device time per stage of the
-                                 last call (CUDA events), valid if timing was enabled  */
+    double  covloss_flops;    /* flops executed by the covloss GEMM, last call         */
+    float   ms_nl, ms_desc, ms_gemm, ms_force, ms_beta, ms_total; /* device time per stage
+                                 of the last call (CUDA events), valid if timing is on */
 } sgpr_stats;
 
 int sgpr_get_stats(sgpr_handle h, sgpr_stats* out);

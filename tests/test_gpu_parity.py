@@ -181,3 +181,26 @@ def test_atom_sharding_sums_to_single_rank_result(case, world):
     assert abs(E - E0) / N < 1e-12
     assert np.abs(F - F0).max() < 1e-11
     assert np.abs(W - W0).max() < 1e-10
+
+
+def test_covloss_matches_reference(case):
+    """beta = get_covloss() (calculator/active.py:781-804), incl. sqrt(vscale), inf for species
+    without variance scale and NaN for centres excluded via a/a_not."""
+    g, eng = case
+    E, F, W, owned, beta = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"], want_beta=True)
+    ref = g["covloss"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(beta), fin)
+    assert np.array_equal(np.isnan(beta), np.isnan(ref))
+    # the sqrt next to the clamp amplifies rounding: compare beta^2
+    assert np.abs(beta[fin] ** 2 - ref[fin] ** 2).max() < 1e-9
+    # asking for beta must not change E/F/W
+    E0, F0, W0, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    assert E == E0 and np.array_equal(W, W0) and np.abs(F - F0).max() < 1e-12
+    # sharded: each rank fills the betas of the atoms it owns
+    parts = np.zeros_like(beta)
+    for rank in range(3):
+        _, _, _, own, b = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"], rank=rank, world=3, want_beta=True)
+        parts[own] = b[own]
+    assert np.array_equal(np.isnan(parts), np.isnan(beta))
+    assert np.abs(parts[fin] ** 2 - beta[fin] ** 2).max() < 1e-12

@@ -90,12 +90,23 @@ def speed(workload="c2", steps=5):
     print(f"{workload}: N={len(pos)} M={model.M} setup {time.time() - t0:.1f}s", flush=True)
     for it in range(steps):
         t = time.time()
-        E, F, W, owned = eng.predict(pos, numbers, cell, True)
+        E, F, W, owned = eng.predict(pos, numbers, cell, True)[:4]
         dt = time.time() - t
         s = eng.stats()
         print(f"  step {it}: {dt * 1e3:.2f} ms wall  E={E:.6f} |F|max={np.abs(F).max():.4f} pairs={s['n_pairs']} "
               f"nl={s['ms_nl']:.3f} desc={s['ms_desc']:.3f} gemm={s['ms_gemm']:.3f} force={s['ms_force']:.3f} total={s['ms_total']:.3f} ms "
               f"gemm TF/s={s['gemm_flops'] / max(s['ms_gemm'], 1e-9) / 1e9:.2f}", flush=True)
+    if os.environ.get("BETA"):
+        model2 = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli=True)
+        eng2 = ab.SgprEngine(model2, species=w["Zs"])
+        eng2.enable_timing(True)
+        for it in range(3):
+            t = time.time()
+            out = eng2.predict(pos, numbers, cell, True, want_beta=True)
+            s = eng2.stats()
+            print(f"  beta step {it}: {1e3 * (time.time() - t):.2f} ms wall, beta stage {s['ms_beta']:.3f} ms, "
+                  f"{s['covloss_flops'] / max(s['ms_beta'], 1e-9) / 1e9:.2f} TF/s, beta max {np.nanmax(out[4]):.4f}", flush=True)
+        eng2.close()
     eng.close()
 
 

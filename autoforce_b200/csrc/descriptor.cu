@@ -99,29 +99,28 @@ __device__ __forceinline__ double pspec_entry(const DescParams& dp, const double
 // ---------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------
-template <int LMAX, int CPL, bool ENV>
+// Phase-B ownership: lane -> (n tile, lm tile) of TN x TL components; per neighbour it loads
+// TN radial values + TL harmonics from shared memory for TN*TL FMAs.
+template <int LMAX, int TN, int TL, bool ENV>
 __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                            const int* __restrict__ row_of,
                                                            const unsigned* __restrict__ ptab,
                                                            const double* __restrict__ nnlk, double* __restrict__ phat,
                                                            double* __restrict__ cbuf, double* __restrict__ pnorm,
                                                            unsigned char* __restrict__ sflag, int per_warp_doubles,
-                                                           int stride) {
+                                                           int stride, int nbp) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* c_s = smem + (size_t)warp * per_warp_doubles;
-    double* buf = c_s + ((dp.csize + 1) & ~1);
+    double* buf = c_s + ((dp.csize + 1) & ~1);          // [32][stride]: f[0..nb) | pad | Y[0..L2) | pad
     int* sp_s = reinterpret_cast<int*>(buf + 32 * stride);
-    // component ownership: comp = lane + 32 t  ->  (n, lm)
-    int offn[CPL], offy[CPL];
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) {
-        const int comp = lane + 32 * t;
-        const int n = comp / dp.L2;
-        offn[t] = n;
-        offy[t] = dp.nb + (comp - n * dp.L2);
-    }
+    const int nLt = (dp.L2 + TL - 1) / TL;
+    const int lm0 = (lane % nLt) * TL, n0 = (lane / nLt) * TN;
+    const bool lane_on = n0 < dp.nb;
     const int sp_stride = dp.nb * dp.L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
+    const int L = dp.lmax + 1;
+    const int npairs = dp.A * (dp.A + 1) / 2;
+    const bool cache_q = dp.D <= 32 * stride;            // packed row fits the (then idle) chunk buffer
     for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
         long long beg, end;
         AtomRec ai;
@@ -150,9 +149,22 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         const bool flag = __any_sync(0xffffffffu, hit);
         __syncwarp();
         int cur_s = -1;
-        double acc[CPL];
+        double acc[TN][TL];
 #pragma unroll
-        for (int t = 0; t < CPL; ++t) acc[t] = 0.0;
+        for (int a = 0; a < TN; ++a)
+#pragma unroll
+            for (int b = 0; b < TL; ++b) acc[a][b] = 0.0;
+        auto flush = [&](int sp) {
+            if (lane_on) {
+#pragma unroll
+                for (int a = 0; a < TN; ++a)
+#pragma unroll
+                    for (int b = 0; b < TL; ++b) {
+                        if (n0 + a < dp.nb && lm0 + b < dp.L2) c_s[sp * sp_stride + (n0 + a) * dp.L2p + lm0 + b] += acc[a][b];
+                        acc[a][b] = 0.0;
+                    }
+            }
+        };
         for (long long k0 = beg; k0 < end; k0 += 32) {
             const long long k = k0 + lane;
             if (k < end) {
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
                     ys = y - kTinyAngle * z;
                     zs = kTinyAngle * y + z;
                 }
-                double* yo = my + dp.nb;
+                double* yo = my + nbp;
                 solid_harmonics<LMAX, false>(c_harm, dp.lmax, x, ys, zs,
                                              [&](int idx, double Y, double, double, double) { yo[idx] = Y; });
                 sp_s[lane] = sp;
@@ -185,41 +197,57 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
             const int cnt = (int)min((long long)32, end - k0);
             for (int jj = 0; jj < cnt; ++jj) {
                 const int s = sp_s[jj];
-                if (s != cur_s) {
-                    if (cur_s >= 0) {
-#pragma unroll
-                        for (int t = 0; t < CPL; ++t) {
-                            if (lane + 32 * t < dp.ncomp)
-                                c_s[cur_s * sp_stride + offn[t] * dp.L2p + (offy[t] - dp.nb)] += acc[t];
-                            acc[t] = 0.0;
-                        }
-                    }
+                if (s != cur_s) {   // warp-uniform; rows are ordered by neighbour species
+                    if (cur_s >= 0) flush(cur_s);
                     cur_s = s;
                 }
-                const double* row = buf + jj * stride;
+                if (lane_on) {
+                    const double* row = buf + jj * stride;
+                    double fv[TN], yv[TL];
 #pragma unroll
-                for (int t = 0; t < CPL; ++t)
-                    if (lane + 32 * t < dp.ncomp) acc[t] += row[offn[t]] * row[offy[t]];
+                    for (int a = 0; a < TN; ++a) fv[a] = row[n0 + a];
+#pragma unroll
+                    for (int b = 0; b < TL; ++b) yv[b] = row[nbp + lm0 + b];
+#pragma unroll
+                    for (int a = 0; a < TN; ++a)
+#pragma unroll
+                        for (int b = 0; b < TL; ++b) acc[a][b] += fv[a] * yv[b];
+                }
             }
             __syncwarp();
         }
-        if (cur_s >= 0) {
-#pragma unroll
-            for (int t = 0; t < CPL; ++t)
-                if (lane + 32 * t < dp.ncomp) c_s[cur_s * sp_stride + offn[t] * dp.L2p + (offy[t] - dp.nb)] += acc[t];
-        }
+        if (cur_s >= 0) flush(cur_s);
         __syncwarp();
-        // power spectrum, norm over ALL blocks (sesoap.py:249-251), packed row out
+        // power spectrum: lanes over pairs (a <= b), all l of a pair from one pass over c_a, c_b;
+        // norm over ALL blocks (sesoap.py:249-251); packed row out
         double ss = 0.0;
-        for (int e = lane; e < dp.D; e += 32) {
-            const double q = pspec_entry(dp, c_s, ptab[e], nnlk[e]);
-            ss += q * q;
+        for (int pair = lane; pair < npairs; pair += 32) {
+            const unsigned w = ptab[pair * L];
+            const double* ca = c_s + (w & 0xff) * dp.L2p;
+            const double* cb = c_s + ((w >> 8) & 0xff) * dp.L2p;
+#pragma unroll
+            for (int l = 0; l <= LMAX; ++l) {
+                if (l <= dp.lmax) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int kk = l * l; kk < (l + 1) * (l + 1); ++kk) sum += ca[kk] * cb[kk];
+                    const double q = sum * nnlk[pair * L + l];
+                    ss += q * q;
+                    if (cache_q) buf[pair * L + l] = q;
+                }
+            }
         }
         ss = warp_sum(ss);
         const double P = dp.normalize ? (sqrt(ss) + kEps) : 1.0;
+        const double rP = 1.0 / P;
         const size_t row = (size_t)row_of[ENV ? env : c] * dp.ldp;
-        for (int e = lane; e < dp.ldp; e += 32)
-            phat[row + e] = (e < dp.D) ? pspec_entry(dp, c_s, ptab[e], nnlk[e]) / P : 0.0;
+        __syncwarp();
+        if (cache_q) {
+            for (int e = lane; e < dp.ldp; e += 32) phat[row + e] = (e < dp.D) ? buf[e] * rP : 0.0;
+        } else {
+            for (int e = lane; e < dp.ldp; e += 32)
+                phat[row + e] = (e < dp.D) ? pspec_entry(dp, c_s, ptab[e], nnlk[e]) * rP : 0.0;
+        }
         if (cbuf) {
             for (int t = lane; t < dp.csize; t += 32) cbuf[(size_t)env * dp.csize + t] = c_s[t];
             if (lane == 0) {
@@ -274,27 +302,32 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         const bool flag = sflag[env] != 0;
         double pg = 0.0;
         if (dp.normalize) {
+#pragma unroll 4
             for (int e = lane; e < dp.D; e += 32) pg += phat[row + e] * gvec[row + e];
             pg = warp_sum(pg);
         }
+#pragma unroll 4
         for (int e = lane; e < dp.D; e += 32) {
             const unsigned w = ptab[e];
             const double gq = gvec[row + e];
             const double dq = dp.normalize ? (gq - phat[row + e] * pg) / P : gq;
             T_s[e] = dq * nnlk[e] * (((w & 0xff) == ((w >> 8) & 0xff)) ? 2.0 : 1.0);
         }
+#pragma unroll 4
         for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
         __syncwarp();
-        // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm]
+        // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm],  tri(a,b) = rs(min) + |a-b|, rs(x) = x A - x(x-1)/2
         for (int o = lane; o < dp.A * dp.L2; o += 32) {
             const int a = o / dp.L2, lm = o - a * dp.L2;
-            const int l = c_l_of_lm[lm];
+            const double* Tl = T_s + c_l_of_lm[lm];
+            const double* cl = c_s + lm;
             double s = 0.0;
-            for (int b = 0; b < dp.A; ++b) {
-                const int lo = min(a, b), hi = max(a, b);
-                const int tri = lo * dp.A - (lo * (lo - 1)) / 2 + (hi - lo);
-                s += T_s[tri * L + l] * c_s[b * dp.L2p + lm];
+            int rs = 0;
+            for (int b = 0; b < a; ++b) {          // pairs (b, a), b < a
+                s += Tl[(rs + a - b) * L] * cl[b * dp.L2p];
+                rs += dp.A - b;
             }
+            for (int b = a; b < dp.A; ++b) s += Tl[(rs + b - a) * L] * cl[b * dp.L2p];   // pairs (a, b), rs == rs(a)
             D_s[a * dp.L2p + lm] = s;
         }
         __syncwarp();
@@ -422,6 +455,7 @@ struct Launch {
 };
 
 Launch plan_forward(const DescParams& dp, int stride) {
+    // c block + 32 neighbour rows + 32 species ints
     int per_warp = ((dp.csize + 1) & ~1) + 32 * stride + 16;
     int warps = 8;
     while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
@@ -434,25 +468,31 @@ Launch plan_backward(const DescParams& dp) {
     return {warps, (size_t)warps * per_warp * 8, per_warp};
 }
 
-template <int LMAX, int CPL, bool ENV>
+template <int LMAX, int TN, int TL, bool ENV>
 int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const int* row_of, double* phat,
                    double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
     const DescParams& dp = h->dp;
-    int stride = dp.nb + dp.L2;
+    // row of a neighbour in the chunk buffer: f padded to whole n tiles, Y padded to whole lm tiles
+    const int nbp = ((dp.nb + TN - 1) / TN) * TN;
+    int stride = nbp + ((dp.L2 + TL - 1) / TL) * TL;
     if ((stride & 1) == 0) stride += 1;  // odd stride: lanes writing their own row hit distinct banks
+    if (((dp.L2 + TL - 1) / TL) * ((dp.nb + TN - 1) / TN) > 32) {
+        set_error("internal: forward tile shape does not cover the components");
+        return SGPR_ERR_INVALID;
+    }
     Launch L = plan_forward(dp, stride);
     if ((size_t)L.per_warp * 8 > 200 * 1024) {
         set_error("descriptor too large for shared memory (S=%d nmax=%d lmax=%d)", dp.S, dp.nb - 1, dp.lmax);
         return SGPR_ERR_INVALID;
     }
-    auto kern = desc_forward_kernel<LMAX, CPL, ENV>;
+    auto kern = desc_forward_kernel<LMAX, TN, TL, ENV>;
     SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     int grid = (n_env + L.warps - 1) / L.warps;
     const int maxgrid = h->sm_count * 16;
     if (grid > maxgrid) grid = maxgrid;
     if (grid < 1) grid = 1;
     kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, row_of, h->ptab.as<unsigned>(), h->nnlk.as<double>(), phat,
-                                             cbuf, pnorm, sflag, L.per_warp, stride);
+                                             cbuf, pnorm, sflag, L.per_warp, stride, nbp);
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
@@ -461,16 +501,16 @@ int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src,
 template <bool ENV>
 int dispatch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const int* row_of, double* phat,
                      double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
-    const int lmax = h->dp.lmax, ncomp = h->dp.ncomp;
-    const int cpl = (ncomp + 31) / 32;
-#define FWD(LM, CP) return launch_forward<LM, CP, ENV>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st)
-    if (lmax <= 3 && cpl <= 2) FWD(3, 2);
-    if (lmax <= 3 && cpl <= 6) FWD(3, 6);
-    if (lmax <= 6 && cpl <= 8) FWD(6, 8);
-    if (lmax <= 6 && cpl <= 14) FWD(6, 14);
-    if (lmax <= 6 && cpl <= 19) FWD(6, 19);
-    if (lmax <= 8 && cpl <= 16) FWD(8, 16);
-    if (lmax <= 8 && cpl <= 31) FWD(8, 31);
+    const int lmax = h->dp.lmax, nb = h->dp.nb;
+    // (LMAX bucket, n-tile, lm-tile): ceil(L2/TL) * ceil(nb/TN) <= 32 lanes
+#define FWD(LM, TN, TL) return launch_forward<LM, TN, TL, ENV>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st)
+    if (lmax <= 3 && nb <= 4) FWD(3, 2, 1);
+    if (lmax <= 3 && nb <= 8) FWD(3, 4, 1);
+    if (lmax <= 3) FWD(3, 6, 1);
+    if (lmax <= 6 && nb <= 6) FWD(6, 2, 5);
+    if (lmax <= 6 && nb <= 9) FWD(6, 3, 5);
+    if (lmax <= 6) FWD(6, 4, 5);
+    if (lmax <= 8) FWD(8, 6, 6);
 #undef FWD
     set_error("unsupported descriptor size lmax=%d nmax=%d", lmax, h->dp.nb - 1);
     return SGPR_ERR_INVALID;

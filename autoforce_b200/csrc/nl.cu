@@ -367,12 +367,17 @@ __device__ __forceinline__ bool pair_test(const Geom& g, const AtomRec& ai, cons
     return __dsqrt_rn(d2) < g.rc;
 }
 
+constexpr int kMaskSlots = 64;
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, const int* __restrict__ active,
                                                        const AtomRec* __restrict__ atoms, const int* __restrict__ abin,
                                                        const int* __restrict__ cstart, Geom g, int S,
                                                        int* __restrict__ nl_cnt, const long long* __restrict__ nl_first,
-                                                       PairRec* __restrict__ pairs, unsigned char* __restrict__ mark) {
+                                                       PairRec* __restrict__ pairs, unsigned char* __restrict__ mark,
+                                                       unsigned* __restrict__ masks) {
+    // masks[env][slot]: accept bit-mask of candidate batch `slot`, written by the count pass and
+    // reused by the fill pass (same traversal), so that the distance tests run only once
     const int lane = threadIdx.x & 31;
     int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= n_env) return;
@@ -386,6 +391,8 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
     const int bx = bin / g.nb[1];
     int count[kMaxSpecies];
     long long base[kMaxSpecies];
+    int slot = 0;
+    unsigned* my_masks = masks + (size_t)wid * kMaskSlots;
 #pragma unroll
     for (int s = 0; s < kMaxSpecies; ++s) count[s] = 0;
     if (FILL) {
@@ -431,12 +438,20 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
                     const int p = p0 + lane;
                     bool acc = false;
                     int sp = 0;
-                    if (p < end) {
+                    if (FILL && slot < kMaskSlots) {
+                        acc = (my_masks[slot] >> lane) & 1u;
+                        if (acc) sp = meta_species(atoms[p].meta);
+                    } else if (p < end) {
                         const AtomRec aj = atoms[p];
                         sp = meta_species(aj.meta);
                         acc = pair_test(g, ai, aj, sx, sy, sz, p == c);
                         if (!FILL && mark && acc) mark[p] = 1;  // atoms whose environment the owner needs (halo)
                     }
+                    if (!FILL && slot < kMaskSlots) {
+                        const unsigned m_all = __ballot_sync(0xffffffffu, acc);
+                        if (lane == 0) my_masks[slot] = m_all;
+                    }
+                    ++slot;
 #pragma unroll
                     for (int s = 0; s < kMaxSpecies; ++s) {
                         if (s < S) {
@@ -481,7 +496,7 @@ static int launch_count(sgpr_context* h, int env0, int n_env, const Geom& g, uns
     const int nblk = (int)(((int64_t)n_env * 32 + T - 1) / T);
     neighbor_kernel<false><<<nblk, T, 0, st>>>(env0, n_env, h->active_all ? nullptr : h->active_list.as<int>(),
                                                h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->S,
-                                               h->nl_cnt.as<int>(), nullptr, nullptr, mark);
+                                               h->nl_cnt.as<int>(), nullptr, nullptr, mark, h->nl_masks.as<unsigned>());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
 }
@@ -524,7 +539,8 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
         const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
         neighbor_kernel<true><<<nblk, T, 0, st>>>(0, na, h->active_all ? nullptr : h->active_list.as<int>(),
                                                   h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, S,
-                                                  h->nl_cnt.as<int>(), first, h->nl_pairs.as<PairRec>(), nullptr);
+                                                  h->nl_cnt.as<int>(), first, h->nl_pairs.as<PairRec>(), nullptr,
+                                                  h->nl_masks.as<unsigned>());
     }
     h->stats.kernel_launches += 4;  // row totals, cub scan (2), fill
     SGPR_CUDA(cudaGetLastError());
@@ -539,6 +555,7 @@ int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, i
     h->active_all = true;
     h->n_active = N;
     SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * h->S + 1)));
+    SGPR_TRY(h->nl_masks.ensure(sizeof(unsigned) * kMaskSlots * ((size_t)N + 1)));
     SGPR_TRY(launch_count(h, 0, (int)N, g, nullptr, st));
     const int nkeys = g.ncell * h->S;
     const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
@@ -609,6 +626,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     SGPR_TRY(h->shard_tmp.ensure(sizeof(int) * (2 * ((size_t)N + 2) + SGPR_MAX_SPECIES + 2)));
     SGPR_TRY(h->row_owned.ensure((size_t)N + 1));
     SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * S + 1)));
+    SGPR_TRY(h->nl_masks.ensure(sizeof(unsigned) * kMaskSlots * ((size_t)N + 1)));
     unsigned char* owned = h->owned.as<unsigned char>();
     unsigned char* mark = owned + (N + 1);
     int* active = h->active_list.as<int>();

@@ -133,7 +133,7 @@ struct sgpr_context {
     sgpr::DevBuf errflag;     // [4] ints
     // ---- per-call workspaces (grow-only)
     sgpr::DevBuf cnt, cstart, rstart, keyrank, atoms, order, rowof, active_list, rowmap;
-    sgpr::DevBuf nl_cnt, nl_first, nl_pairs, scan_tmp;
+    sgpr::DevBuf nl_cnt, nl_first, nl_pairs, nl_masks, scan_tmp;
     sgpr::DevBuf owned, shard_tmp, row_owned;    // atom sharding: owned/mark masks, scans, per-row ownership
     sgpr::DevBuf phat, cbuf, pnorm, sflag, gmat, gvec, epart, wpart, fcell, misc;
     sgpr::DevBuf stage_pos, stage_z, stage_out;  // device staging for the host API

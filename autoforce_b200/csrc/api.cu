@@ -109,6 +109,37 @@ __global__ void beta_finish_kernel(int n_active, const int* __restrict__ active,
     }
 }
 
+// local energies e_r = sum of the per-(column tile, warp) partials written by the kernel-matrix
+// GEMM (fixed order -> reproducible); also block partial sums of the owned rows for the total.
+struct RowSpecies {
+    int row_first[SGPR_MAX_SPECIES + 1];
+    int n_part[SGPR_MAX_SPECIES];   // 0 where the species has no usable inducing points
+    int S;
+};
+__global__ void row_energy_kernel(int n_rows, RowSpecies rs, const double* __restrict__ part, int part_ld,
+                                  const unsigned char* __restrict__ row_owned, double* __restrict__ erow,
+                                  double* __restrict__ epart) {
+    __shared__ double red[256];
+    double tot = 0.0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        int np = 0;
+#pragma unroll
+        for (int s = 0; s < SGPR_MAX_SPECIES; ++s)
+            if (s < rs.S && r >= rs.row_first[s] && r < rs.row_first[s + 1]) np = rs.n_part[s];
+        double e = 0.0;
+        for (int p = 0; p < np; ++p) e += part[(size_t)p * part_ld + r];
+        erow[r] = e;
+        if (!row_owned || row_owned[r]) tot += e;
+    }
+    red[threadIdx.x] = tot;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) epart[blockIdx.x] = red[0];
+}
+
 __global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ atoms, const double* __restrict__ fcell,
                                       const unsigned char* __restrict__ owned, double* __restrict__ F,
                                       unsigned char* __restrict__ owned_out) {
@@ -368,6 +399,10 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
             }
         SGPR_TRY(upload(h->ptab, ptab.data(), sizeof(unsigned) * dp.D));
         SGPR_TRY(upload(h->nnlk, nnlk.data(), sizeof(double) * dp.D));
+        // chain-rule table of the back projection: dp/dc picks up kappa*nnl and a factor 2 on a == b
+        std::vector<double> ttab(dp.ldp, 0.0);
+        for (int e = 0; e < dp.D; ++e) ttab[e] = nnlk[e] * (((ptab[e] & 0xff) == ((ptab[e] >> 8) & 0xff)) ? 2.0 : 1.0);
+        SGPR_TRY(upload(h->ttab, ttab.data(), sizeof(double) * dp.ldp));
     }
 
     // inducing set, grouped by central species
@@ -491,7 +526,7 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -565,10 +600,21 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world));
     const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
     const int* active = h->active_all ? nullptr : h->active_list.as<int>();
-    const int grid_g = gemm_grid_size(h);
+    const int grid_g = 128;   // blocks (= energy partials) of row_energy_kernel
     const int nblk_b = backward_grid(h);
     const int nblk_x = 64;
     const size_t nrows = (size_t)h->n_active + 1;
+    RowSpecies rs{};
+    rs.S = h->S;
+    int max_part = 1;
+    for (int s = 0; s <= h->S; ++s) rs.row_first[s] = h->row_first[s];
+    for (int s = 0; s < h->S; ++s) {
+        const int Ms = h->m_first[s + 1] - h->m_first[s];
+        rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? gemm_energy_parts(Ms) : 0;
+        if (rs.n_part[s] > max_part) max_part = rs.n_part[s];
+    }
+    SGPR_TRY(h->erow_part.ensure(sizeof(double) * (size_t)max_part * nrows));
+    SGPR_TRY(h->erow.ensure(sizeof(double) * nrows));
     SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
     SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
     SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + nblk_x)));
@@ -579,6 +625,10 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
     if (beta_d) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
     SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
+    row_energy_kernel<<<grid_g, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows,
+                                              h->active_all ? nullptr : h->row_owned.as<unsigned char>(),
+                                              h->erow.as<double>(), h->epart.as<double>());
+    h->stats.kernel_launches += 1;
     SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
     SGPR_TRY(descriptor_backward_atoms(h, g, owned, st));
@@ -687,9 +737,12 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_forward(sgpr_h
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
     SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g));
-    const int grid_g = gemm_grid_size(h);
     SGPR_TRY(h->gmat.ensure(sizeof(double) * ((size_t)N + 1) * h->ldg));
-    SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + 64)));
+    {
+        int max_part = 1;
+        for (int s = 0; s < h->S; ++s) max_part = std::max(max_part, gemm_energy_parts(h->m_first[s + 1] - h->m_first[s]));
+        SGPR_TRY(h->erow_part.ensure(sizeof(double) * (size_t)max_part * ((size_t)N + 1)));
+    }
     SGPR_TRY(h->rowmap.ensure(sizeof(int) * ((size_t)N + 1)));
     SGPR_CUDA(cudaMemsetAsync(K_d, 0, sizeof(double) * (size_t)N * h->M, st));
     if (N > 0 && h->M > 0) {

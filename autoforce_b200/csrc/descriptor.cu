@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
                                                            const int* __restrict__ row_of,
                                                            const unsigned* __restrict__ ptab,
                                                            const double* __restrict__ nnlk, double* __restrict__ phat,
-                                                           double* __restrict__ cbuf, double* __restrict__ pnorm,
+                                                           double* __restrict__ cbuf, double* __restrict__ prow,
                                                            unsigned char* __restrict__ sflag, int per_warp_doubles,
                                                            int stride, int nbp) {
     extern __shared__ __align__(16) double smem[];
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         if (cbuf) {
             for (int t = lane; t < dp.csize; t += 32) cbuf[(size_t)env * dp.csize + t] = c_s[t];
             if (lane == 0) {
-                pnorm[env] = P;
+                prow[row_of[c]] = P;   // consumed by the back-projection epilogue (row order)
                 sflag[env] = flag ? 1 : 0;
             }
         }
@@ -272,12 +272,12 @@ struct BackOut {
 template <int LMAX, int NB>
 __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                             const int* __restrict__ row_of,
-                                                            const unsigned* __restrict__ ptab,
-                                                            const double* __restrict__ nnlk,
+                                                            const double* __restrict__ tvec,
                                                             const double* __restrict__ phat,
-                                                            const double* __restrict__ gvec,
+                                                            const double* __restrict__ ttab,
+                                                            const double* __restrict__ erow,
+                                                            const double* __restrict__ prow, double xi,
                                                             const double* __restrict__ cbuf,
-                                                            const double* __restrict__ pnorm,
                                                             const unsigned char* __restrict__ sflag, BackOut out,
                                                             int per_warp_doubles) {
     extern __shared__ __align__(16) double smem[];
@@ -298,21 +298,14 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         const long long beg = src.nl_first[env], end = src.nl_first[env + 1];
         if (end == beg || !out.sp_on[si]) continue;   // warp-uniform
         const size_t row = (size_t)row_of[c] * dp.ldp;
-        const double P = pnorm[env];
         const bool flag = sflag[env] != 0;
-        double pg = 0.0;
-        if (dp.normalize) {
+        // chain rule through the normalisation (sesoap.py:229-235): dE/dq = (g - q_hat (q_hat.g)) / P with
+        // q_hat.g = sum_m G_im k_im = xi e_i (the local energy from the kernel-matrix GEMM) -> no dot pass
+        const int r = row_of[c];
+        const double pg = dp.normalize ? xi * erow[r] : 0.0;
+        const double rP = dp.normalize ? 1.0 / prow[r] : 1.0;
 #pragma unroll 4
-            for (int e = lane; e < dp.D; e += 32) pg += phat[row + e] * gvec[row + e];
-            pg = warp_sum(pg);
-        }
-#pragma unroll 4
-        for (int e = lane; e < dp.D; e += 32) {
-            const unsigned w = ptab[e];
-            const double gq = gvec[row + e];
-            const double dq = dp.normalize ? (gq - phat[row + e] * pg) / P : gq;
-            T_s[e] = dq * nnlk[e] * (((w & 0xff) == ((w >> 8) & 0xff)) ? 2.0 : 1.0);
-        }
+        for (int e = lane; e < dp.D; e += 32) T_s[e] = (tvec[row + e] - phat[row + e] * pg) * rP * ttab[e];
 #pragma unroll 4
         for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
         __syncwarp();
@@ -528,8 +521,8 @@ int launch_backward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src
     auto kern = desc_backward_kernel<LMAX, NB>;
     SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, h->rowof.as<int>() + (h->last_N + 1),
-                                             h->ptab.as<unsigned>(), h->nnlk.as<double>(), h->phat.as<double>(),
-                                             h->gvec.as<double>(), h->cbuf.as<double>(), h->pnorm.as<double>(),
+                                             h->gvec.as<double>(), h->phat.as<double>(), h->ttab.as<double>(),
+                                             h->erow.as<double>(), h->prow.as<double>(), h->xi, h->cbuf.as<double>(),
                                              h->sflag.as<unsigned char>(), out, L.per_warp);
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
@@ -552,7 +545,7 @@ int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st) {
     const int na = (int)h->n_active;
     const DescParams& dp = h->dp;
     SGPR_TRY(h->cbuf.ensure(sizeof(double) * ((size_t)na * dp.csize + 1)));
-    SGPR_TRY(h->pnorm.ensure(sizeof(double) * ((size_t)na + 1)));
+    SGPR_TRY(h->prow.ensure(sizeof(double) * ((size_t)na + 1)));
     SGPR_TRY(h->sflag.ensure((size_t)na + 1));
     if (na == 0) return SGPR_OK;
     EnvSrc src{};
@@ -561,7 +554,7 @@ int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st) {
     src.nl_first = h->nl_first.as<long long>();
     src.active = h->active_all ? nullptr : h->active_list.as<int>();
     return dispatch_forward<false>(h, g, na, src, h->rowof.as<int>() + (h->last_N + 1), h->phat.as<double>(),
-                                   h->cbuf.as<double>(), h->pnorm.as<double>(), h->sflag.as<unsigned char>(), st);
+                                   h->cbuf.as<double>(), h->prow.as<double>(), h->sflag.as<unsigned char>(), st);
 }
 
 int backward_grid(sgpr_context* h) { return h->sm_count * 16; }

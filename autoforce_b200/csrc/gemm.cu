@@ -52,8 +52,8 @@ int launch_gemm(sgpr_context* h, GemmBatch& b, cudaStream_t st) {
 
 }  // namespace
 
-// upper bound of the kernel-matrix grid (size of the per-CTA energy partial array)
-int gemm_grid_size(sgpr_context* h) { return CfgK::MINB * h->sm_count; }
+// number of per-row energy partials written by the kernel-matrix GEMM for a species with Ms inducing points
+int gemm_energy_parts(int Ms) { return ((Ms + CfgK::BN - 1) / CfgK::BN) * CfgK::WN; }
 
 // Kernel-matrix GEMM, all central species in ONE grouped launch (rows h->row_first, inducing
 // points h->m_first).  Writes G (h->gmat, [n_rows, ldg]) and per-CTA energy partials into
@@ -82,8 +82,8 @@ int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_ma
         a.row_map = row_map_d ? row_map_d + r0 : nullptr;
         a.xi = h->xi;
         a.xi_int = h->xi_int;
-        a.epart = h->epart.as<double>();
-        a.row_owned = h->active_all ? nullptr : h->row_owned.as<unsigned char>() + r0;
+        a.erow_part = h->erow_part.as<double>() + r0;
+        a.erow_ld = (int)h->n_active + 1;
         a.Kc = store_kc ? h->kcmat.as<double>() + (size_t)r0 * h->ldg : nullptr;
         add_problem<CfgK>(b, a);
         h->stats.gemm_flops += 2.0 * a.M * (double)a.N * a.K;

@@ -24,8 +24,8 @@ struct GemmArgs {
     const int* row_map;  // [M] or nullptr
     double xi;
     int xi_int;        // xi if it is a small positive integer, else -1
-    double* epart;     // [gridDim.x] per-CTA energy partial (taken from problem 0)
-    const unsigned char* row_owned;  // [M] count this row's energy (atom sharding), nullptr = all
+    double* erow_part; // per-row energy partials: erow_part[(tile_n * WN + warp_n) * erow_ld + row]
+    int erow_ld;
     double* Kc;        // optional [M, ldg] <- k^xi in GEMM row/column order (input of the covloss GEMM)
     // epilogue 3 (covloss): per-row partial sums of squares, part[(tile_n * WN + warp_n) * part_ld + row]
     double* part;
@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < BK / 4; ++q) koff[q] = swz(gid, 2 * q + (tig >> 1)) * 2 + (tig & 1);
     const int n_tiles = batch.tile_start[batch.n_prob];
-    double e_acc = 0.0;
 
     for (int gtile = blockIdx.x; gtile < n_tiles; gtile += gridDim.x) {
         // problem (central species) of this tile; static unroll keeps the parameters in the constant bank
@@ -178,11 +177,12 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             const int r = row0 + wm * TM * 8 + i * 8 + gid;
-            if (r >= g.M) continue;
-            const double ew = (EPI == 1 && g.row_owned) ? (g.row_owned[r] ? 1.0 : 0.0) : 1.0;
+            const bool rv = r < g.M;   // no early exit: the quad shuffles below need every lane
+            double e_row = 0.0;   // EPI 1: sum_m mu_m k^xi over this warp's columns
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int c = col0 + wn * TN * 8 + j * 8 + 2 * tig;
+                if (!rv) continue;
                 if (EPI == 1) {
                     double v[2];
 #pragma unroll
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
                             const double pw = powm1(k, g.xi, g.xi_int);
                             const double m = g.mu[cc];
                             gv = g.xi * m * pw;
-                            e_acc += ew * (m * pw * k);
+                            e_row += m * pw * k;
                             if (g.Kmat) {
                                 const size_t kr = g.row_map ? (size_t)g.row_map[r] : (size_t)r;
                                 g.Kmat[kr * g.ldk + g.col_map[cc]] = pw * k;
@@ -218,6 +218,11 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
                     }
                 }
             }
+            if (EPI == 1) {
+                e_row += __shfl_xor_sync(0xffffffffu, e_row, 1);
+                e_row += __shfl_xor_sync(0xffffffffu, e_row, 2);
+                if (tig == 0 && rv) g.erow_part[(size_t)(tn * C::WN + wn) * g.erow_ld + r] = e_row;
+            }
         }
         if (EPI == 3) {
             // row-wise sum of squares of this warp's 8*TN columns, reduced over the quad
@@ -235,19 +240,6 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
                 ss += __shfl_xor_sync(0xffffffffu, ss, 2);
                 if (tig == 0 && r < g.M) g.part[(size_t)(tn * C::WN + wn) * g.part_ld + r] = ss;
             }
-        }
-    }
-    if (EPI == 1) {
-        // deterministic per-CTA reduction of the energy partials
-        __shared__ double red[NT / 32];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, o);
-        if (lane == 0) red[warp] = e_acc;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int w = 0; w < NT / 32; ++w) s += red[w];
-            batch.p[0].epart[blockIdx.x] = s;
         }
     }
 }

@@ -125,6 +125,8 @@ struct sgpr_context {
     sgpr::DevBuf vscale_d;    // [S] model._vscale (inf where unseen)
     sgpr::DevBuf clone_d;     // [S] c of a neighbour-less atom of species s
     sgpr::DevBuf kcmat, cpart;  // covloss: K^xi [rows, ldg], per-row partial sums of squares
+    sgpr::DevBuf erow_part, erow, prow;  // per-row energy partials / local energies / descriptor norms
+    sgpr::DevBuf ttab;          // [D] kappa*nnl*(1 + [a==b]) per packed entry
     sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
     sgpr::DevBuf ztab;        // [128] atomic number -> species
     sgpr::DevBuf ind_perm_d;  // [M]
@@ -174,7 +176,7 @@ int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, 
                        cudaStream_t st);
 
 // ---- gemm.cu ----------------------------------------------------------------------
-int gemm_grid_size(sgpr_context* h);
+int gemm_energy_parts(int Ms);
 int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st);
 int gemm_covloss_parts(sgpr_context* h);
 int gemm_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);

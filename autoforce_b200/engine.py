@@ -65,7 +65,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    path = path or library_path()
+    path = path or os.environ.get("SGPR_B200_LIB") or library_path()   # env override: A/B builds of the library
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -78,6 +78,20 @@ def main():
             traceback.print_exc()
 
 
+def box_speed():
+    """cuBLAS DGEMM 4096^3 as a box-speed indicator (boxes differ by several percent)."""
+    a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+    torch.matmul(a, a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        torch.matmul(a, a)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"box speed: cuBLAS DGEMM 4096^3 {5 * 2 * 4096**3 / e0.elapsed_time(e1) / 1e9:.2f} TFLOP/s", flush=True)
+
+
 def speed(workload="c2", steps=5):
     from autoforce_b200 import synth
 
@@ -112,6 +126,7 @@ def speed(workload="c2", steps=5):
 
 if __name__ == "__main__":
     main()
+    box_speed()
     for wl in os.environ.get("SPEED", "c2,c3").split(","):
         if wl:
             try:

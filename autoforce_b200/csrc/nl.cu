@@ -347,37 +347,70 @@ int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_
 // ---------------------------------------------------------------------------------
 // neighbour search: one warp per atom, lanes over the candidates of a bin run
 // ---------------------------------------------------------------------------------
+// exact image shift  ((S0*c0 + S1*c1) + S2*c2)  in the reference's rounding sequence (no FMA)
+__device__ __forceinline__ void shift_vec(const Geom& g, int S0, int S1, int S2, double& s0, double& s1, double& s2) {
+    const double a = (double)S0, b = (double)S1, c = (double)S2;
+    s0 = __dadd_rn(__dadd_rn(__dmul_rn(a, g.cell[0]), __dmul_rn(b, g.cell[3])), __dmul_rn(c, g.cell[6]));
+    s1 = __dadd_rn(__dadd_rn(__dmul_rn(a, g.cell[1]), __dmul_rn(b, g.cell[4])), __dmul_rn(c, g.cell[7]));
+    s2 = __dadd_rn(__dadd_rn(__dmul_rn(a, g.cell[2]), __dmul_rn(b, g.cell[5])), __dmul_rn(c, g.cell[8]));
+}
+
+// Accept/reject exactly as the reference:  sqrt(sum(r*r)) < rc  with  r = (x_j - x_i) + shift.
+// (sh0,sh1,sh2) is the shift of the bin run, valid when i and j carry the same wrap shift (the
+// common case); the square root is only evaluated when d^2 is within 1e-14 of rc^2, elsewhere
+// comparing squares gives the same answer.
 __device__ __forceinline__ bool pair_test(const Geom& g, const AtomRec& ai, const AtomRec& aj, int sx, int sy, int sz,
-                                          bool same) {
-    // image shift relative to the positions as given:  S = S_bin - w_j + w_i
-    const int S0 = sx - meta_w(aj.meta, 0) + meta_w(ai.meta, 0);
-    const int S1 = sy - meta_w(aj.meta, 1) + meta_w(ai.meta, 1);
-    const int S2 = sz - meta_w(aj.meta, 2) + meta_w(ai.meta, 2);
-    if (same && S0 == 0 && S1 == 0 && S2 == 0) return false;
-    // r = (x_j - x_i) + ((S0*c0 + S1*c1) + S2*c2), rounded like the reference (no FMA)
-    double r[3];
-    const double xj[3] = {aj.x, aj.y, aj.z}, xi[3] = {ai.x, ai.y, ai.z};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double sh = __dadd_rn(__dadd_rn(__dmul_rn((double)S0, g.cell[k]), __dmul_rn((double)S1, g.cell[3 + k])),
-                              __dmul_rn((double)S2, g.cell[6 + k]));
-        r[k] = __dadd_rn(__dadd_rn(xj[k], -xi[k]), sh);
+                                          double sh0, double sh1, double sh2, double rc2_lo, double rc2_hi, bool same) {
+    bool zero_shift = (sx | sy | sz) == 0;
+    if ((unsigned)(aj.meta >> 40) != (unsigned)(ai.meta >> 40)) {
+        // image shift relative to the positions as given:  S = S_bin - w_j + w_i
+        const int S0 = sx - meta_w(aj.meta, 0) + meta_w(ai.meta, 0);
+        const int S1 = sy - meta_w(aj.meta, 1) + meta_w(ai.meta, 1);
+        const int S2 = sz - meta_w(aj.meta, 2) + meta_w(ai.meta, 2);
+        zero_shift = (S0 | S1 | S2) == 0;
+        shift_vec(g, S0, S1, S2, sh0, sh1, sh2);
     }
-    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])), __dmul_rn(r[2], r[2]));
-    return __dsqrt_rn(d2) < g.rc;
+    if (same && zero_shift) return false;
+    const double rx = __dadd_rn(__dadd_rn(aj.x, -ai.x), sh0);
+    const double ry = __dadd_rn(__dadd_rn(aj.y, -ai.y), sh1);
+    const double rz = __dadd_rn(__dadd_rn(aj.z, -ai.z), sh2);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+    bool acc = d2 < rc2_lo;
+    if (!acc && d2 <= rc2_hi) acc = __dsqrt_rn(d2) < g.rc;
+    return acc;
+}
+
+// bin index n + periodic wrap -> (wrapped bin, image shift); false if outside a non-periodic box
+__device__ __forceinline__ bool wrap_bin(int n, int nb, int pbc, int& nw, int& sh) {
+    sh = 0;
+    nw = n;
+    if (pbc) {
+        while (nw < 0) {
+            nw += nb;
+            --sh;
+        }
+        while (nw >= nb) {
+            nw -= nb;
+            ++sh;
+        }
+        return true;
+    }
+    return n >= 0 && n < nb;
 }
 
 constexpr int kMaskSlots = 64;
 
-template <bool FILL>
+// One warp per environment.  COUNT pass: distance tests, per-species counts (packed 16-bit
+// per-lane counters, one warp reduction at the end), accept masks per candidate batch and halo
+// marks.  FILL pass: replays the traversal, takes the accept bits from the masks and writes the
+// pairs species-sorted (per-species ballots give each accepted candidate its rank).
+template <bool FILL, int NS>
 __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, const int* __restrict__ active,
                                                        const AtomRec* __restrict__ atoms, const int* __restrict__ abin,
                                                        const int* __restrict__ cstart, Geom g, int S,
                                                        int* __restrict__ nl_cnt, const long long* __restrict__ nl_first,
                                                        PairRec* __restrict__ pairs, unsigned char* __restrict__ mark,
                                                        unsigned* __restrict__ masks) {
-    // masks[env][slot]: accept bit-mask of candidate batch `slot`, written by the count pass and
-    // reused by the fill pass (same traversal), so that the distance tests run only once
     const int lane = threadIdx.x & 31;
     int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= n_env) return;
@@ -389,51 +422,47 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
     bin /= g.nb[2];
     const int by = bin % g.nb[1];
     const int bx = bin / g.nb[1];
-    int count[kMaxSpecies];
-    long long base[kMaxSpecies];
+    int count[NS];
+    long long base[NS];
+    unsigned long long pc0 = 0ull, pc1 = 0ull;   // COUNT: packed per-lane counters, 16 bits per species
     int slot = 0;
     unsigned* my_masks = masks + (size_t)wid * kMaskSlots;
+    const double rc2 = g.rc * g.rc;
+    const double rc2_lo = rc2 * (1.0 - 1e-14), rc2_hi = rc2 * (1.0 + 1e-14);
 #pragma unroll
-    for (int s = 0; s < kMaxSpecies; ++s) count[s] = 0;
+    for (int s = 0; s < NS; ++s) count[s] = 0;
     if (FILL) {
         long long o = nl_first[wid];
 #pragma unroll
-        for (int s = 0; s < kMaxSpecies; ++s) {
+        for (int s = 0; s < NS; ++s) {
             base[s] = o;
             if (s < S) o += nl_cnt[(long long)wid * S + s];
         }
     }
     for (int dx = -g.reach[0]; dx <= g.reach[0]; ++dx) {
-        int nx = bx + dx, sx = 0;
-        if (g.pbc[0]) {
-            sx = (nx >= 0) ? nx / g.nb[0] : -((-nx + g.nb[0] - 1) / g.nb[0]);
-            nx -= sx * g.nb[0];
-        } else if (nx < 0 || nx >= g.nb[0]) continue;
+        int nx, sx;
+        if (!wrap_bin(bx + dx, g.nb[0], g.pbc[0], nx, sx)) continue;
         for (int dy = -g.reach[1]; dy <= g.reach[1]; ++dy) {
-            int ny = by + dy, sy = 0;
-            if (g.pbc[1]) {
-                sy = (ny >= 0) ? ny / g.nb[1] : -((-ny + g.nb[1] - 1) / g.nb[1]);
-                ny -= sy * g.nb[1];
-            } else if (ny < 0 || ny >= g.nb[1]) continue;
+            int ny, sy;
+            if (!wrap_bin(by + dy, g.nb[1], g.pbc[1], ny, sy)) continue;
             // z bins of this (x,y) column: contiguous in cell order -> one merged run when the
             // stencil does not wrap (or leave the box) inside the column
             const int zlo = bz - g.reach[2], zhi = bz + g.reach[2];
             const bool merged = (zlo >= 0 && zhi < g.nb[2]);
             for (int dz = merged ? 0 : -g.reach[2]; dz <= (merged ? 0 : g.reach[2]); ++dz) {
-                int nz = bz + dz, sz = 0, nz_last;
+                int nz, sz = 0, nz_last;
                 if (merged) {
                     nz = zlo;
                     nz_last = zhi;
                 } else {
-                    if (g.pbc[2]) {
-                        sz = (nz >= 0) ? nz / g.nb[2] : -((-nz + g.nb[2] - 1) / g.nb[2]);
-                        nz -= sz * g.nb[2];
-                    } else if (nz < 0 || nz >= g.nb[2]) continue;
+                    if (!wrap_bin(bz + dz, g.nb[2], g.pbc[2], nz, sz)) continue;
                     nz_last = nz;
                 }
                 const int b2 = (nx * g.nb[1] + ny) * g.nb[2] + nz;
                 const int b3 = (nx * g.nb[1] + ny) * g.nb[2] + nz_last;
                 const int beg = cstart[b2 * S], end = cstart[b3 * S + S];
+                double sh0 = 0.0, sh1 = 0.0, sh2 = 0.0;
+                if (!FILL) shift_vec(g, sx, sy, sz, sh0, sh1, sh2);
                 for (int p0 = beg; p0 < end; p0 += 32) {
                     const int p = p0 + lane;
                     bool acc = false;
@@ -444,41 +473,68 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
                     } else if (p < end) {
                         const AtomRec aj = atoms[p];
                         sp = meta_species(aj.meta);
-                        acc = pair_test(g, ai, aj, sx, sy, sz, p == c);
-                        if (!FILL && mark && acc) mark[p] = 1;  // atoms whose environment the owner needs (halo)
+                        if (FILL) shift_vec(g, sx, sy, sz, sh0, sh1, sh2);   // rare: more than kMaskSlots batches
+                        acc = pair_test(g, ai, aj, sx, sy, sz, sh0, sh1, sh2, rc2_lo, rc2_hi, p == c);
                     }
-                    if (!FILL && slot < kMaskSlots) {
-                        const unsigned m_all = __ballot_sync(0xffffffffu, acc);
-                        if (lane == 0) my_masks[slot] = m_all;
-                    }
-                    ++slot;
+                    if (!FILL) {
+                        if (acc) {
+                            if (mark) mark[p] = 1;   // atoms whose environment the owner needs (halo)
+                            const unsigned long long one = 1ull << (16 * (sp & 3));
+                            if (NS <= 4 || sp < 4) pc0 += one;
+                            else pc1 += one;
+                        }
+                        if (slot < kMaskSlots) {
+                            const unsigned m_all = __ballot_sync(0xffffffffu, acc);
+                            if (lane == 0) my_masks[slot] = m_all;
+                        }
+                    } else {
 #pragma unroll
-                    for (int s = 0; s < kMaxSpecies; ++s) {
-                        if (s < S) {
+                        for (int s = 0; s < NS; ++s) {
                             const unsigned m = __ballot_sync(0xffffffffu, acc && sp == s);
-                            if (FILL) {
-                                if (acc && sp == s) {
-                                    PairRec pr;
-                                    pr.j = p;
-                                    pr.sb[0] = (signed char)sx;
-                                    pr.sb[1] = (signed char)sy;
-                                    pr.sb[2] = (signed char)sz;
-                                    pr.sp = (unsigned char)sp;
-                                    pairs[base[s] + count[s] + __popc(m & ((1u << lane) - 1u))] = pr;
-                                }
+                            if (acc && sp == s) {
+                                PairRec pr;
+                                pr.j = p;
+                                pr.sb[0] = (signed char)sx;
+                                pr.sb[1] = (signed char)sy;
+                                pr.sb[2] = (signed char)sz;
+                                pr.sp = (unsigned char)sp;
+                                pairs[base[s] + count[s] + __popc(m & ((1u << lane) - 1u))] = pr;
                             }
                             count[s] += __popc(m);
                         }
                     }
+                    ++slot;
                 }
             }
         }
     }
-    if (!FILL && lane == 0) {
+    if (!FILL) {
+        // warp sums of the packed counters (each species total < 65536)
 #pragma unroll
-        for (int s = 0; s < kMaxSpecies; ++s)
-            if (s < S) nl_cnt[(long long)wid * S + s] = count[s];
+        for (int o = 16; o > 0; o >>= 1) {
+            pc0 += __shfl_xor_sync(0xffffffffu, pc0, o);
+            if (NS > 4) pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (s < S) nl_cnt[(long long)wid * S + s] = (int)(((s < 4 ? pc0 : pc1) >> (16 * (s & 3))) & 0xffffull);
+        }
     }
+}
+
+template <bool FILL>
+static void launch_neighbor(int nblk, int T, cudaStream_t st, int S, int env0, int n_env, const int* active,
+                            const AtomRec* atoms, const int* abin, const int* cstart, const Geom& g, int* nl_cnt,
+                            const long long* nl_first, PairRec* pairs, unsigned char* mark, unsigned* masks) {
+    if (S <= 1)
+        neighbor_kernel<FILL, 1><<<nblk, T, 0, st>>>(env0, n_env, active, atoms, abin, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks);
+    else if (S <= 2)
+        neighbor_kernel<FILL, 2><<<nblk, T, 0, st>>>(env0, n_env, active, atoms, abin, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks);
+    else if (S <= 4)
+        neighbor_kernel<FILL, 4><<<nblk, T, 0, st>>>(env0, n_env, active, atoms, abin, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks);
+    else
+        neighbor_kernel<FILL, 8><<<nblk, T, 0, st>>>(env0, n_env, active, atoms, abin, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks);
 }
 
 __global__ void row_total_kernel(int n, int S, const int* __restrict__ nl_cnt, long long* __restrict__ tot) {
@@ -494,9 +550,9 @@ static int launch_count(sgpr_context* h, int env0, int n_env, const Geom& g, uns
     if (n_env <= 0) return SGPR_OK;
     const int T = 256;
     const int nblk = (int)(((int64_t)n_env * 32 + T - 1) / T);
-    neighbor_kernel<false><<<nblk, T, 0, st>>>(env0, n_env, h->active_all ? nullptr : h->active_list.as<int>(),
-                                               h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->S,
-                                               h->nl_cnt.as<int>(), nullptr, nullptr, mark, h->nl_masks.as<unsigned>());
+    launch_neighbor<false>(nblk, T, st, h->S, env0, n_env, h->active_all ? nullptr : h->active_list.as<int>(),
+                           h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->nl_cnt.as<int>(), nullptr,
+                           nullptr, mark, h->nl_masks.as<unsigned>());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
 }
@@ -537,10 +593,9 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
     SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
     if (na > 0) {
         const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
-        neighbor_kernel<true><<<nblk, T, 0, st>>>(0, na, h->active_all ? nullptr : h->active_list.as<int>(),
-                                                  h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, S,
-                                                  h->nl_cnt.as<int>(), first, h->nl_pairs.as<PairRec>(), nullptr,
-                                                  h->nl_masks.as<unsigned>());
+        launch_neighbor<true>(nblk, T, st, S, 0, na, h->active_all ? nullptr : h->active_list.as<int>(),
+                              h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->nl_cnt.as<int>(), first,
+                              h->nl_pairs.as<PairRec>(), nullptr, h->nl_masks.as<unsigned>());
     }
     h->stats.kernel_launches += 4;  // row totals, cub scan (2), fill
     SGPR_CUDA(cudaGetLastError());

@@ -285,6 +285,26 @@ def main():
             "stages_ms_per_step": {k[3:]: stage[k] / K for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total")},
             "pairs": int(stage.get("n_pairs", 0)), "active_envs_rank0": int(stage.get("n_active", 0)),
         }
+        if world == 1:
+            # covloss (calculator/active.py:781-804) runs every prediction step in the reference but is not part
+            # of the metric: reported separately, same structure, model with choli = 0.5 I
+            try:
+                model_c = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli=True)
+                eng_c = ab.SgprEngine(model_c, species=w["Zs"], device=local_rank)
+                eng_c.enable_timing(True)
+                tb, fl = [], 0.0
+                for it in range(4):
+                    eng_c.predict(pos_variants[it % len(pos_variants)], numbers, cell, pbc, want_beta=True)
+                    st_c = eng_c.stats()
+                    if it > 0:
+                        tb.append(st_c["ms_beta"])
+                        fl = st_c["covloss_flops"]
+                eng_c.close()
+                mb = sum(tb) / len(tb)
+                line["covloss"] = {"ms_per_step": mb, "tflops": fl / (mb * 1e-3) / 1e12, "flops_per_step": fl,
+                                   "note": "extra device time per step when beta is requested; FP64 DMMA GEMM K.choli^T + row sum of squares"}
+            except Exception as ex:  # pragma: no cover
+                line["covloss"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle.cpu_bench import CpuBench

@@ -509,6 +509,19 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         delete h;
         return st;
     }
+    {   // GEMM engine: tcgen05 int8-sliced (default, needs normalised descriptors) or FP64 DMMA
+        const char* eng = getenv("SGPR_GEMM");
+        const char* trs = getenv("SGPR_I8_TR");
+        h->use_i8 = dp.normalize && !(eng && strcmp(eng, "dmma") == 0);
+        h->i8_tr = (trs && atoi(trs) == 8) ? 8 : 7;
+        if (h->use_i8) {
+            st = i8_prepare_model(h, false);
+            if (st != SGPR_OK) {
+                delete h;
+                return st;
+            }
+        }
+    }
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.d_packed = dp.D;
     h->stats.d_full = dp.A * dp.A * L;
@@ -526,9 +539,10 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (int i = 0; i < 6; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -543,14 +557,18 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
     }
     SGPR_CUDA(cudaSetDevice(h->device));
     SGPR_CUDA(cudaDeviceSynchronize());
-    return upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr);
+    SGPR_TRY(upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr));
+    if (mu_h && h->use_i8) SGPR_TRY(i8_prepare_model(h, true));
+    return SGPR_OK;
 }
 
 // =====================================================================================
 // pipeline
 // =====================================================================================
 static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
-                       const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1) {
+                       const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false) {
+    h->use_i8_now = i8 && h->use_i8;
+    h->stats.i8_ops = 0.0;
     // geometry -> cell sort -> neighbour list -> descriptors (rows in species-major order)
     if (N < 0 || N > 0x7fffff00ll) {
         set_error("bad atom count");
@@ -574,6 +592,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     h->stats.n_pairs = n_pairs;
     if (h->timing) cudaEventRecord(h->ev[1], st);
     SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)h->n_active + 1) * h->dp.ldp));
+    if (h->use_i8_now) SGPR_TRY(i8_ensure_step_buffers(h, (size_t)h->n_active));
     SGPR_TRY(descriptor_forward_atoms(h, *g, st));
     if (h->timing) cudaEventRecord(h->ev[2], st);
     return SGPR_OK;
@@ -597,7 +616,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
-    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world));
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/beta_d == nullptr));
     const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
     const int* active = h->active_all ? nullptr : h->active_list.as<int>();
     const int grid_g = 128;   // blocks (= energy partials) of row_energy_kernel
@@ -610,12 +629,12 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     for (int s = 0; s <= h->S; ++s) rs.row_first[s] = h->row_first[s];
     for (int s = 0; s < h->S; ++s) {
         const int Ms = h->m_first[s + 1] - h->m_first[s];
-        rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? gemm_energy_parts(Ms) : 0;
+        rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? (h->use_i8_now ? i8_energy_parts(Ms) : gemm_energy_parts(Ms)) : 0;
         if (rs.n_part[s] > max_part) max_part = rs.n_part[s];
     }
     SGPR_TRY(h->erow_part.ensure(sizeof(double) * (size_t)max_part * nrows));
     SGPR_TRY(h->erow.ensure(sizeof(double) * nrows));
-    SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
+    if (!h->use_i8_now) SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
     SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
     SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + nblk_x)));
     SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
@@ -624,12 +643,18 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
     SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
     if (beta_d) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
-    SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
+    if (h->use_i8_now)
+        SGPR_TRY(i8_kernel_matrix(h, st));
+    else
+        SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
     row_energy_kernel<<<grid_g, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows,
                                               h->active_all ? nullptr : h->row_owned.as<unsigned char>(),
                                               h->erow.as<double>(), h->epart.as<double>());
     h->stats.kernel_launches += 1;
-    SGPR_TRY(gemm_back_projection(h, st));
+    if (h->use_i8_now)
+        SGPR_TRY(i8_back_projection(h, st));
+    else
+        SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
     SGPR_TRY(descriptor_backward_atoms(h, g, owned, st));
     if (N > 0) {
@@ -680,6 +705,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
 static int ensure_pinned(sgpr_context* h, size_t bytes) {
     if (bytes <= h->pinned_bytes) return SGPR_OK;
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
     h->pinned = nullptr;
     h->pinned_bytes = 0;
     SGPR_CUDA(cudaMallocHost(&h->pinned, bytes + bytes / 4));

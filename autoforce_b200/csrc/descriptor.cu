@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
                                                            const double* __restrict__ nnlk, double* __restrict__ phat,
                                                            double* __restrict__ cbuf, double* __restrict__ prow,
                                                            unsigned char* __restrict__ sflag, int per_warp_doubles,
-                                                           int stride, int nbp) {
+                                                           int stride, int nbp, signed char* __restrict__ p8,
+                                                           long long p8_slice, int kp1) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* c_s = smem + (size_t)warp * per_warp_doubles;
@@ -247,6 +248,29 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         } else {
             for (int e = lane; e < dp.ldp; e += 32)
                 phat[row + e] = (e < dp.D) ? pspec_entry(dp, c_s, ptab[e], nnlk[e]) * rP : 0.0;
+        }
+        if (p8) {
+            // operand of the tcgen05 kernel-matrix GEMM: 6 balanced base-256 digits of q_hat * 2^46,
+            // slice-major, 4 consecutive entries (one 32-bit store per slice) per lane
+            const long long prow = (long long)row_of[ENV ? env : c] * kp1;
+            for (int e4 = lane * 4; e4 < dp.D; e4 += 128) {
+                unsigned packed[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e4 + q;
+                    double x = 0.0;
+                    if (e < dp.D) x = (cache_q ? buf[e] : pspec_entry(dp, c_s, ptab[e], nnlk[e])) * rP;
+                    long long v = __double2ll_rn(x * 70368744177664.0);   // 2^46
+#pragma unroll
+                    for (int t = 5; t >= 0; --t) {
+                        const int dg = (int)((v + 128) & 255) - 128;
+                        packed[t] |= (unsigned)(dg & 255) << (8 * q);
+                        v = (v - dg) >> 8;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 6; ++t) *reinterpret_cast<unsigned*>(p8 + (long long)t * p8_slice + prow + e4) = packed[t];
+            }
         }
         if (cbuf) {
             for (int t = lane; t < dp.csize; t += 32) cbuf[(size_t)env * dp.csize + t] = c_s[t];
@@ -485,7 +509,9 @@ int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src,
     if (grid > maxgrid) grid = maxgrid;
     if (grid < 1) grid = 1;
     kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, row_of, h->ptab.as<unsigned>(), h->nnlk.as<double>(), phat,
-                                             cbuf, pnorm, sflag, L.per_warp, stride, nbp);
+                                             cbuf, pnorm, sflag, L.per_warp, stride, nbp,
+                                             (!ENV && h->use_i8_now) ? h->p8.as<signed char>() : nullptr,
+                                             (long long)h->i8_cap_rows * h->i8_kp1, h->i8_kp1);
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SGPR_OK;

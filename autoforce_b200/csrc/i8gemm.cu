@@ -1,0 +1,307 @@
+// The two hot GEMMs of the prediction path on the 5th-generation tensor cores (tcgen05 + TMEM + TMA):
+// float64-accurate through int8 digit slicing with exact int32 accumulation (i8gemm_kernel.cuh).
+//
+//   (1) kernel matrix   k[i,m] = q_hat_i . z_hat_m   (similarity/universal.py:109-122), epilogue:
+//         e_i partials  sum_m mu_m k^xi               (calculator/active.py:548-550)
+//         A2 = digits of k^(xi-1)                      (operand of the back projection)
+//   (2) back projection g[i,:] = mumax * sum_m k^(xi-1)[i,m] * (xi mu_m z_hat_m / mumax)
+//       = dE_i/dq_hat_i  (autograd through universal.py:121 in calculator/active.py:587-599)
+//
+// Operands: q_hat digits are written by the descriptor kernel, z_hat digits at sgpr_create,
+// (xi mu z_hat^T / mumax) digits at sgpr_create / sgpr_set_weights.  All |values| <= 1 because the
+// descriptors are normalised (|k| <= 1 by Cauchy-Schwarz); un-normalised models use the DMMA path.
+#include <math.h>
+
+#include "i8gemm_kernel.cuh"
+#include "sgpr_internal.cuh"
+
+namespace sgpr {
+
+using namespace i8g;
+
+namespace {
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+
+int make_map(CUtensorMap* m, const void* base, int ns, long long rows, int Kpad, long long slice_stride_rows, int box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available");
+            return SGPR_ERR_CUDA;
+        }
+        g_encode = (EncodeFn)fn;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)(rows > 0 ? rows : 1), (cuuint64_t)ns};
+    cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)slice_stride_rows * Kpad};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)ns};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld K=%d", (int)r, rows, Kpad);
+        return SGPR_ERR_CUDA;
+    }
+    return SGPR_OK;
+}
+
+// balanced base-256 digits of x * 2^(8 ns - 2), most significant first
+template <int NS>
+__device__ __forceinline__ void digits(double x, signed char* d) {
+    long long v = __double2ll_rn(x * (double)(1ll << (8 * NS - 2)));
+#pragma unroll
+    for (int t = NS - 1; t >= 0; --t) {
+        const int dg = (int)((v + 128) & 255) - 128;
+        d[t] = (signed char)dg;
+        v = (v - dg) >> 8;
+    }
+}
+
+// float64 rows -> digit slices:  out[t][r][k] for r < rows, k < K ; zero for K <= k < Kpad
+template <int NS>
+__global__ void slice_rows_kernel(const double* __restrict__ X, long long ldx, int rows, int K, int Kpad, double scale,
+                                  const double* __restrict__ col_scale, signed char* __restrict__ out,
+                                  long long slice_stride) {
+    const long long total = (long long)rows * Kpad;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / Kpad), k = (int)(idx - (long long)r * Kpad);
+        signed char d[NS];
+        double x = 0.0;
+        if (k < K) x = X[(long long)r * ldx + k] * scale * (col_scale ? col_scale[k] : 1.0);
+        digits<NS>(x, d);
+#pragma unroll
+        for (int t = 0; t < NS; ++t) out[(long long)t * slice_stride + (long long)r * Kpad + k] = d[t];
+    }
+}
+
+constexpr int kNS = 6;
+
+struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
+    const double* mu[kMaxSpecies];       // per problem: mu of the species' inducing block
+    double* erow_part[kMaxSpecies];      // + r0
+    signed char* g8[kMaxSpecies];        // + r0 * Mp   (slice 0)
+    int erow_ld;
+    int Mp;
+    long long g8_slice;                  // bytes between slices
+    double xi;
+    int xi_int;
+    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+        if (row >= M) return;
+        signed char dg[kNS][16];
+        double e = 0.0;
+        const double* mup = mu[p];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = col0 + j;
+            double pw = 0.0;
+            if (c < N) {
+                const double k = v[j];
+                if (xi_int >= 1) {
+                    pw = 1.0;
+                    for (int t = 1; t < xi_int; ++t) pw *= k;
+                } else {
+                    pw = pow(k, xi - 1.0);
+                }
+                e += mup[c] * pw * k;
+            }
+            signed char d[kNS];
+            digits<kNS>(pw, d);
+#pragma unroll
+            for (int t = 0; t < kNS; ++t) dg[t][j] = d[t];
+        }
+        // one 16-byte store per slice (columns beyond N get zero digits: the K padding of GEMM 2)
+        if (col0 < Mp) {
+#pragma unroll
+            for (int t = 0; t < kNS; ++t)
+                *reinterpret_cast<int4*>(g8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) =
+                    *reinterpret_cast<const int4*>(dg[t]);
+        }
+        // energy partial of this 16-column chunk: accumulated per (column tile) by the 4 chunk calls
+        double* ep = erow_part[p] + (long long)(col0 >> 4) * erow_ld + row;
+        *ep = e;
+    }
+};
+
+struct Epi2 {   // back projection: g = mumax * C
+    double* gvec[kMaxSpecies];           // + r0 * ldp
+    int ldp;
+    double mumax;
+    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+        if (row >= M) return;
+        double* dst = gvec[p] + (long long)row * ldp + col0;
+        if (col0 + 16 <= N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(v[j] * mumax, v[j + 1] * mumax);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < N) dst[j] = v[j] * mumax;
+        }
+    }
+};
+
+template <int TR, class Epi>
+int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
+    constexpr int STAGES = 3;
+    auto kern = i8gemm_kernel<kNS, TR, STAGES, Epi>;
+    const size_t smem = smem_bytes<kNS, STAGES>();
+    static bool attr_done[2][16] = {};
+    bool& done = attr_done[sizeof(Epi) == sizeof(Epi1) ? 0 : 1][TR];
+    if (!done) {
+        SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    int grid = h->sm_count;
+    if (cm.tile_start[cm.n_prob] < grid) grid = cm.tile_start[cm.n_prob];
+    if (grid < 1) return SGPR_OK;
+    kern<<<grid, NTHREADS, smem, st>>>(cm, probs_d, epi);
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
+}  // namespace
+
+int i8_energy_parts(int Ms) { return ((Ms + BN - 1) / BN) * (BN / 16); }
+
+// digit slices of the static operands: z_hat (GEMM 1) and xi mu z_hat^T / mumax (GEMM 2)
+int i8_prepare_model(sgpr_context* h, bool weights_only) {
+    const DescParams& dp = h->dp;
+    const int M = h->M, S = h->S;
+    h->i8_kp1 = (dp.D + 63) / 64 * 64;
+    int maxMs = 0;
+    for (int s = 0; s < S; ++s) maxMs = std::max(maxMs, h->m_first[s + 1] - h->m_first[s]);
+    h->i8_mp = std::max(64, (maxMs + 63) / 64 * 64);
+    if (M == 0) return SGPR_OK;
+    if (!weights_only) {
+        SGPR_TRY(h->z8.ensure((size_t)kNS * M * h->i8_kp1 + 64));
+        slice_rows_kernel<kNS><<<h->sm_count * 4, 256>>>(h->zhat.as<double>(), dp.ldp, M, dp.D, h->i8_kp1, 1.0, nullptr,
+                                                         h->z8.as<signed char>(), (long long)M * h->i8_kp1);
+        SGPR_CUDA(cudaGetLastError());
+    }
+    // mumax: power of two >= max_m xi |mu_m|
+    double mx = 0.0;
+    for (double m : h->mu_host) mx = std::max(mx, std::fabs(h->xi * m));
+    h->i8_mumax = mx > 0 ? std::ldexp(1.0, (int)std::ceil(std::log2(mx))) : 1.0;
+    // per species: rows e of zhat_t [D, ld_zt], columns m scaled by xi mu_m / mumax
+    SGPR_TRY(h->zt8.ensure((size_t)S * kNS * dp.D * h->i8_mp + 64));
+    SGPR_CUDA(cudaMemset(h->zt8.p, 0, (size_t)S * kNS * dp.D * h->i8_mp));
+    std::vector<double> cs(M + 1, 0.0);
+    for (int p = 0; p < M; ++p) cs[p] = h->xi * h->mu_host[h->ind_perm[p]] / h->i8_mumax;
+    SGPR_TRY(h->misc.ensure(sizeof(double) * (M + 1)));
+    SGPR_CUDA(cudaMemcpy(h->misc.p, cs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
+    for (int s = 0; s < S; ++s) {
+        const int m0 = h->m_first[s], Ms = h->m_first[s + 1] - m0;
+        if (Ms == 0) continue;
+        slice_rows_kernel<kNS><<<h->sm_count * 4, 256>>>(h->zhat_t.as<double>() + h->zt_off[s], h->ld_zt, dp.D, Ms, h->i8_mp, 1.0,
+                                                         h->misc.as<double>() + m0,
+                                                         h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp,
+                                                         (long long)dp.D * h->i8_mp);
+        SGPR_CUDA(cudaGetLastError());
+    }
+    SGPR_CUDA(cudaDeviceSynchronize());
+    return SGPR_OK;
+}
+
+// buffers written by the descriptor kernel (q_hat digits) and by GEMM 1 (k^(xi-1) digits)
+int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows) {
+    const size_t cap = n_rows + 1;
+    if (cap > h->i8_cap_rows) {
+        const size_t c = cap + cap / 4;
+        SGPR_TRY(h->p8.ensure((size_t)kNS * c * h->i8_kp1 + 64));
+        SGPR_TRY(h->g8.ensure((size_t)kNS * c * h->i8_mp + 64));
+        // pad columns of p8 (D <= k < Kp1) are never written by the descriptor kernel: keep them zero
+        SGPR_CUDA(cudaMemset(h->p8.p, 0, (size_t)kNS * c * h->i8_kp1));
+        h->i8_cap_rows = c;
+    }
+    return SGPR_OK;
+}
+
+static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Problem>& probs, int* prob_species) {
+    const DescParams& dp = h->dp;
+    cm = Common{};
+    probs.clear();
+    for (int s = 0; s < h->S; ++s) {
+        const int r0 = h->row_first[s], r1 = h->row_first[s + 1];
+        const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
+        if (r1 == r0 || m1 == m0 || !dp.central_enabled[s]) continue;
+        Problem P;
+        if (which == 1) {
+            P.M = r1 - r0;
+            P.N = m1 - m0;
+            P.Kpad = h->i8_kp1;
+            SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>() + (size_t)r0 * h->i8_kp1, kNS, P.M, P.Kpad, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * h->i8_kp1, kNS, P.N, P.Kpad, (long long)h->M, BN));
+        } else {
+            P.M = r1 - r0;
+            P.N = dp.D;
+            P.Kpad = ((m1 - m0) + 63) / 64 * 64;
+            SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, kNS, dp.D, h->i8_mp, (long long)dp.D, BN));
+        }
+        prob_species[cm.n_prob] = s;
+        cm.tile_start[cm.n_prob + 1] = cm.tile_start[cm.n_prob] + ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN);
+        cm.n_prob++;
+        probs.push_back(P);
+        const int npairs = h->i8_tr == 8 ? 26 : 21;
+        h->stats.gemm_flops += 2.0 * P.M * (double)P.N * (which == 1 ? dp.D : (m1 - m0));
+        h->stats.i8_ops += 2.0 * P.M * (double)P.N * P.Kpad * npairs;
+    }
+    return SGPR_OK;
+}
+
+static int upload_problems(sgpr_context* h, int slot, const std::vector<Problem>& probs, cudaStream_t st, const Problem** out) {
+    SGPR_TRY(h->i8_probs.ensure(sizeof(Problem) * 2 * kMaxSpecies));
+    if (!h->i8_probs_pinned) SGPR_CUDA(cudaMallocHost(&h->i8_probs_pinned, sizeof(Problem) * 2 * kMaxSpecies));
+    Problem* pin = (Problem*)h->i8_probs_pinned + slot * kMaxSpecies;
+    Problem* dev = h->i8_probs.as<Problem>() + slot * kMaxSpecies;
+    for (size_t i = 0; i < probs.size(); ++i) pin[i] = probs[i];
+    if (!probs.empty()) SGPR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(Problem) * probs.size(), cudaMemcpyHostToDevice, st));
+    *out = dev;
+    return SGPR_OK;
+}
+
+int i8_kernel_matrix(sgpr_context* h, cudaStream_t st) {
+    Common cm;
+    std::vector<Problem> probs;
+    int ps[kMaxSpecies];
+    SGPR_TRY(build_problems(h, 1, cm, probs, ps));
+    if (cm.n_prob == 0) return SGPR_OK;
+    const Problem* probs_d = nullptr;
+    SGPR_TRY(upload_problems(h, 0, probs, st, &probs_d));
+    Epi1 e{};
+    for (int p = 0; p < cm.n_prob; ++p) {
+        const int s = ps[p], r0 = h->row_first[s], m0 = h->m_first[s];
+        e.mu[p] = h->mu.as<double>() + m0;
+        e.erow_part[p] = h->erow_part.as<double>() + r0;
+        e.g8[p] = h->g8.as<signed char>() + (size_t)r0 * h->i8_mp;
+    }
+    e.erow_ld = (int)h->n_active + 1;
+    e.Mp = h->i8_mp;
+    e.g8_slice = (long long)h->i8_cap_rows * h->i8_mp;
+    e.xi = h->xi;
+    e.xi_int = h->xi_int;
+    return h->i8_tr == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+}
+
+int i8_back_projection(sgpr_context* h, cudaStream_t st) {
+    Common cm;
+    std::vector<Problem> probs;
+    int ps[kMaxSpecies];
+    SGPR_TRY(build_problems(h, 2, cm, probs, ps));
+    if (cm.n_prob == 0) return SGPR_OK;
+    const Problem* probs_d = nullptr;
+    SGPR_TRY(upload_problems(h, 1, probs, st, &probs_d));
+    Epi2 e{};
+    for (int p = 0; p < cm.n_prob; ++p) e.gvec[p] = h->gvec.as<double>() + (size_t)h->row_first[ps[p]] * h->dp.ldp;
+    e.ldp = h->dp.ldp;
+    e.mumax = h->i8_mumax;
+    return h->i8_tr == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+}
+
+}  // namespace sgpr

@@ -1,0 +1,334 @@
+// FP64-accurate GEMM on the 5th-generation tensor cores (tcgen05, sm_100a) by integer slicing.
+//
+//   C[M x N] = A[M x K] . B[N x K]^T ,   |A|,|B| <= 1 (rows are normalised descriptors / k^(xi-1))
+//
+// Each operand is held as NS balanced signed digits in base 256 ("Ozaki scheme"):
+//   x ~= 2^-(8 NS - 2) * sum_t a_t 256^(NS - t),   a_t in [-128, 127]   (int8; one bit of headroom)
+// so that  A.B^T = 2^-2(8NS-2) * sum_{t,u} 256^(2NS - t - u)  (a_t . b_u^T),  every slice product an
+// int8 x int8 -> int32 GEMM that tcgen05.mma kind::i8 evaluates EXACTLY (|sum| <= K 128^2 pairs < 2^31
+// for K <= 16384).  Pairs with t + u > TR are dropped (they are below the rounding of the retained
+// ones); all pairs with the same t + u share one TMEM accumulator, so the epilogue converts TR - 1
+// int32 tiles to float64.  For unit-norm rows: NS = 6, TR = 7 (21 slice products) agrees with the
+// float64 product to ~1e-12 absolute, NS = 6, TR = 8 (26 products) to ~3e-14.
+//
+// Kernel structure (one CTA per SM, persistent over tiles): warp 0 = TMA producer (one 3-D bulk
+// tensor copy per operand per stage brings all NS slices of a 128 x 64 B / 64 x 64 B K-chunk,
+// SWIZZLE_64B), warp 1 = single-thread tcgen05.mma issuer (2 k-steps x pairs per stage, accumulators
+// in TMEM: (TR-1) x 64 columns), warps 2-5 = epilogue (tcgen05.ld -> float64 -> fused epilogue).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgpr {
+namespace i8g {
+
+constexpr int BM = 128, BN = 64, BKB = 64;     // tile; BKB = K bytes (= int8 elements) per stage
+constexpr int MAXS = 7;                        // max slices
+constexpr int NTHREADS = 192;                  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// one elected lane of a converged warp (keeps the surrounding code warp-uniform, so descriptors and
+// TMEM addresses stay in uniform registers and UTCIMMA issues without per-instruction waterfall loops)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns of TMEM -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_64B, rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+    return d;
+}
+// instruction descriptor: int8 x int8 -> int32, both K-major, M = 128, N = BN
+__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+    uint32_t d = 0;
+    d |= 2u << 4;                  // c_format = S32
+    d |= 1u << 7;                  // a_format = signed int8
+    d |= 1u << 10;                 // b_format = signed int8
+    d |= (uint32_t)(N >> 3) << 17; // n_dim
+    d |= (uint32_t)(M >> 4) << 24; // m_dim
+    return d;
+}
+
+struct Problem {
+    CUtensorMap mapA;    // int8 [NS][rowsA][Kpad], box {64, 128, NS}
+    CUtensorMap mapB;    // int8 [NS][rowsB][Kpad], box {64,  64, NS}
+    int M, N, Kpad;      // Kpad multiple of 64 (zero padded)
+};
+
+struct Common {
+    int n_prob;
+    int tile_start[9];   // first tile of each problem (problem-major)
+};
+
+template <int NS, int TR>
+struct Scheme {
+    static constexpr int NG = TR - 1;                       // accumulator groups (t + u = 2 .. TR)
+    static constexpr int A_BYTES = NS * BM * BKB, B_BYTES = NS * BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(NG * BN <= 512, "accumulators exceed TMEM");
+    static_assert(NS <= MAXS && TR <= 2 * NS && TR >= NS + 1, "bad slicing scheme");
+    static constexpr int pairs() {
+        int n = 0;
+        for (int t = 1; t <= NS; ++t)
+            for (int u = 1; u <= NS; ++u) n += (t + u <= TR);
+        return n;
+    }
+};
+
+// 16 TMEM columns of every accumulator group -> float64:  T = sum_g acc_g 256^(NG-1-g), combined exactly in
+// two int64 halves (|acc_g| < 2^27: hi < 2^51, lo < 2^43), one fma; result = T * 2^-(8 (NG-1) + 12).
+template <int NG>
+__device__ __forceinline__ void combine16(uint32_t taddr_lane_col, double* v) {
+    int32_t r[NG][16];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) tmem_ld16(taddr_lane_col + g * BN, r[g]);
+    tmem_ld_wait();
+    constexpr int NH = NG < 4 ? NG : 4;      // groups in the high half
+    const double hs = (double)(1ll << (8 * (NG - NH)));
+    const double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        long long hi = 0, lo = 0;
+#pragma unroll
+        for (int g = 0; g < NH; ++g) hi = hi * 256 + (long long)r[g][j];
+#pragma unroll
+        for (int g = NH; g < NG; ++g) lo = lo * 256 + (long long)r[g][j];
+        v[j] = fma((double)hi, hs, (double)lo) * sc;
+    }
+}
+
+// Epilogue functor:  epi(prob, row, col0, v[16], M, N)  called by each of the 128 epilogue threads (one
+// output row each) for every 16-column chunk of its row.
+template <int NS, int TR, int STAGES, class Epi, int DEBUG_SKIP = 0>
+__global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_constant__ Common cm,
+                                                             const Problem* __restrict__ probs, Epi epi) {
+    using SC = Scheme<NS, TR>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * SC::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t tmem_cols = 512;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);               // one arrive per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = cm.tile_start[cm.n_prob];
+
+    if (warp == 0) {
+        // ===================== TMA producer (converged warp, elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int gt = blockIdx.x; gt < n_tiles; gt += gridDim.x) {
+            int pi = 0;
+            for (int q = 1; q < cm.n_prob; ++q)
+                if (gt >= cm.tile_start[q]) pi = q;
+            const Problem& P = probs[pi];
+            const int tile = gt - cm.tile_start[pi];
+            const int tiles_n = (P.N + BN - 1) / BN;
+            const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+            const int nk = P.Kpad / BKB;
+            for (int kt = 0; kt < nk; ++kt) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    uint8_t* sa = smem + (size_t)stage * SC::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], SC::STAGE_BYTES);
+                    tma_load_3d(sa, &P.mapA, &full_bar[stage], kt * BKB, tm * BM, 0);
+                    tma_load_3d(sa + SC::A_BYTES, &P.mapB, &full_bar[stage], kt * BKB, tn * BN, 0);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (converged warp, one elected lane issues; fully unrolled) ==========
+        {
+            const uint32_t idesc = make_idesc_i8(BM, BN);
+            const uint64_t desc_hi = make_desc_sw64(0);      // everything but the start address
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int gt = blockIdx.x; gt < n_tiles; gt += gridDim.x) {
+                int pi = 0;
+                for (int q = 1; q < cm.n_prob; ++q)
+                    if (gt >= cm.tile_start[q]) pi = q;
+                const int nk = probs[pi].Kpad / BKB;
+                mbar_wait(tmem_empty, tphase ^ 1);      // epilogue has drained the accumulators
+                tc_fence_after();
+                for (int kt = 0; kt < nk; ++kt) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * SC::STAGE_BYTES);
+                    const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+                    const uint64_t bdesc = desc_hi | (uint64_t)(((sa + SC::A_BYTES) >> 4) & 0x3FFF);
+                    const uint32_t later = kt > 0 ? 1u : 0u;
+                    if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < BKB / 32; ++ks) {
+#pragma unroll
+                        for (int t = 1; t <= NS; ++t) {
+#pragma unroll
+                            for (int u = 1; u <= NS; ++u) {
+                                if (t + u <= TR) {
+                                    // the first product of a tile into a group's accumulator overwrites it:
+                                    // groups 0..NS-1 are first reached at t == 1, the others at u == NS
+                                    const uint32_t accum = (ks == 0 && (t == 1 || u == NS)) ? later : 1u;
+                                    mma_i8(tmem_base + (t + u - 2) * BN, adesc + (((t - 1) * (BM * BKB) + ks * 32) >> 4),
+                                           bdesc + (((u - 1) * (BN * BKB) + ks * 32) >> 4), idesc, accum);
+                                }
+                            }
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);       // smem stage is free once these MMAs retire
+                    if (kt == nk - 1) tc_commit(tmem_full);   // accumulators of this tile complete
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 own TMEM lanes 32*(warp%4)..+31) =====================
+        const int q = warp & 3;
+        const int row_in_tile = q * 32 + lane;
+        uint32_t tphase = 0;
+        for (int gt = blockIdx.x; gt < n_tiles; gt += gridDim.x) {
+            int pi = 0;
+            for (int qq = 1; qq < cm.n_prob; ++qq)
+                if (gt >= cm.tile_start[qq]) pi = qq;
+            const Problem& P = probs[pi];
+            const int tile = gt - cm.tile_start[pi];
+            const int tiles_n = (P.N + BN - 1) / BN;
+            const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+            mbar_wait(tmem_full, tphase);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 16) {
+                if (DEBUG_SKIP == 2) break;   // timing experiment: no epilogue at all
+                double v[16];
+                combine16<SC::NG>(lane_addr + cc, v);
+                if (DEBUG_SKIP == 1) {        // timing experiment: no stores
+                    double s = 0;
+                    for (int j = 0; j < 16; ++j) s += v[j];
+                    if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN + cc, v, P.M, P.N);
+                    continue;
+                }
+                epi(pi, tm * BM + row_in_tile, tn * BN + cc, v, P.M, P.N);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+template <int NS, int STAGES>
+constexpr size_t smem_bytes() { return (size_t)STAGES * NS * (BM + BN) * BKB + 1024 + 256; }
+
+}  // namespace i8g
+}  // namespace sgpr

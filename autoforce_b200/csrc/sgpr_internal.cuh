@@ -127,6 +127,17 @@ struct sgpr_context {
     sgpr::DevBuf kcmat, cpart;  // covloss: K^xi [rows, ldg], per-row partial sums of squares
     sgpr::DevBuf erow_part, erow, prow;  // per-row energy partials / local energies / descriptor norms
     sgpr::DevBuf ttab;          // [D] kappa*nnl*(1 + [a==b]) per packed entry
+    // ---- tcgen05 int8-sliced GEMM path (i8gemm.cu)
+    bool use_i8 = false;        // GEMMs on tcgen05 (int8 digit slices) instead of FP64 DMMA
+    bool use_i8_now = false;    // ... for the current call (covloss / compat calls use the DMMA path)
+    int i8_tr = 7;              // truncation t + u <= i8_tr (7: 21 slice products, 8: 26)
+    int i8_kp1 = 0, i8_mp = 0;  // K paddings (multiples of 64) of GEMM 1 (D) and GEMM 2 (max M_s)
+    size_t i8_cap_rows = 0;     // row capacity of p8 / g8 (slice stride)
+    double i8_mumax = 1.0;      // power of two >= max xi |mu|
+    sgpr::DevBuf z8, zt8;       // static digit slices: z_hat [6][M][kp1], (xi mu z_hat^T / mumax) [S][6][D][mp]
+    sgpr::DevBuf p8, g8;        // per-step digit slices: q_hat [6][cap][kp1], k^(xi-1) [6][cap][mp]
+    sgpr::DevBuf i8_probs;      // device copies of the tensor-map problem descriptors
+    void* i8_probs_pinned = nullptr;
     sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
     sgpr::DevBuf ztab;        // [128] atomic number -> species
     sgpr::DevBuf ind_perm_d;  // [M]
@@ -180,6 +191,13 @@ int gemm_energy_parts(int Ms);
 int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st);
 int gemm_covloss_parts(sgpr_context* h);
 int gemm_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
+
+// ---- i8gemm.cu --------------------------------------------------------------------
+int i8_prepare_model(sgpr_context* h, bool weights_only);
+int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows);
+int i8_energy_parts(int Ms);
+int i8_kernel_matrix(sgpr_context* h, cudaStream_t st);
+int i8_back_projection(sgpr_context* h, cudaStream_t st);
 int gemm_back_projection(sgpr_context* h, cudaStream_t st);
 
 }  // namespace sgpr

@@ -33,7 +33,7 @@ class sgpr_model_desc(ctypes.Structure):
 class sgpr_stats(ctypes.Structure):
     _fields_ = [
         ("n_atoms", c_int64), ("n_active", c_int64), ("n_pairs", c_int64), ("d_packed", c_int32), ("d_full", c_int32),
-        ("kernel_launches", c_int64), ("gemm_flops", c_double), ("covloss_flops", c_double), ("ms_nl", c_float),
+        ("kernel_launches", c_int64), ("gemm_flops", c_double), ("covloss_flops", c_double), ("i8_ops", c_double), ("ms_nl", c_float),
         ("ms_desc", c_float), ("ms_gemm", c_float), ("ms_force", c_float), ("ms_beta", c_float), ("ms_total", c_float),
     ]
 

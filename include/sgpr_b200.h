@@ -167,6 +167,8 @@ typedef struct {
     int64_t kernel_launches;  /* CUDA kernels launched by the last hot-path call        */
     double  gemm_flops;       /* flops executed by the two kernel GEMMs, last call     */
     double  covloss_flops;    /* flops executed by the covloss GEMM, last call         */
+    double  i8_ops;           /* int8 tensor-core operations of the sliced GEMMs (0 on the
+                                 FP64 DMMA path), last call                            */
     float   ms_nl, ms_desc, ms_gemm, ms_force, ms_beta, ms_total; /* device time per stage
                                  of the last call (CUDA events), valid if timing is on */
 } sgpr_stats;

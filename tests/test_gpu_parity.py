@@ -194,9 +194,10 @@ def test_covloss_matches_reference(case):
     assert np.array_equal(np.isnan(beta), np.isnan(ref))
     # the sqrt next to the clamp amplifies rounding: compare beta^2
     assert np.abs(beta[fin] ** 2 - ref[fin] ** 2).max() < 1e-9
-    # asking for beta must not change E/F/W
+    # asking for beta must not change E/F/W (the covloss call runs the float64 DMMA GEMMs, the plain call the
+    # tcgen05 int8-sliced ones: equal to ~1e-12 relative, not bit-identical)
     E0, F0, W0, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
-    assert E == E0 and np.array_equal(W, W0) and np.abs(F - F0).max() < 1e-12
+    assert abs(E - E0) < 1e-10 * max(1.0, abs(E0)) and np.abs(W - W0).max() < 1e-9 and np.abs(F - F0).max() < 1e-10
     # sharded: each rank fills the betas of the atoms it owns
     parts = np.zeros_like(beta)
     for rank in range(3):

@@ -254,19 +254,29 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
             // slice-major, 4 consecutive entries (one 32-bit store per slice) per lane
             const long long prow = (long long)row_of[ENV ? env : c] * kp1;
             for (int e4 = lane * 4; e4 < dp.D; e4 += 128) {
-                unsigned packed[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+                unsigned long long u[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int e = e4 + q;
                     double x = 0.0;
                     if (e < dp.D) x = (cache_q ? buf[e] : pspec_entry(dp, c_s, ptab[e], nnlk[e])) * rP;
-                    long long v = __double2ll_rn(x * 70368744177664.0);   // 2^46
+                    // bytes of (rint(x 2^46) + bias) ^ bias are the balanced base-256 digits (i8gemm.cu)
+                    const long long v = __double2ll_rn(x * 70368744177664.0);
+                    u[q] = ((unsigned long long)(v + 0x808080808080ll)) ^ 0x808080808080ull;
+                }
+                unsigned packed[6];
 #pragma unroll
-                    for (int t = 5; t >= 0; --t) {
-                        const int dg = (int)((v + 128) & 255) - 128;
-                        packed[t] |= (unsigned)(dg & 255) << (8 * q);
-                        v = (v - dg) >> 8;
+                for (int t = 0; t < 6; ++t) {
+                    const int b = 5 - t;   // slice t (most significant first) = byte 5 - t
+                    unsigned w0, w1, w2, w3;
+                    if (b < 4) {
+                        w0 = (unsigned)u[0]; w1 = (unsigned)u[1]; w2 = (unsigned)u[2]; w3 = (unsigned)u[3];
+                    } else {
+                        w0 = (unsigned)(u[0] >> 32); w1 = (unsigned)(u[1] >> 32); w2 = (unsigned)(u[2] >> 32); w3 = (unsigned)(u[3] >> 32);
                     }
+                    const unsigned bb = (unsigned)(b & 3);
+                    const unsigned sel = bb | ((4u + bb) << 4);
+                    packed[t] = __byte_perm(__byte_perm(w0, w1, sel), __byte_perm(w2, w3, sel), 0x5410);
                 }
 #pragma unroll
                 for (int t = 0; t < 6; ++t) *reinterpret_cast<unsigned*>(p8 + (long long)t * p8_slice + prow + e4) = packed[t];

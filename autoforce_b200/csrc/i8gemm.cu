@@ -50,16 +50,33 @@ int make_map(CUtensorMap* m, const void* base, int ns, long long rows, int Kpad,
     return SGPR_OK;
 }
 
-// balanced base-256 digits of x * 2^(8 ns - 2), most significant first
+// Balanced base-256 digits of v = rint(x * 2^(8 NS - 2)):  v = sum_t d_t 256^t, d_t in [-128, 127].
+// Adding the bias 128 * (1 + 256 + ... + 256^(NS-1)) makes every coefficient d_t + 128 lie in [0, 255],
+// i.e. the bytes of (v + bias) ARE the digits + 128; xor 0x80 turns them into two's-complement int8.
 template <int NS>
-__device__ __forceinline__ void digits(double x, signed char* d) {
-    long long v = __double2ll_rn(x * (double)(1ll << (8 * NS - 2)));
-#pragma unroll
-    for (int t = NS - 1; t >= 0; --t) {
-        const int dg = (int)((v + 128) & 255) - 128;
-        d[t] = (signed char)dg;
-        v = (v - dg) >> 8;
+__device__ __forceinline__ unsigned long long digit_bytes(double x) {
+    constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * NS)) - 1ull);
+    const long long v = __double2ll_rn(x * (double)(1ll << (8 * NS - 2)));
+    return ((unsigned long long)(v + (long long)BIAS)) ^ BIAS;   // byte t = digit t (t = 0 least significant)
+}
+// byte b of four digit words -> one 32-bit word (columns j .. j+3 of one slice)
+__device__ __forceinline__ unsigned gather_byte(const unsigned long long* u, int b) {
+    unsigned w0, w1, w2, w3;
+    if (b < 4) {
+        w0 = (unsigned)u[0]; w1 = (unsigned)u[1]; w2 = (unsigned)u[2]; w3 = (unsigned)u[3];
+    } else {
+        w0 = (unsigned)(u[0] >> 32); w1 = (unsigned)(u[1] >> 32); w2 = (unsigned)(u[2] >> 32); w3 = (unsigned)(u[3] >> 32);
+        b -= 4;
     }
+    const unsigned sel = (unsigned)b | ((unsigned)(4 + b) << 4);
+    const unsigned t01 = __byte_perm(w0, w1, sel), t23 = __byte_perm(w2, w3, sel);
+    return __byte_perm(t01, t23, 0x5410);
+}
+template <int NS>
+__device__ __forceinline__ void digits(double x, signed char* d) {   // most significant first
+    const unsigned long long u = digit_bytes<NS>(x);
+#pragma unroll
+    for (int t = 0; t < NS; ++t) d[t] = (signed char)((u >> (8 * (NS - 1 - t))) & 0xff);
 }
 
 // float64 rows -> digit slices:  out[t][r][k] for r < rows, k < K ; zero for K <= k < Kpad
@@ -92,38 +109,56 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
     int xi_int;
     __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
         if (row >= M) return;
-        signed char dg[kNS][16];
-        double e = 0.0;
         const double* mup = mu[p];
+        double pw[16];
+        // k^(xi-1): the usual exponents unrolled (independent multiplies), anything else by pow()
+        if (xi_int == 4) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pw[j] = v[j] * v[j] * v[j];
+        } else if (xi_int == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pw[j] = v[j];
+        } else if (xi_int == 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pw[j] = v[j] * v[j];
+        } else if (xi_int == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pw[j] = 1.0;
+        } else {
+            for (int j = 0; j < 16; ++j) {
+                if (xi_int >= 1) {
+                    double r = 1.0;
+                    for (int t = 1; t < xi_int; ++t) r *= v[j];
+                    pw[j] = r;
+                } else {
+                    pw[j] = pow(v[j], xi - 1.0);
+                }
+            }
+        }
+        double e = 0.0;
+        unsigned long long u[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int c = col0 + j;
-            double pw = 0.0;
-            if (c < N) {
-                const double k = v[j];
-                if (xi_int >= 1) {
-                    pw = 1.0;
-                    for (int t = 1; t < xi_int; ++t) pw *= k;
-                } else {
-                    pw = pow(k, xi - 1.0);
-                }
-                e += mup[c] * pw * k;
-            }
-            signed char d[kNS];
-            digits<kNS>(pw, d);
-#pragma unroll
-            for (int t = 0; t < kNS; ++t) dg[t][j] = d[t];
+            const bool in = col0 + j < N;
+            const double pj = in ? pw[j] : 0.0;
+            e += (in ? mup[col0 + j] : 0.0) * pj * v[j];
+            u[j] = digit_bytes<kNS>(pj);
         }
         // one 16-byte store per slice (columns beyond N get zero digits: the K padding of GEMM 2)
         if (col0 < Mp) {
 #pragma unroll
-            for (int t = 0; t < kNS; ++t)
-                *reinterpret_cast<int4*>(g8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) =
-                    *reinterpret_cast<const int4*>(dg[t]);
+            for (int t = 0; t < kNS; ++t) {
+                const int b = kNS - 1 - t;   // slice t (most significant first) = byte NS-1-t
+                int4 w;
+                w.x = (int)gather_byte(u + 0, b);
+                w.y = (int)gather_byte(u + 4, b);
+                w.z = (int)gather_byte(u + 8, b);
+                w.w = (int)gather_byte(u + 12, b);
+                *reinterpret_cast<int4*>(g8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+            }
         }
-        // energy partial of this 16-column chunk: accumulated per (column tile) by the 4 chunk calls
-        double* ep = erow_part[p] + (long long)(col0 >> 4) * erow_ld + row;
-        *ep = e;
+        // energy partial of this 16-column chunk
+        erow_part[p][(long long)(col0 >> 4) * erow_ld + row] = e;
     }
 };
 

@@ -156,6 +156,33 @@ struct Scheme {
 
 // 16 TMEM columns of every accumulator group -> float64:  T = sum_g acc_g 256^(NG-1-g), combined exactly in
 // two int64 halves (|acc_g| < 2^27: hi < 2^51, lo < 2^43), one fma; result = T * 2^-(8 (NG-1) + 12).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+template <int NG>
+__device__ __forceinline__ void combine8(uint32_t taddr_lane_col, double* v) {
+    int32_t r[NG][8];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) tmem_ld8(taddr_lane_col + g * BN, r[g]);
+    tmem_ld_wait();
+    constexpr int NH = NG < 4 ? NG : 4;
+    const double hs = (double)(1ll << (8 * (NG - NH)));
+    const double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        long long hi = 0, lo = 0;
+#pragma unroll
+        for (int g = 0; g < NH; ++g) hi = hi * 256 + (long long)r[g][j];
+#pragma unroll
+        for (int g = NH; g < NG; ++g) lo = lo * 256 + (long long)r[g][j];
+        v[j] = fma((double)hi, hs, (double)lo) * sc;
+    }
+}
+
 template <int NG>
 __device__ __forceinline__ void combine16(uint32_t taddr_lane_col, double* v) {
     int32_t r[NG][16];
@@ -303,23 +330,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             mbar_wait(tmem_full, tphase);
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int cc = 0; cc < BN; cc += 16) {
-                if (DEBUG_SKIP == 2) break;   // timing experiment: no epilogue at all
-                double v[16];
-                combine16<SC::NG>(lane_addr + cc, v);
-                if (DEBUG_SKIP == 1) {        // timing experiment: no stores
-                    double s = 0;
-                    for (int j = 0; j < 16; ++j) s += v[j];
-                    if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN + cc, v, P.M, P.N);
-                    continue;
-                }
-                epi(pi, tm * BM + row_in_tile, tn * BN + cc, v, P.M, P.N);
+            // drain the accumulators into float64 registers, hand TMEM back to the MMA warp, and only
+            // then run the (expensive) fused epilogue: it overlaps with the next tile's main loop
+            double v[BN];
+            if (DEBUG_SKIP != 2) {
+#pragma unroll
+                for (int cc = 0; cc < BN; cc += 8) combine8<SC::NG>(lane_addr + cc, v + cc);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
             tphase ^= 1;
+            if (DEBUG_SKIP == 0) {
+#pragma unroll
+                for (int cc = 0; cc < BN; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + cc, v + cc, P.M, P.N);
+            } else if (DEBUG_SKIP == 1) {
+                double s = 0;
+                for (int j = 0; j < BN; ++j) s += v[j];
+                if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN, v, P.M, P.N);
+            }
         }
     }
     tc_fence_before();

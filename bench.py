@@ -228,7 +228,8 @@ def main():
     # ---- device-resident leg (value) with per-stage CUDA-event timing inside the library
     eng.enable_timing(True)
     sampler = ClockSampler(local_rank)
-    stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "launches": 0}
+    stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "i8_ops": 0.0,
+             "launches": 0}
 
     def step_device_acc(it):
         step_device(it)
@@ -237,6 +238,7 @@ def main():
             for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total"):
                 stage[k] += s[k]
             stage["gemm_flops"] += s["gemm_flops"]
+            stage["i8_ops"] += s["i8_ops"]
             stage["launches"] += s["kernel_launches"]
             stage["n_active"] = s["n_active"]
             stage["n_pairs"] = s["n_pairs"]
@@ -257,17 +259,35 @@ def main():
         value = N * K / (ms_dev * 1e-3)
         e2e = N * K / (wall_e2e * 1e-3)
         gemm_s = stage["ms_gemm"] * 1e-3
-        achieved = stage["gemm_flops"] / gemm_s / 1e12 if gemm_s > 0 else None
+        fp64_equiv = stage["gemm_flops"] / gemm_s / 1e12 if gemm_s > 0 else None
         try:
-            peak = dgemm_peak_tflops()
+            dgemm_peak = dgemm_peak_tflops()
+        except Exception:  # pragma: no cover
+            dgemm_peak = None
+        use_i8 = stage["i8_ops"] > 0
+        if use_i8:
+            # the GEMMs run on tcgen05 as int8 digit-slice products: roofline in int8 tensor operations
+            achieved = stage["i8_ops"] / gemm_s / 1e12
+            peak, peak_src = 4500.0, "fallback: nominal dense int8 tensor peak of B200 (MEASURED_PEAKS.json lists bf16 only)"
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                peak = 2.0 * float(mp["bf16_tflops"])
+                peak_src = "2 x measured dense bf16 peak of MEASURED_PEAKS.json (int8 tensor rate = 2 x bf16; burst figure)"
+            except Exception:
+                pass
+            kernel_name = "i8gemm_kernel (tcgen05.mma kind::i8, TMA + TMEM): FP64-accurate kernel GEMM + back projection as int8 digit-slice products"
+            unit = "TOP/s (int8)"
+        else:
+            achieved = fp64_equiv
+            peak = dgemm_peak if dgemm_peak else 40.0
             peak_src = "measured in-run: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has no FP64 entry)"
-        except Exception as ex:  # pragma: no cover
-            peak, peak_src = 40.0, f"nominal B200 FP64 (in-run DGEMM failed: {ex})"
+            kernel_name = "gemm_tn_kernel (FP64 DMMA kernel-matrix GEMM + back projection)"
+            unit = "TFLOP/s"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get("gemm_dram_bytes_per_launch")
+                traffic = json.load(open(tpath)).get(args.workload, {}).get("i8gemm_dram_bytes_per_launch" if use_i8 else "gemm_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
@@ -278,9 +298,11 @@ def main():
                     "h2d_bytes_per_step": int(N * 24 + N * 4), "d2h_bytes_per_step": int(N * 24 + 16 * 8 + N)},
             "gpu_launches": int(stage["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (FP64 DMMA kernel-matrix GEMM + back projection)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+            "roofline": {"bound": "tensor", "kernel": kernel_name,
+                         "achieved": achieved, "peak": peak, "unit": unit, "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
+                         "fp64_equivalent_tflops": fp64_equiv, "cublas_dgemm_tflops_in_run": dgemm_peak,
+                         "int8_ops_per_step": stage["i8_ops"] / K,
                          "flops_per_step": stage["gemm_flops"] / K, "gemm_ms_per_step": stage["ms_gemm"] / K},
             "stages_ms_per_step": {k[3:]: stage[k] / K for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total")},
             "pairs": int(stage.get("n_pairs", 0)), "active_envs_rank0": int(stage.get("n_active", 0)),

@@ -152,6 +152,30 @@ __global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ ato
     if (owned_out) owned_out[i] = owned ? owned[c] : 1;
 }
 
+// dL/dx = -F in the caller's order, plus per-block partials of sum_k x_k (x) F_k (for dL/dcell)
+__global__ void vjp_finish_kernel(int64_t N, const AtomRec* __restrict__ atoms, const double* __restrict__ fcell,
+                                  double* __restrict__ gpos, double* __restrict__ xf_part) {
+    __shared__ double red[9][128];
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x) {
+        const AtomRec a = atoms[c];
+        const int i = meta_orig(a.meta);
+        const double f[3] = {fcell[3 * c], fcell[3 * c + 1], fcell[3 * c + 2]};
+        const double x[3] = {a.x, a.y, a.z};
+        for (int q = 0; q < 3; ++q) gpos[3 * (size_t)i + q] = -f[q];
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) acc[p * 3 + q] += x[p] * f[q];
+    }
+    for (int q = 0; q < 9; ++q) red[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int q = 0; q < 9; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 9) xf_part[blockIdx.x * 9 + threadIdx.x] = red[threadIdx.x][0];
+}
+
 __global__ void final_reduce_kernel(int n_e, const double* __restrict__ epart, int n_x, const double* __restrict__ xpart,
                                     int n_w, const double* __restrict__ wpart, double* __restrict__ E,
                                     double* __restrict__ W) {
@@ -569,6 +593,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
                        const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false) {
     h->use_i8_now = i8 && h->use_i8;
     h->stats.i8_ops = 0.0;
+    h->fwd_valid = false;
     // geometry -> cell sort -> neighbour list -> descriptors (rows in species-major order)
     if (N < 0 || N > 0x7fffff00ll) {
         set_error("bad atom count");
@@ -787,13 +812,78 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_forward(sgpr_h
     }
     SGPR_CUDA(cudaGetLastError());
     SGPR_CUDA(cudaStreamSynchronize(st));
+    h->fwd_valid = true;
     return SGPR_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_handle h, const double* gK_d, void* stream, double* gpos_d, double* gcell_h) {
-    (void)h; (void)gK_d; (void)stream; (void)gpos_d; (void)gcell_h;
-    set_error("sgpr_kernel_backward is not available in this build");
-    return SGPR_ERR_INVALID;
+    // Vector-Jacobian product of the LAST sgpr_kernel_forward:  L = sum_im gK[i,m] K[i,m]
+    //   dL/dk[i,m] = gK[i,m] xi k^(xi-1)   -> same pipeline as the prediction with mu_m replaced by gK[i,m]
+    //   dL/dxyz = -F ;  dL/dcell[k,:] = sum_pairs S_k g = (cell^-T (W + sum_k x_k (x) F_k))[k,:]
+    if (!h || !gK_d || !gpos_d || !gcell_h) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    if (!h->fwd_valid) {
+        set_error("sgpr_kernel_backward needs a preceding sgpr_kernel_forward on this handle");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    const int64_t N = h->last_N;
+    const Geom g = h->last_geom;
+    const size_t nrows = (size_t)h->n_active + 1;
+    const int nblk_b = backward_grid(h), grid_e = 128, nblk_x = 64;
+    RowSpecies rs{};
+    rs.S = h->S;
+    int max_part = 1;
+    for (int s = 0; s <= h->S; ++s) rs.row_first[s] = h->row_first[s];
+    for (int s = 0; s < h->S; ++s) {
+        const int Ms = h->m_first[s + 1] - h->m_first[s];
+        rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? gemm_energy_parts(Ms) : 0;
+        max_part = std::max(max_part, rs.n_part[s]);
+    }
+    SGPR_TRY(h->gmat.ensure(sizeof(double) * nrows * h->ldg));
+    SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
+    SGPR_TRY(h->erow_part.ensure(sizeof(double) * (size_t)max_part * nrows));
+    SGPR_TRY(h->erow.ensure(sizeof(double) * nrows));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * (grid_e + 16 + 9 * nblk_x)));
+    SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
+    SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
+    SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
+    SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+    SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * (grid_e + 16 + 9 * nblk_x), st));
+    h->use_i8_now = false;
+    if (N > 0 && h->M > 0) {
+        SGPR_TRY(gemm_kernel_matrix(h, nullptr, h->M, h->rowmap.as<int>(), false, st, gK_d));
+        row_energy_kernel<<<grid_e, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows, nullptr,
+                                                  h->erow.as<double>(), h->epart.as<double>());
+        SGPR_TRY(gemm_back_projection(h, st));
+        SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
+    }
+    double* xf_part = h->epart.as<double>() + grid_e + 16;
+    double* EW = h->epart.as<double>() + grid_e;   // [E, W(9)] scratch
+    if (N > 0)
+        vjp_finish_kernel<<<nblk_x, 128, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(), gpos_d, xf_part);
+    final_reduce_kernel<<<1, 256, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), EW, EW + 1);
+    double host[16 + 9 * 64];
+    SGPR_CUDA(cudaMemcpyAsync(host, EW, sizeof(double) * (16 + 9 * nblk_x), cudaMemcpyDeviceToHost, st));
+    SGPR_CUDA(cudaStreamSynchronize(st));
+    double Y[9];
+    for (int q = 0; q < 9; ++q) {
+        double xf = 0.0;
+        for (int b = 0; b < nblk_x; ++b) xf += host[16 + b * 9 + q];
+        Y[q] = host[1 + q] + xf;   // W + sum x (x) F = cell^T (sum_pairs S (x) g)
+    }
+    // C = cell^-T Y ;  g.inv = cell^-1 (frac_c = sum_k pos_k inv[k][c])  ->  C[k][b] = sum_a inv[a][k] Y[a][b]
+    for (int k = 0; k < 3; ++k)
+        for (int b = 0; b < 3; ++b) {
+            double c = 0.0;
+            for (int a = 0; a < 3; ++a) c += g.inv[a * 3 + k] * Y[a * 3 + b];
+            gcell_h[k * 3 + b] = g.pbc[k] ? c : 0.0;
+        }
+    SGPR_CUDA(cudaGetLastError());
+    return SGPR_OK;
 }
 
 // =====================================================================================

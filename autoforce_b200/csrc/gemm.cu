@@ -58,7 +58,8 @@ int gemm_energy_parts(int Ms) { return ((Ms + CfgK::BN - 1) / CfgK::BN) * CfgK::
 // Kernel-matrix GEMM, all central species in ONE grouped launch (rows h->row_first, inducing
 // points h->m_first).  Writes G (h->gmat, [n_rows, ldg]) and per-CTA energy partials into
 // h->epart [grid]; optionally K^xi into Kmat (caller's row/column order).
-int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st) {
+int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st,
+                       const double* wmat) {
     GemmBatch b{};
     for (int s = 0; s < h->S; ++s) {
         const int r0 = h->row_first[s], r1 = h->row_first[s + 1];
@@ -77,6 +78,7 @@ int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_ma
         a.ldg = h->ldg;
         a.n_store = (a.N + 1) & ~1;
         a.Kmat = Kmat;
+        a.wmat = wmat;
         a.ldk = ldk;
         a.col_map = h->ind_perm_d.as<int>() + m0;
         a.row_map = row_map_d ? row_map_d + r0 : nullptr;

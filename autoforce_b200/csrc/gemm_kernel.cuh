@@ -27,6 +27,8 @@ struct GemmArgs {
     double* erow_part; // per-row energy partials: erow_part[(tile_n * WN + warp_n) * erow_ld + row]
     int erow_ld;
     double* Kc;        // optional [M, ldg] <- k^xi in GEMM row/column order (input of the covloss GEMM)
+    const double* wmat;  // optional per-element weights dL/dK [*, ldk] (caller's order via the maps) used
+                         // INSTEAD of mu[col]: vector-Jacobian product of the kernel matrix
     // epilogue 3 (covloss): per-row partial sums of squares, part[(tile_n * WN + warp_n) * part_ld + row]
     double* part;
     int part_ld;
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(C::NT, C::MINB) gemm_tn_kernel(const __grid_co
                         if (cc < g.N) {
                             const double k = acc[i][j][t];
                             const double pw = powm1(k, g.xi, g.xi_int);
-                            const double m = g.mu[cc];
+                            const double m = g.wmat ? g.wmat[(g.row_map ? (size_t)g.row_map[r] : (size_t)r) * g.ldk + g.col_map[cc]]
+                                                    : g.mu[cc];
                             gv = g.xi * m * pw;
                             e_row += m * pw * k;
                             if (g.Kmat) {

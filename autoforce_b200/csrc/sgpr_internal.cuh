@@ -158,6 +158,7 @@ struct sgpr_context {
     int64_t n_active = 0;
     int64_t n_owned = 0;
     bool active_all = true;
+    bool fwd_valid = false;                  // state of the last sgpr_kernel_forward is intact (for the VJP)
     int row_first[SGPR_MAX_SPECIES + 1];     // first descriptor row of each central species
     sgpr::Geom last_geom;
     sgpr_stats stats;
@@ -188,7 +189,8 @@ int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, 
 
 // ---- gemm.cu ----------------------------------------------------------------------
 int gemm_energy_parts(int Ms);
-int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st);
+int gemm_kernel_matrix(sgpr_context* h, double* Kmat, int ldk, const int* row_map_d, bool store_kc, cudaStream_t st,
+                       const double* wmat = nullptr);
 int gemm_covloss_parts(sgpr_context* h);
 int gemm_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
 

@@ -93,6 +93,42 @@ def _ptr(a):
     return c_void_p(a.ctypes.data)
 
 
+def _make_cov_function():
+    import torch
+
+    class _CovFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, xyz, lll, engine, numbers, pbc):
+            K = engine.kernel_matrix(xyz.detach(), numbers, lll.detach().cpu().numpy(), pbc)
+            ctx.engine = engine
+            ctx.xyz_dev, ctx.lll_dev = xyz.device, lll.device
+            return K.to(xyz.device)
+
+        @staticmethod
+        def backward(ctx, gK):
+            gpos, gcell = ctx.engine.kernel_matrix_vjp(gK)
+            import torch as _t
+
+            return gpos.to(ctx.xyz_dev), _t.as_tensor(gcell).to(ctx.lll_dev), None, None, None
+
+    return _CovFn
+
+
+class _CovProxy:
+    """Lazy holder so that importing the module does not import torch."""
+
+    _fn = None
+
+    @classmethod
+    def apply(cls, *args):
+        if cls._fn is None:
+            cls._fn = _make_cov_function()
+        return cls._fn.apply(*args)
+
+
+_Cov = _CovProxy
+
+
 class SgprEngine:
     """One handle on one CUDA device.  Host-side mirror of the C ABI."""
 
@@ -206,6 +242,27 @@ class SgprEngine:
         _check(self.lib, self.lib.sgpr_kernel_forward(self._h, N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()),
                                                       _ptr(cell_h), _ptr(pbc_h), self._stream(), c_void_p(K.data_ptr())))
         return K
+
+    def kernel_matrix_vjp(self, gK):
+        """Vector-Jacobian product of the LAST kernel_matrix() call: given gK = dL/dK [N, M] returns
+        (dL/dxyz [N,3] device tensor, dL/dcell [3,3] numpy) -- what torch.autograd.grad does in the
+        reference (calculator/active.py:587-599, regression/gppotential.py:905-911)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        gK = gK.to(dev, torch.float64).contiguous()
+        N = gK.shape[0]
+        gpos = torch.empty((N, 3), dtype=torch.float64, device=dev)
+        gcell = np.zeros(9)
+        _check(self.lib, self.lib.sgpr_kernel_backward(self._h, c_void_p(gK.data_ptr()), self._stream(), c_void_p(gpos.data_ptr()),
+                                                       _ptr(gcell)))
+        return gpos, gcell.reshape(3, 3)
+
+    def cov(self, xyz, lll, numbers, pbc):
+        """Differentiable kernel matrix: ``cov = model.gp.kern(atoms, model.X)`` (calculator/active.py:464) as a
+        torch tensor [N, M] on xyz's device that back-propagates into ``xyz`` (positions) and ``lll`` (cell) --
+        the seam the on-the-fly training control flow needs."""
+        return _Cov.apply(xyz, lll, self, np.asarray(numbers), tuple(bool(b) for b in np.broadcast_to(np.asarray(pbc), (3,))))
 
     # ------------------------------------------------------------------ parity hooks
     def neighbors(self, pos, numbers, cell, pbc):

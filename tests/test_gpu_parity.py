@@ -205,3 +205,38 @@ def test_covloss_matches_reference(case):
         parts[own] = b[own]
     assert np.array_equal(np.isnan(parts), np.isnan(beta))
     assert np.abs(parts[fin] ** 2 - beta[fin] ** 2).max() < 1e-12
+
+
+def test_differentiable_cov_matches_reference_autograd(case):
+    """Compat mode: cov[N,M] as a differentiable torch tensor.  With E = (cov @ mu).sum(), autograd
+    through sgpr_kernel_forward / sgpr_kernel_backward must reproduce the reference's forces and stress
+    (calculator/active.py:587-611: F = -dE/dxyz, stress = (-sum F (x) x + sum cellgrad (x) lll) / V)."""
+    import torch
+
+    g, eng = case
+    xyz = torch.tensor(g["pos"], dtype=torch.float64, requires_grad=True)
+    lll = torch.tensor(g["cell"], dtype=torch.float64, requires_grad=True)
+    cov = eng.cov(xyz, lll, g["numbers"], g["meta"]["pbc"])
+    assert cov.shape == g["K"].shape and np.abs(cov.detach().numpy() - g["K"]).max() < 1e-12
+    mu = torch.tensor(g["mu"], dtype=torch.float64)
+    E = (cov @ mu).sum()
+    gx, gl = torch.autograd.grad(E, [xyz, lll])
+    forces = -gx.numpy()
+    assert np.abs(forces - g["forces"]).max() < TOL_F
+    stress1 = -(forces[:, None, :] * g["pos"][:, :, None]).sum(axis=0)
+    stress2 = (gl.numpy()[:, None, :] * g["cell"][:, :, None]).sum(axis=0)
+    vol = abs(np.linalg.det(g["cell"])) or -2.0
+    stress = ((stress1 + stress2) / vol).reshape(-1)[[0, 4, 8, 5, 2, 1]]
+    assert np.abs(stress - g["stress"]).max() < TOL_S
+    # a random cotangent: forces of L = sum_im w_im K_im against finite differences of the forward hook
+    rng = np.random.default_rng(0)
+    w = torch.tensor(rng.normal(size=g["K"].shape))
+    cov = eng.cov(xyz, lll, g["numbers"], g["meta"]["pbc"])
+    (gx,) = torch.autograd.grad((cov * w).sum(), [xyz])
+    i, k, d = len(g["pos"]) // 2, 1, 1e-5
+    p = g["pos"].copy()
+    p[i, k] += d
+    Lp = float((eng.kernel_matrix(p, g["numbers"], g["cell"], g["meta"]["pbc"]).cpu() * w).sum())
+    p[i, k] -= 2 * d
+    Lm = float((eng.kernel_matrix(p, g["numbers"], g["cell"], g["meta"]["pbc"]).cpu() * w).sum())
+    assert abs((Lp - Lm) / (2 * d) - float(gx[i, k])) < 1e-6 * max(1.0, abs(float(gx[i, k])))

@@ -389,6 +389,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     for (int s = 0; s < SGPR_MAX_SPECIES; ++s) {
         dp.radii[s] = 1.0;
         dp.central_enabled[s] = 0;
+        dp.nbr_enabled[s] = 0;
         h->species_Z[s] = -1;
     }
     for (int s = 0; s < S; ++s) {
@@ -402,6 +403,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->z_to_species[z] = s;
         dp.radii[s] = d->radii[s];
         dp.central_enabled[s] = d->central_enabled[s] ? 1 : 0;
+        dp.nbr_enabled[s] = d->neighbor_enabled[s] ? 1 : 0;
     }
     h->xi = d->xi;
     h->xi_int = (d->xi == std::floor(d->xi) && d->xi >= 1 && d->xi <= 64) ? (int)d->xi : -1;

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
                 const double d = sqrt(d2);
                 double R, Rpd;
                 radial(d, u, dp.rc, R, Rpd);
+                if (!dp.nbr_enabled[sp]) R = 0.0;   // species outside the descriptor's `b` list
                 double* my = buf + lane * stride;
                 double fn = R;
                 for (int n = 0; n < dp.nb; ++n) {
@@ -370,6 +371,10 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
             const double d = sqrt(d2);
             double R, Rpd;
             radial(d, u, dp.rc, R, Rpd);
+            if (!dp.nbr_enabled[sp]) {
+                R = 0.0;
+                Rpd = 0.0;
+            }
             double f[NB], hh[NB], Tn[NB];
             {
                 double pw = 1.0;  // d2^(n-1)

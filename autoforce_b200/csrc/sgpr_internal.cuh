@@ -79,6 +79,7 @@ struct DescParams {
     double rc;
     double radii[kMaxSpecies];
     int central_enabled[kMaxSpecies];
+    int nbr_enabled[kMaxSpecies];   // 0: neighbours of this species are left out of the expansion
 };
 
 // host-side mirror of a grow-only device buffer

@@ -24,7 +24,7 @@ class sgpr_model_desc(ctypes.Structure):
     _fields_ = [
         ("lmax", c_int32), ("nmax", c_int32), ("xi", c_double), ("rc", c_double), ("normalize", c_int32),
         ("n_species", c_int32), ("species_Z", c_int32 * MAX_SPECIES), ("radii", c_double * MAX_SPECIES),
-        ("central_enabled", c_int32 * MAX_SPECIES), ("M", c_int32), ("ind_first_h", c_void_p), ("ind_r_h", c_void_p),
+        ("central_enabled", c_int32 * MAX_SPECIES), ("neighbor_enabled", c_int32 * MAX_SPECIES), ("M", c_int32), ("ind_first_h", c_void_p), ("ind_r_h", c_void_p),
         ("ind_b_h", c_void_p), ("ind_Z_h", c_void_p), ("mu_h", c_void_p), ("mean_w_h", c_void_p),
         ("choli_h", c_void_p), ("vscale_h", c_void_p), ("device", c_int32),
     ]
@@ -153,7 +153,8 @@ class SgprEngine:
         for s, z in enumerate(self.species):
             d.species_Z[s] = z
             d.radii[s] = model.unit_of(z)
-            d.central_enabled[s] = 0 if z in model.a_not else 1
+            d.central_enabled[s] = 1 if model.is_centre(z) else 0
+            d.neighbor_enabled[s] = 1 if model.is_neighbour(z) else 0
             mean_w[s] = model.mean_w.get(z, 0.0)
             vscale[s] = model.vscale.get(z, np.inf)
         d.M = model.M

@@ -53,7 +53,8 @@ class _SoapKernelBase:
         return SgprModel.from_envs(
             list(envs), lmax=self.lmax, nmax=self.nmax, xi=float(self.exponent), rc=float(self.cutoff), kind=self.kind,
             normalize=self.normalize, radii=self._radii_dict(), default_radius=self._default_radius(),
-            a_not=tuple(self._a.exceptions), mu=mu)
+            a_not=tuple(getattr(self._a, "exceptions", ())), a_only=tuple(getattr(self, "a_only", ())),
+            b_only=tuple(getattr(self, "b", ())), mu=mu)
 
     @property
     def a(self):
@@ -107,6 +108,23 @@ class SeSoapKernel(_SoapKernelBase):
     @property
     def state_args(self):
         return f"{self._args}, radii={self.radii}, normalize={self.normalize}"
+
+
+class SubSeSoapKernel(SeSoapKernel):
+    """similarity/sesoap.py:27-43: fixed central species ``a`` and neighbour species list ``b`` (dense
+    [S^2 * dim] descriptor); ``default_kernel(species=...)`` builds one per central species."""
+
+    def __init__(self, lmax, nmax, exponent, cutoff, a, b, radii=1.0, normalize=True):
+        super().__init__(lmax, nmax, exponent, cutoff, a=None, radii=radii, normalize=normalize)
+        self.a_only = (int(a),)
+        self.b = sorted(int(z) for z in (b if hasattr(b, "__iter__") else [b]))
+        self._a = int(a)
+        self.dim = len(self.b) ** 2 * (nmax + 1) ** 2 * (lmax + 1)
+        self._args = f"{lmax}, {nmax}, {exponent}, {cutoff}, {a}, {b}"
+
+    @property
+    def a(self):
+        return self._a
 
 
 class UniversalSoapKernel(_SoapKernelBase):

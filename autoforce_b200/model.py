@@ -28,6 +28,8 @@ class SgprModel:
     radii: dict = field(default_factory=dict)   # Z -> length unit; others -> default_radius
     default_radius: float = 1.0
     a_not: tuple = ()                 # species excluded as centres (EqAll exceptions)
+    a_only: tuple = ()                # if non-empty: the only central species (SubSeSoapKernel `a`s)
+    b_only: tuple = ()                # if non-empty: the only neighbour species that enter the descriptor (`b`)
     ind_Z: np.ndarray = None          # [M]
     ind_first: np.ndarray = None      # [M+1]
     ind_r: np.ndarray = None          # [nnz,3]
@@ -54,6 +56,8 @@ class SgprModel:
         self.mean_w = {int(k): float(v) for k, v in self.mean_w.items()}
         self.vscale = {int(k): float(v) for k, v in self.vscale.items()}
         self.a_not = tuple(int(z) for z in self.a_not)
+        self.a_only = tuple(int(z) for z in self.a_only)
+        self.b_only = tuple(int(z) for z in self.b_only)
 
     @property
     def M(self):
@@ -61,6 +65,12 @@ class SgprModel:
 
     def unit_of(self, z):
         return self.radii.get(int(z), self.default_radius)
+
+    def is_centre(self, z):
+        return int(z) not in self.a_not and (not self.a_only or int(z) in self.a_only)
+
+    def is_neighbour(self, z):
+        return not self.b_only or int(z) in self.b_only
 
     def species(self, extra=()):
         """Sorted atomic numbers of the model (+ ``extra``): the dense species table."""
@@ -81,8 +91,19 @@ class SgprModel:
         """Extract from a reference ``PosteriorPotential`` (regression/gppotential.py:453).
         Supports one SeSoapKernel / UniversalSoapKernel in ``model.gp.kern.kernels``."""
         kerns = list(model.gp.kern.kernels)
-        if len(kerns) != 1:
-            raise NotImplementedError("only single-kernel models are supported (got %d kernels)" % len(kerns))
+        a_only, b_only = (), ()
+        if len(kerns) > 1 or type(kerns[0]).__name__ == "SubSeSoapKernel":
+            # default_kernel(species=...) (calculator/active.py:28-38): one SubSeSoapKernel per central species,
+            # all with the same hyper-parameters and neighbour list b -> one dense model, centres = the a's
+            if not all(type(k).__name__ == "SubSeSoapKernel" for k in kerns):
+                raise NotImplementedError("kernel lists are supported for SubSeSoapKernel only")
+            k0 = kerns[0]
+            sig = lambda k: (int(k.descriptor.ylm.lmax), int(k.descriptor.nmax), float(k.kern.eta) if hasattr(k.kern, "eta") else None,
+                             float(k.cutoff), tuple(k.b), repr(k.descriptor.radii), bool(k.descriptor.normalize))
+            if any(sig(k) != sig(k0) for k in kerns):
+                raise NotImplementedError("SubSeSoapKernels with different hyper-parameters need one engine each")
+            a_only = tuple(int(k.a) for k in kerns)
+            b_only = tuple(int(z) for z in k0.b)
         k = kerns[0]
         cname = type(k).__name__
         desc = k.descriptor
@@ -95,7 +116,7 @@ class SgprModel:
             envs.append((int(loc.number), r, b))
             species.add(int(loc.number))
             species.update(int(z) for z in b)
-        if cname == "SeSoapKernel":
+        if cname in ("SeSoapKernel", "SubSeSoapKernel"):
             kind = "sesoap"
             radii = {z: float(desc.radii.get(z)) for z in species}
             default = float(desc.radii.get(10 ** 6)) if _safe_default(desc.radii) else 1.0
@@ -106,8 +127,9 @@ class SgprModel:
             raise NotImplementedError(f"kernel class {cname} is not supported")
         a = getattr(k, "_a", None)
         a_not = tuple(getattr(a, "exceptions", ()) or ())
-        if a is not None and not hasattr(a, "exceptions"):
+        if cname != "SubSeSoapKernel" and a is not None and not hasattr(a, "exceptions"):
             raise NotImplementedError("kernels restricted to a fixed central species (a=Z) are not supported")
+        exponent = k.exponent if cname != "SubSeSoapKernel" else _subse_exponent(k)
         mean = model.mean
         mean_w = {}
         for z, w in getattr(mean, "weights", {}).items():
@@ -115,8 +137,8 @@ class SgprModel:
         vscale = {int(z): float(v) for z, v in getattr(model, "_vscale", {}).items()}
         choli = getattr(model, "choli", None)
         return cls.from_envs(
-            envs, lmax=lmax, nmax=nmax, xi=float(k.exponent), rc=float(k.cutoff), kind=kind,
-            normalize=bool(desc.normalize), radii=radii, default_radius=default, a_not=a_not,
+            envs, lmax=lmax, nmax=nmax, xi=float(exponent), rc=float(k.cutoff), kind=kind,
+            normalize=bool(desc.normalize), radii=radii, default_radius=default, a_not=a_not, a_only=a_only, b_only=b_only,
             mu=np.asarray(model.mu.detach().cpu().numpy(), dtype=float), mean_w=mean_w,
             choli=None if choli is None else np.asarray(choli.detach().cpu().numpy(), dtype=float), vscale=vscale,
         )
@@ -125,7 +147,7 @@ class SgprModel:
     def save(self, path):
         meta = dict(format="autoforce_b200.sgpr_model", version=1, lmax=self.lmax, nmax=self.nmax, xi=self.xi, rc=self.rc,
                     kind=self.kind, normalize=self.normalize, radii={str(k): v for k, v in self.radii.items()},
-                    default_radius=self.default_radius, a_not=list(self.a_not),
+                    default_radius=self.default_radius, a_not=list(self.a_not), a_only=list(self.a_only), b_only=list(self.b_only),
                     mean_w={str(k): v for k, v in self.mean_w.items()}, vscale={str(k): v for k, v in self.vscale.items()})
         arrays = dict(ind_Z=self.ind_Z, ind_first=self.ind_first, ind_r=self.ind_r, ind_b=self.ind_b, mu=self.mu)
         if self.choli is not None:
@@ -140,9 +162,16 @@ class SgprModel:
             raise ValueError(f"{path}: not an autoforce_b200 model file")
         return cls(lmax=meta["lmax"], nmax=meta["nmax"], xi=meta["xi"], rc=meta["rc"], kind=meta["kind"],
                    normalize=meta["normalize"], radii=meta["radii"], default_radius=meta["default_radius"],
-                   a_not=tuple(meta["a_not"]), ind_Z=z["ind_Z"], ind_first=z["ind_first"], ind_r=z["ind_r"],
+                   a_not=tuple(meta["a_not"]), a_only=tuple(meta.get("a_only", ())), b_only=tuple(meta.get("b_only", ())),
+                   ind_Z=z["ind_Z"], ind_first=z["ind_first"], ind_r=z["ind_r"],
                    ind_b=z["ind_b"], mu=z["mu"], mean_w=meta["mean_w"], choli=z["choli"] if "choli" in z.files else None,
                    vscale=meta["vscale"])
+
+
+def _subse_exponent(k):
+    """SubSeSoapKernel keeps its exponent inside ``kern = DotProd() ** exponent`` (similarity/sesoap.py:29);
+    the eval-able argument string is '{lmax}, {nmax}, {exponent}, {cutoff}, {a}, {b}'."""
+    return float(k._args.split(",")[2])
 
 
 def _safe_default(radii):

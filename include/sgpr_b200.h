@@ -62,7 +62,11 @@ typedef struct {
                                      species of the inducing set AND of the structures */
     double  radii[SGPR_MAX_SPECIES];         /* length unit of neighbour species s     */
     int32_t central_enabled[SGPR_MAX_SPECIES]; /* 0 = species excluded as a centre
-                                     (`a`/`a_not`, universal.py:44-49,85,101)          */
+                                     (`a`/`a_not`, universal.py:44-49,85,101; the `a` of
+                                     SubSeSoapKernel, similarity/sesoap.py:27-43)       */
+    int32_t neighbor_enabled[SGPR_MAX_SPECIES]; /* 0 = neighbours of this species do not
+                                     enter the descriptor (species outside the `b` list of
+                                     SubSeSoap, descriptor/sesoap.py:263-335)            */
     int32_t M;                    /* number of inducing LCEs                          */
     const int64_t* ind_first_h;   /* [M+1] CSR offsets into ind_r / ind_b             */
     const double*  ind_r_h;       /* [nnz,3]  Local._r  (descriptor/atoms.py:36-52)   */

@@ -51,6 +51,13 @@ def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()
             rad = SpecialRadii({int(k): float(v) for k, v in radii.items() if k != "others"}, float(radii.get("others", 1.0)))
         a = EqAll(list(a_not)) if len(a_not) else None
         return SeSoapKernel(lmax, nmax, xi, float(rc), a=a, radii=rad)
+    elif kind == "subsesoap":
+        # default_kernel(species=...) of calculator/active.py:28-38
+        from theforce.descriptor.sesoap import DefaultRadii
+        from theforce.similarity.sesoap import SubSeSoapKernel
+
+        species = list(radii["species"])
+        return [SubSeSoapKernel(lmax, nmax, xi, float(rc), z, species, radii=DefaultRadii()) for z in species]
     elif kind == "universal":
         from theforce.similarity.universal import UniversalSoapKernel
 
@@ -134,6 +141,6 @@ def ref_predict(model, pos, cell, pbc, numbers, want_descriptors=()):
     desc = {}
     for a in want_descriptors:
         v = ta.loc[a].__dict__.get("kern_0_value")
-        desc[int(a)] = None if v is None else v.detach().to_dense().numpy().copy()
+        desc[int(a)] = None if (v is None or not v.is_sparse) else v.detach().to_dense().numpy().copy()
     out["descriptors"] = desc
     return out

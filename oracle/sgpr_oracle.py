@@ -57,6 +57,8 @@ class OracleModel:
     vscale: dict = field(default_factory=dict)  # Z -> vscale
     normalize: bool = True
     a_not: tuple = ()  # species excluded as centres (similarity/universal.py:44-49,85)
+    a_only: tuple = ()  # if non-empty: the central species of the SubSeSoapKernels (similarity/sesoap.py:27-43)
+    b_only: tuple = ()  # if non-empty: neighbour species that enter the descriptor (SubSeSoap `numbers`)
     default_radius: float = 1.0
 
     @property
@@ -65,6 +67,13 @@ class OracleModel:
 
     def unit_of(self, z):
         return float(self.radii.get(int(z), self.default_radius))
+
+    def excluded_centres(self, Z):
+        Z = np.asarray(Z, dtype=np.int64)
+        ex = np.isin(Z, np.asarray(self.a_not, dtype=np.int64))
+        if len(self.a_only):
+            ex |= ~np.isin(Z, np.asarray(self.a_only, dtype=np.int64))
+        return ex
 
     def species_table(self, extra=()):
         s = set(int(z) for z in self.ind_Z)
@@ -397,6 +406,8 @@ def descriptor_batch(model, species, R, Zb, mask, want_aux=False):
     n2 = 2.0 * np.arange(model.nmax + 1)
     rad, drad = _radial(model, units, d, grad=want_aux)
     rad = rad * mask
+    if len(model.b_only):  # SubSeSoap sums only over the species of its list (descriptor/sesoap.py:322-326)
+        rad = rad * np.isin(Zb, np.asarray(model.b_only, dtype=np.int64))
     f = rad[:, None, :] * d[:, None, :] ** n2[None, :, None]  # [B,n,nn]
     flag = shear_flag(xyz, mask)  # [B]
     if want_aux:
@@ -483,8 +494,8 @@ def kernel_from_descriptors(model, P, Zc, lone_c, Zh, lone_m):
     B, M = len(P), len(Zh)
     dot = P.reshape(B, -1) @ Zh.reshape(M, -1).T
     same = Zc[:, None] == np.asarray(model.ind_Z)[None, :]
-    ok_c = ~np.isin(Zc, np.asarray(model.a_not, dtype=np.int64)) & ~lone_c
-    ok_m = ~np.isin(np.asarray(model.ind_Z), np.asarray(model.a_not, dtype=np.int64)) & ~lone_m
+    ok_c = ~model.excluded_centres(Zc) & ~lone_c
+    ok_m = ~model.excluded_centres(model.ind_Z) & ~lone_m
     K = np.where(same & ok_c[:, None] & ok_m[None, :], _powxi(dot, model.xi), 0.0)
     K = K + (same & lone_c[:, None] & lone_m[None, :])
     return K, dot, same & ok_c[:, None] & ok_m[None, :]
@@ -531,7 +542,7 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
         e_local[k0 : k0 + len(idx)] = K @ mu
         # self kernel k(x,x) (active.py:785-788): 1 for a normalised descriptor, 0 for an
         # excluded centre, 1 for a neighbour-less atom (similarity.py:94-103)
-        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, 1.0, np.where(np.isin(numbers[idx], np.asarray(model.a_not, dtype=np.int64)), 0.0, 1.0))
+        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, 1.0, np.where(model.excluded_centres(numbers[idx]), 0.0, 1.0))
         if Kout is not None:
             Kout[k0 : k0 + len(idx)] = K
         xi = model.xi

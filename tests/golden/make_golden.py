@@ -127,6 +127,14 @@ def case_inputs(name):
         sp, sc, sn = fcc(2, [3, 8], 0.15, 115, a0=3.9)
         envs = pick_inducing(sp, sc, True, sn, 5.0, 10, 16)
         pbc = [True] * 3
+    elif name == "subse_3sp":
+        # default_kernel(species=[3, 8]): one SubSeSoapKernel per central species; S atoms (16) are present in
+        # the structure but are neither centres nor counted as neighbours
+        kern = dict(kind="subsesoap", lmax=3, nmax=2, xi=4, rc=5.0, species=[3, 8])
+        pos, cell, num = fcc((2, 2, 3), [3, 8, 16], 0.1, 17, a0=3.9)
+        sp, sc, sn = fcc(3, [3, 8, 16], 0.15, 117, a0=3.9)
+        envs = [e for e in pick_inducing(sp, sc, True, sn, 5.0, 15, 18) if e[0] in (3, 8)]
+        pbc = [True] * 3
     else:
         raise KeyError(name)
     M = len(envs)
@@ -141,6 +149,7 @@ def case_inputs(name):
 
 CASES = [
     "cu108_sesoap", "cu108_perfect", "lipso108", "tric_oh", "universal_2sp", "cluster_lone", "slab_ttf", "highres_l6n8", "anot_xi2",
+    "subse_3sp",
 ]
 
 
@@ -157,7 +166,8 @@ def species_dense(desc, species, kind):
 def run_case(name):
     c = case_inputs(name)
     k = c["kernel"]
-    kern = rr.make_kernel(k["kind"], k["lmax"], k["nmax"], k["xi"], k["rc"], a_not=k.get("a_not", ()))
+    kern = rr.make_kernel(k["kind"], k["lmax"], k["nmax"], k["xi"], k["rc"], a_not=k.get("a_not", ()),
+                          radii={"species": k["species"]} if k["kind"] == "subsesoap" else None)
     model = rr.synth_model(kern, c["envs"], c["mu"], c["mean_w"], c["choli"], c["vscale"])
     t0 = time.time()
     want = [0, len(c["pos"]) // 2, len(c["pos"]) - 1]
@@ -173,17 +183,21 @@ def run_case(name):
     ind_first = np.cumsum([0] + [len(e[2]) for e in envs]).astype(np.int64)
     species = np.unique(np.concatenate([c["numbers"]] + [e[2] for e in envs] + [[e[0] for e in envs]]).astype(np.int64))
     descs = {}
-    for a, d in ref["descriptors"].items():
-        if d is not None:
-            descs[f"desc_{a}"] = species_dense(d, species, k["kind"])
-    # descriptors of the inducing LCEs cached by the reference (loc.kern_0_value)
     zdesc = []
-    for loc in model.X:
-        v = loc.__dict__.get("kern_0_value")
-        zdesc.append(np.zeros((len(species), len(species), kern.dim)) if v is None else species_dense(v.detach().to_dense().numpy(), species, k["kind"]))
+    if k["kind"] == "subsesoap":
+        zdesc = [np.zeros((1,))] * len(model.X)   # dense per-kernel caches: not stored (the oracle is pinned through K)
+    else:
+        for a, d in ref["descriptors"].items():
+            if d is not None:
+                descs[f"desc_{a}"] = species_dense(d, species, k["kind"])
+        # descriptors of the inducing LCEs cached by the reference (loc.kern_0_value)
+        for loc in model.X:
+            v = loc.__dict__.get("kern_0_value")
+            zdesc.append(np.zeros((len(species), len(species), kern.dim)) if v is None else species_dense(v.detach().to_dense().numpy(), species, k["kind"]))
     meta = dict(kernel=k, pbc=[bool(x) for x in c["pbc"]], mean_w={str(z): w for z, w in c["mean_w"].items()},
                 vscale={str(z): v for z, v in c["vscale"].items()}, species=[int(z) for z in species],
                 unit=(float(kern.descriptor.unit) if k["kind"] == "universal" else None),
+                a_only=(k["species"] if k["kind"] == "subsesoap" else []), b_only=(k["species"] if k["kind"] == "subsesoap" else []),
                 generator="tests/golden/make_golden.py", reference="theforce v2021.09", ref_seconds=round(dt, 2))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),

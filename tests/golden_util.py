@@ -40,4 +40,19 @@ def oracle_model(g, big=False):
         ind_Z=g["ind_Z"], ind_r=g["envs_r"], ind_b=g["envs_b"], mu=g["mu_big"] if big else g["mu"],
         mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()}, choli=g["choli"],
         vscale={int(z): v for z, v in g["meta"]["vscale"].items()}, a_not=tuple(k.get("a_not", ())),
+        a_only=tuple(g["meta"].get("a_only", ())), b_only=tuple(g["meta"].get("b_only", ())),
     )
+
+
+def b200_model(g, big=False):
+    """The same golden model as an autoforce_b200.SgprModel (product-side container)."""
+    import autoforce_b200 as ab
+
+    k = g["meta"]["kernel"]
+    radii, default = golden_radii(g["meta"])
+    return ab.SgprModel(
+        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind="universal" if k["kind"] == "universal" else "sesoap",
+        radii=radii, default_radius=default, a_not=tuple(k.get("a_not", ())), a_only=tuple(g["meta"].get("a_only", ())),
+        b_only=tuple(g["meta"].get("b_only", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
+        mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
+        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()})

@@ -107,3 +107,27 @@ def test_extract_from_reference_model():
     assert np.array_equal(m.ind_r, g["ind_r"]) and np.array_equal(m.ind_b, g["ind_b"])
     assert np.array_equal(m.mu, g["mu"]) and np.array_equal(m.choli, g["choli"])
     assert m.mean_w == {int(z): w for z, w in g["meta"]["mean_w"].items()}
+
+
+def test_extract_subsesoap_kernel_list_from_reference_model():
+    """default_kernel(species=...) = one SubSeSoapKernel per central species (calculator/active.py:28-38)."""
+    from oracle import ref_runner as rr
+
+    if not rr.reference_available():
+        pytest.skip("/root/reference not present")
+    import autoforce_b200 as ab
+    from golden_util import load_golden
+
+    g = load_golden("subse_3sp")
+    k = g["meta"]["kernel"]
+    kern = rr.make_kernel("subsesoap", k["lmax"], k["nmax"], k["xi"], k["rc"], radii={"species": k["species"]})
+    envs = [(int(z), r, b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    ref_model = rr.synth_model(kern, envs, g["mu"], {int(z): w for z, w in g["meta"]["mean_w"].items()}, g["choli"],
+                               {int(z): v for z, v in g["meta"]["vscale"].items()})
+    m = ab.SgprModel.from_posterior_potential(ref_model)
+    assert (m.lmax, m.nmax, m.xi, m.rc) == (k["lmax"], k["nmax"], float(k["xi"]), k["rc"])
+    assert m.a_only == (3, 8) and m.b_only == (3, 8)
+    assert m.is_centre(3) and not m.is_centre(16) and m.is_neighbour(8) and not m.is_neighbour(16)
+    assert np.array_equal(m.ind_r, g["ind_r"]) and np.array_equal(m.mu, g["mu"])
+    mirror = ab.SubSeSoapKernel(3, 2, 4, 5.0, 3, [3, 8], radii=ab.DefaultRadii())
+    assert mirror.state == kern[0].state

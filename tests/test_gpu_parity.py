@@ -20,15 +20,9 @@ TOL_S = 1e-9            # north_star: 1e-6 eV/A^3
 
 
 def model_from_golden(g, big=False):
-    import autoforce_b200 as ab
+    from golden_util import b200_model
 
-    k = g["meta"]["kernel"]
-    radii, default = golden_radii(g["meta"])
-    return ab.SgprModel(
-        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind=k["kind"], radii=radii, default_radius=default,
-        a_not=tuple(k.get("a_not", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
-        mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
-        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()})
+    return b200_model(g, big)
 
 
 def sorted_rows(first, J, S):
@@ -63,6 +57,8 @@ def test_neighbor_list_bit_exact(case):
 
 def test_descriptors_match_reference_cache(case):
     g, eng = case
+    if g["meta"]["kernel"]["kind"] == "subsesoap":
+        pytest.skip("dense per-kernel caches are not stored for SubSeSoapKernel lists")
     species = np.array(g["meta"]["species"])
     Zh = eng.inducing_descriptors()
     keep = ~np.isin(g["ind_Z"], np.array(g["meta"]["kernel"].get("a_not", []), dtype=np.int64))

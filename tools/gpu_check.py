@@ -20,13 +20,9 @@ import autoforce_b200 as ab  # noqa: E402
 
 
 def model_from_golden(g, big=False):
-    k = g["meta"]["kernel"]
-    radii, default = golden_radii(g["meta"])
-    return ab.SgprModel(
-        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind=k["kind"], radii=radii, default_radius=default,
-        a_not=tuple(k.get("a_not", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
-        mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
-        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()})
+    from golden_util import b200_model
+
+    return b200_model(g, big)
 
 
 def sorted_rows(first, J, S):

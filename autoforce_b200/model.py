@@ -85,6 +85,14 @@ class SgprModel:
         b = np.concatenate([np.asarray(e[2], dtype=np.int32).reshape(-1) for e in envs]) if envs else np.zeros(0, np.int32)
         return cls(ind_Z=np.array([e[0] for e in envs], dtype=np.int32), ind_first=first, ind_r=r, ind_b=b, **kw)
 
+    @classmethod
+    def from_tape(cls, path, mu=None, **kw):
+        """Inducing LCEs from an AutoForce ``.sgpr`` tape (theforce/io/sgprio.py); hyper-parameters and the
+        weights are passed by the caller (the tape stores neither)."""
+        from .sgprio import read_lces
+
+        return cls.from_envs(read_lces(path), mu=mu, **kw)
+
     # ------------------------------------------------------------------ reference model
     @classmethod
     def from_posterior_potential(cls, model):

@@ -131,3 +131,46 @@ def test_extract_subsesoap_kernel_list_from_reference_model():
     assert np.array_equal(m.ind_r, g["ind_r"]) and np.array_equal(m.mu, g["mu"])
     mirror = ab.SubSeSoapKernel(3, 2, 4, 5.0, 3, [3, 8], radii=ab.DefaultRadii())
     assert mirror.state == kern[0].state
+
+
+def test_sgpr_tape_reader_roundtrip(tmp_path):
+    """autoforce_b200.sgprio against the tape format of theforce/io/sgprio.py:16-143 (include: directives,
+    atoms blocks skipped, 8-decimal coordinates)."""
+    import autoforce_b200 as ab
+    from autoforce_b200 import sgprio
+
+    rng = np.random.default_rng(3)
+    envs = [(29, rng.normal(size=(4, 3)), np.array([29, 8, 8, 1])), (8, np.zeros((0, 3)), np.zeros(0, int)), (1, rng.normal(size=(2, 3)), np.array([8, 29]))]
+    inc = tmp_path / "inc.sgpr"
+    main = tmp_path / "model.sgpr"
+    with open(inc, "w") as f:
+        sgprio.write_lce(f, *envs[2])
+    with open(main, "w") as f:
+        sgprio.write_lce(f, *envs[0])
+        f.write("\\nstart: atoms\\n2\\nLattice=\\"1 0 0 0 1 0 0 0 1\\" Properties=species:S:1:pos:R:3\\nCu 0 0 0\\nO 0.5 0.5 0.5\\nend: atoms\\n")
+        sgprio.write_lce(f, *envs[1])
+        f.write("include: inc.sgpr\\ninclude: model.sgpr\\n")   # self-include must be ignored
+    got = sgprio.read_lces(str(main))
+    assert [e[0] for e in got] == [29, 8, 1]
+    for (z, r, b), (z0, r0, b0) in zip(got, envs):
+        assert np.array_equal(b, b0) and np.abs(r - np.asarray(r0).reshape(-1, 3)).max(initial=0.0) < 5e-9
+    m = ab.SgprModel.from_tape(str(main), lmax=3, nmax=3, xi=4.0, rc=6.0, radii={1: 0.5})
+    assert m.M == 3 and list(m.ind_first) == [0, 4, 4, 6]
+    # same bytes as the reference's writer, when the reference is importable
+    from oracle import ref_runner as rr
+
+    if rr.reference_available():
+        import io
+
+        import torch
+
+        rr.import_reference()
+        from theforce.descriptor.atoms import Local
+        from theforce.io.sgprio import write_lce as ref_write
+
+        z, r, b = envs[0]
+        loc = Local(0, np.arange(1, 5), z, b, torch.as_tensor(r))
+        buf_ref, buf_own = io.StringIO(), io.StringIO()
+        ref_write(loc, buf_ref)
+        sgprio.write_lce(buf_own, z, r, b)
+        assert buf_own.getvalue() == "\\nstart: local\\n" + buf_ref.getvalue() + "end: local\\n"

@@ -147,9 +147,9 @@ def test_sgpr_tape_reader_roundtrip(tmp_path):
         sgprio.write_lce(f, *envs[2])
     with open(main, "w") as f:
         sgprio.write_lce(f, *envs[0])
-        f.write("\\nstart: atoms\\n2\\nLattice=\\"1 0 0 0 1 0 0 0 1\\" Properties=species:S:1:pos:R:3\\nCu 0 0 0\\nO 0.5 0.5 0.5\\nend: atoms\\n")
+        f.write("\nstart: atoms\n2\nLattice=\"1 0 0 0 1 0 0 0 1\" Properties=species:S:1:pos:R:3\nCu 0 0 0\nO 0.5 0.5 0.5\nend: atoms\n")
         sgprio.write_lce(f, *envs[1])
-        f.write("include: inc.sgpr\\ninclude: model.sgpr\\n")   # self-include must be ignored
+        f.write("include: inc.sgpr\ninclude: model.sgpr\n")   # self-include must be ignored
     got = sgprio.read_lces(str(main))
     assert [e[0] for e in got] == [29, 8, 1]
     for (z, r, b), (z0, r0, b0) in zip(got, envs):
@@ -173,4 +173,4 @@ def test_sgpr_tape_reader_roundtrip(tmp_path):
         buf_ref, buf_own = io.StringIO(), io.StringIO()
         ref_write(loc, buf_ref)
         sgprio.write_lce(buf_own, z, r, b)
-        assert buf_own.getvalue() == "\\nstart: local\\n" + buf_ref.getvalue() + "end: local\\n"
+        assert buf_own.getvalue() == "\nstart: local\n" + buf_ref.getvalue() + "end: local\n"

@@ -592,7 +592,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
 // pipeline
 // =====================================================================================
 static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
-                       const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false) {
+                       const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false,
+                       bool with_halo = true) {
     h->use_i8_now = i8 && h->use_i8;
     h->stats.i8_ops = 0.0;
     h->fwd_valid = false;
@@ -614,7 +615,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     if (world == 1)
         SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs));  // synchronises the stream
     else
-        SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs));
+        SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs, with_halo));
     h->stats.n_active = h->n_active;
     h->stats.n_pairs = n_pairs;
     if (h->timing) cudaEventRecord(h->ev[1], st);
@@ -625,11 +626,15 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     return SGPR_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
-                            const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
-                            double* W_d, double* beta_d, uint8_t* owned_d) {
-    if (!h || !cell_h || !pbc_h || !E_d || !F_d || !W_d || (N > 0 && (!pos_d || !Z_d))) {
+static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                        const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
+                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h) {
+    if (!h || !cell_h || !pbc_h || !E_d || (!F_d && !peer_f_h) || !W_d || (N > 0 && (!pos_d || !Z_d))) {
         set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    if (peer_f_h && world > SGPR_MAX_RANKS) {
+        set_error("peer-memory force exchange supports at most %d ranks", SGPR_MAX_RANKS);
         return SGPR_ERR_INVALID;
     }
     if (world < 1 || rank < 0 || rank >= world) {
@@ -643,7 +648,18 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
-    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/beta_d == nullptr));
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/beta_d == nullptr,
+                         /*with_halo=*/peer_f_h == nullptr));
+    PeerForces peers{};
+    if (peer_f_h) {
+        peers.world = world;
+        for (int r = 0; r < world; ++r) {
+            peers.peer_f[r] = (double*)(uintptr_t)peer_f_h[r];
+            peers.bounds[r] = (int)((N * r) / world);
+        }
+        peers.bounds[world] = (int)N;
+        h->p2p_rank = rank;
+    }
     const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
     const int* active = h->active_all ? nullptr : h->active_list.as<int>();
     const int grid_g = 128;   // blocks (= energy partials) of row_energy_kernel
@@ -668,7 +684,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
     SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)grid_g + nblk_x), st));
     SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
-    SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+    if (!peer_f_h) SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
     if (beta_d) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
     if (h->use_i8_now)
         SGPR_TRY(i8_kernel_matrix(h, st));
@@ -683,14 +699,15 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
     else
         SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
-    SGPR_TRY(descriptor_backward_atoms(h, g, owned, st));
+    SGPR_TRY(descriptor_backward_atoms(h, g, owned, st, peer_f_h ? &peers : nullptr));
     if (N > 0) {
         atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, active, h->atoms.as<AtomRec>(),
                                                   h->nl_first.as<long long>(), owned, h->mean_w_d.as<double>(),
                                                   h->lone_mu.as<double>(),
                                                   h->epart.as<double>() + (size_t)grid_g);
-        scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
-                                                                      owned, F_d, owned_d);
+        if (!peer_f_h)
+            scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
+                                                                          owned, F_d, owned_d);
     }
     final_reduce_kernel<<<1, 256, 0, st>>>(grid_g, h->epart.as<double>(), nblk_x,
                                            h->epart.as<double>() + (size_t)grid_g, nblk_b,
@@ -726,6 +743,41 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h
         cudaEventElapsedTime(&h->stats.ms_beta, h->ev[4], h->ev[5]);
         cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[5]);
     }
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                            const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
+                            double* W_d, double* beta_d, uint8_t* owned_d) {
+    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, nullptr);
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_predict_p2p(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                                const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world, void* stream,
+                                const uint64_t* peer_f_h, double* E_d, double* W_d) {
+    if (!peer_f_h || world < 1) {
+        set_error("null peer table");
+        return SGPR_ERR_INVALID;
+    }
+    if (world == 1) {
+        set_error("sgpr_predict_p2p needs world > 1 (use sgpr_predict)");
+        return SGPR_ERR_INVALID;
+    }
+    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f_h);
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double* F_d, uint8_t* owned_d) {
+    if (!h || !own_f_d || !F_d) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    const int64_t N = h->last_N;
+    if (N > 0)
+        scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), own_f_d,
+                                                                      h->owned.as<unsigned char>(), F_d, owned_d);
+    SGPR_CUDA(cudaGetLastError());
     return SGPR_OK;
 }
 

@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
 // backward: forces + virial
 // ---------------------------------------------------------------------------------
 struct BackOut {
+    PeerForces peers;            // world > 0: neighbour forces are added into the owner rank's buffer (NVLink)
     double* fcell;               // [N,3] forces in cell order (atomically accumulated)
     double* wpart;               // [gridDim.x, 9] per-block virial partials
     const unsigned char* owned;  // by cell-order index, nullptr = all owned
@@ -429,7 +430,17 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
                 Wacc[3] += ry * Gx; Wacc[4] += ry * Gy; Wacc[5] += ry * Gz;
                 Wacc[6] += rz * Gx; Wacc[7] += rz * Gy; Wacc[8] += rz * Gz;
             }
-            if (!out.owned || out.owned[j]) {
+            if (out.peers.world > 0) {
+                // owner of neighbour j: rank r with bounds[r] <= j < bounds[r+1]; its buffer is peer-mapped
+                int r = 0;
+#pragma unroll
+                for (int q = 1; q < SGPR_MAX_RANKS; ++q)
+                    if (q < out.peers.world && j >= out.peers.bounds[q]) r = q;
+                double* dst = out.peers.peer_f[r] + 3 * (size_t)j;
+                atomicAdd(dst, -Gx);
+                atomicAdd(dst + 1, -Gy);
+                atomicAdd(dst + 2, -Gz);
+            } else if (!out.owned || out.owned[j]) {
                 atomicAdd(out.fcell + 3 * (size_t)j, -Gx);
                 atomicAdd(out.fcell + 3 * (size_t)j + 1, -Gy);
                 atomicAdd(out.fcell + 3 * (size_t)j + 2, -Gz);
@@ -600,7 +611,8 @@ int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st) {
 
 int backward_grid(sgpr_context* h) { return h->sm_count * 16; }
 
-int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st) {
+int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st,
+                              const PeerForces* peers) {
     const int na = (int)h->n_active;
     if (na == 0) return SGPR_OK;
     EnvSrc src{};
@@ -609,7 +621,8 @@ int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned cha
     src.nl_first = h->nl_first.as<long long>();
     src.active = h->active_all ? nullptr : h->active_list.as<int>();
     BackOut out{};
-    out.fcell = h->fcell.as<double>();
+    if (peers) out.peers = *peers;
+    out.fcell = (peers && peers->world > 0) ? peers->peer_f[h->p2p_rank] : h->fcell.as<double>();
     out.wpart = h->wpart.as<double>();
     out.owned = owned_d;
     out.sp_on = h->sp_on.as<unsigned char>();

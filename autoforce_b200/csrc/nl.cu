@@ -670,7 +670,7 @@ __global__ void species_rows_kernel(int na, const int* __restrict__ active, cons
 // Owned range of the cell order + exact one-cutoff halo (atoms that have an owned atom as a
 // neighbour).  Active list = owned ++ halo; rows are species-major over the active list.
 int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
-                           int64_t* n_pairs) {
+                           int64_t* n_pairs, bool with_halo) {
     const int S = h->S;
     const int c0 = (int)((N * rank) / world), c1 = (int)((N * (rank + 1)) / world);
     const int n_own = c1 - c0;
@@ -693,18 +693,18 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     const int nblkN = (int)((N + 1 + T - 1) / T);
     shard_init_kernel<<<nblkN, T, 0, st>>>(N, c0, c1, owned, mark, active, rowof);
     h->n_active = n_own;
-    SGPR_TRY(launch_count(h, 0, n_own, g, mark, st));
-    halo_flag_kernel<<<nblkN, T, 0, st>>>(N, owned, mark, flag);
-    {
+    SGPR_TRY(launch_count(h, 0, n_own, g, with_halo ? mark : nullptr, st));
+    int n_halo = 0;
+    if (with_halo) {
+        halo_flag_kernel<<<nblkN, T, 0, st>>>(N, owned, mark, flag);
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, flag, pos, (int)N + 1, st);
         SGPR_TRY(h->scan_tmp.ensure(tmp));
         SGPR_CUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp, flag, pos, (int)N + 1, st));
+        halo_scatter_kernel<<<nblkN, T, 0, st>>>(N, flag, pos, n_own, active);
+        SGPR_CUDA(cudaMemcpyAsync(&n_halo, pos + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaStreamSynchronize(st));
     }
-    halo_scatter_kernel<<<nblkN, T, 0, st>>>(N, flag, pos, n_own, active);
-    int n_halo = 0;
-    SGPR_CUDA(cudaMemcpyAsync(&n_halo, pos + N, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaStreamSynchronize(st));
     const int na = n_own + n_halo;
     h->n_active = na;
     SGPR_TRY(launch_count(h, n_own, n_halo, g, nullptr, st));

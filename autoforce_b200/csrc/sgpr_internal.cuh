@@ -9,6 +9,8 @@
 #include "../../include/sgpr_b200.h"
 #include "sgpr_math.cuh"
 
+#define SGPR_MAX_RANKS 16
+
 namespace sgpr {
 
 // ----------------------------------------------------------------------------------
@@ -159,6 +161,7 @@ struct sgpr_context {
     int64_t n_active = 0;
     int64_t n_owned = 0;
     bool active_all = true;
+    int p2p_rank = 0;                        // this rank in a peer-memory force exchange
     bool fwd_valid = false;                  // state of the last sgpr_kernel_forward is intact (for the VJP)
     int row_first[SGPR_MAX_SPECIES + 1];     // first descriptor row of each central species
     sgpr::Geom last_geom;
@@ -175,7 +178,7 @@ int build_geometry(sgpr_context* h, int64_t N, const double* pos_d, const double
 int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const Geom& g, cudaStream_t st);
 int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs);
 int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
-                           int64_t* n_pairs);
+                           int64_t* n_pairs, bool with_halo = true);
 int scan_exclusive_ll(sgpr_context* h, const long long* in, long long* out, int n, cudaStream_t st);
 
 // ---- descriptor.cu ----------------------------------------------------------------
@@ -183,7 +186,14 @@ int upload_harm_coef();
 int descriptor_forward_env(sgpr_context* h, int M, const long long* env_first_d, const double* env_r_d,
                            const unsigned char* env_sp_d, const int* row_of_d, double* phat_d, cudaStream_t st);
 int descriptor_forward_atoms(sgpr_context* h, const Geom& g, cudaStream_t st);
-int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st);
+// peer-memory force exchange: neighbour forces go to the owner rank's buffer (peer_f[r] valid on this device)
+struct PeerForces {
+    double* peer_f[SGPR_MAX_RANKS];
+    int bounds[SGPR_MAX_RANKS + 1];   // first cell-order index owned by each rank
+    int world;                        // 0 = disabled
+};
+int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st,
+                              const PeerForces* peers = nullptr);
 int backward_grid(sgpr_context* h);
 int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, const int* src_row_d, double* full_d,
                        cudaStream_t st);

@@ -49,6 +49,9 @@ EXPORTS = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_predict_host": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_predict_p2p": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    "sgpr_p2p_collect": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_forward": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_neighbors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -91,6 +94,56 @@ def _check(lib, status):
 
 def _ptr(a):
     return c_void_p(a.ctypes.data)
+
+
+class PeerForceExchange:
+    """Atom-sharded prediction without halo recompute: every rank evaluates the environments it owns and adds
+    the forces on atoms of other ranks straight into their accumulation buffers over NVLink (peer-mapped
+    symmetric memory, ``sgpr_predict_p2p``).  The only collective is the all-reduce of E + 3x3 virial
+    (10 doubles), which doubles as the barrier after which each rank collects its own forces.
+    Two accumulation buffers alternate between steps so that zeroing never races with remote adds."""
+
+    def __init__(self, engine, N, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.engine, self.N = engine, int(N)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = torch.device("cuda", engine.device)
+        self.stride = 3 * self.N + 8
+        self.buf = symm.empty(2 * self.stride, dtype=torch.float64, device=dev)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.parity = 0
+        self.ew = torch.zeros(10, dtype=torch.float64, device=dev)
+        self.F = torch.zeros((self.N, 3), dtype=torch.float64, device=dev)
+        self.owned = torch.zeros(self.N, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    def step(self, pos_t, z_t, cell, pbc):
+        """Device tensors in; returns (E, F_owned [N,3], W [3,3] tensor, owned mask) with E and W already summed
+        over the ranks."""
+        import torch.distributed as dist
+
+        eng, lib = self.engine, self.engine.lib
+        p = self.parity
+        # the other buffer was collected at the end of the previous step: clear it for the next one
+        self.buf[(1 - p) * self.stride:(2 - p) * self.stride].zero_()
+        peers = np.array([ptr + 8 * p * self.stride for ptr in self.ptrs], dtype=np.uint64)
+        cell_h, pbc_h = eng._geom(cell, pbc)
+        _check(lib, lib.sgpr_predict_p2p(eng._h, self.N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()), _ptr(cell_h),
+                                         _ptr(pbc_h), self.rank, self.world, eng._stream(), _ptr(peers),
+                                         c_void_p(self.ew.data_ptr()), c_void_p(self.ew.data_ptr() + 8)))
+        dist.all_reduce(self.ew, group=self.group)   # E + virial; also: every rank's force kernel has finished
+        own = self.buf[p * self.stride:(p + 1) * self.stride]
+        _check(lib, lib.sgpr_p2p_collect(eng._h, eng._stream(), c_void_p(own.data_ptr()), c_void_p(self.F.data_ptr()),
+                                         c_void_p(self.owned.data_ptr())))
+        self.parity = 1 - p
+        return self.ew[0], self.F, self.ew[1:].view(3, 3), self.owned
 
 
 def _make_cov_function():
@@ -232,6 +285,10 @@ class SgprEngine:
                                                _ptr(pbc_h), rank, world, self._stream(), c_void_p(E.data_ptr()),
                                                c_void_p(F.data_ptr()), c_void_p(W.data_ptr()), None, None))
         return E, F, W
+
+    def peer_exchange(self, N, group=None):
+        """Set up the peer-memory (NVLink) force exchange for structures of N atoms (torch symmetric memory)."""
+        return PeerForceExchange(self, N, group)
 
     def kernel_matrix(self, pos, numbers, cell, pbc):
         import torch

@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="atoms in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variants", type=int, default=4, help="pre-generated perturbed position sets cycled over the steps")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "halo"],
+                    help="multi-GPU force exchange: peer-memory adds over NVLink (default) or halo recompute")
     return ap.parse_args()
 
 
@@ -52,12 +54,13 @@ def workload_inputs(name, variants):
     return w, pos_variants, cell, numbers
 
 
-def config_of(name, w, N, M, world):
+def config_of(name, w, N, M, world, exchange="none"):
     return {
         "workload": f"{name}: fcc-derived {N}-atom {'/'.join(str(z) for z in w['Zs'])} solid, frozen random-init SGPR model "
                     f"M={M}, SeSoap lmax={w['lmax']} nmax={w['nmax']} rc={w['rc']}, xi=4",
         "atoms": N, "inducing": M, "species": len(w["Zs"]),
-        "parallelism": f"atoms sharded over {world} GPU(s); positions replicated; all-reduce of E + 3x3 virial only",
+        "parallelism": f"atoms sharded over {world} GPU(s); positions replicated; all-reduce of E + 3x3 virial only"
+                       + ("" if world == 1 else f"; forces: {exchange}"),
         "cache": "working set (pair list + descriptor/gradient matrices, >500 MB at c3) exceeds the 126 MB L2; positions change every step",
     }
 
@@ -192,7 +195,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    exchange = "none"
+    px = None
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                px = eng.peer_exchange(N)
+            except Exception as ex:  # symmetric memory unavailable -> halo recompute
+                if rank == 0:
+                    print(f"bench: peer-memory exchange unavailable ({ex}); falling back to halo recompute", file=sys.stderr)
+                exchange = "halo"
+        ok = torch.tensor([1 if exchange == "p2p" else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange, px = "halo", None
+    pin_pos = torch.empty((N, 3), dtype=torch.float64).pin_memory() if px is not None else None
+    pin_F = torch.empty((N, 3), dtype=torch.float64).pin_memory() if px is not None else None
+    dev_pos = torch.empty((N, 3), dtype=torch.float64, device=dev) if px is not None else None
+
     def step_device(it):
+        if px is not None:
+            px.step(pos_d[it % len(pos_d)], z_d, cell, pbc)
+            return
         E, F, W = eng.predict_device(pos_d[it % len(pos_d)], z_d, cell, pbc, rank=rank, world=world, out=out)
         if world > 1:  # the only collective of the path: 10 doubles
             ew[0:1].copy_(E)
@@ -200,6 +225,14 @@ def main():
             dist.all_reduce(ew)
 
     def step_host(it):
+        if px is not None:   # host buffers in and out around the peer-memory step
+            pin_pos.copy_(torch.from_numpy(pos_variants[it % len(pos_variants)]))
+            dev_pos.copy_(pin_pos, non_blocking=True)
+            E, F, W, owned = px.step(dev_pos, z_d, cell, pbc)
+            pin_F.copy_(F, non_blocking=True)
+            Eh = float(E.item())   # D2H of the reduced energy: synchronises the step
+            torch.cuda.current_stream().synchronize()
+            return Eh
         E, F, W, owned = eng.predict(pos_variants[it % len(pos_variants)], numbers, cell, pbc, rank=rank, world=world)
         if world > 1:
             t = torch.tensor([E] + list(W.reshape(-1)), dtype=torch.float64, device=dev)
@@ -293,7 +326,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_of(args.workload, w, N, model.M, world),
+            "data": "synthetic", "config": config_of(args.workload, w, N, model.M, world, {"p2p": "peer-memory adds over NVLink into the owner's buffer (no halo recompute)", "halo": "owner-computes with one-cutoff halo recompute", "none": ""}[exchange]),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": wall_e2e / K,
                     "h2d_bytes_per_step": int(N * 24 + N * 4), "d2h_bytes_per_step": int(N * 24 + 16 * 8 + N)},
             "gpu_launches": int(stage["launches"]),

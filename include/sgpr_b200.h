@@ -127,6 +127,23 @@ int sgpr_predict_host(sgpr_handle h, int64_t N, const double* pos_h, const int32
                       const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world,
                       double* E_h, double* F_h, double* W_h, double* beta_h, uint8_t* owned_h);
 
+/* Atom-sharded prediction with a PEER-MEMORY force exchange over NVLink instead of the halo recompute
+ * of sgpr_predict(rank, world): every rank evaluates only the environments it owns; the force each
+ * environment exerts on a neighbour owned by another rank is added (red.global.add.f64) straight into
+ * that rank's accumulation buffer through a peer mapping.  Replaces the reference's all_reduce of the
+ * [N,3] force array (calculator/active.py:601); the only collective left is the caller's all-reduce
+ * of E_d[1] and W_d[9].
+ *   peer_f_h [world]  host array of device pointers: peer_f_h[r] = rank r's accumulation buffer
+ *                     (3*N doubles, cell order, zero on entry), mapped into this device's address space
+ *                     (e.g. torch symmetric memory / cudaIpcOpenMemHandle); peer_f_h[rank] is local.
+ * After ALL ranks have finished this call (the caller's E/W all-reduce is the barrier), each rank reads
+ * its own forces with sgpr_p2p_collect. */
+int sgpr_predict_p2p(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                     const double* cell_h, const int32_t* pbc_h, int32_t rank, int32_t world,
+                     void* stream, const uint64_t* peer_f_h, double* E_d, double* W_d);
+/* own accumulation buffer -> F_d [N,3] (caller's atom order; 0 for atoms of other ranks), owned_d [N]. */
+int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double* F_d, uint8_t* owned_d);
+
 /* Kernel matrix cov = model.gp.kern(atoms, model.X)  (calculator/active.py:464,
  * regression/gppotential.py:47-50,63-64; similarity/similarity.py:17-31).
  *   K_d [N,M] row-major, atoms and inducing LCEs in the caller's order. */

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
 
     hdr = open(os.path.join(ROOT, "include", "sgpr_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(sgpr_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(sgpr_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     assert declared == set(eng.EXPORTS), (declared ^ set(eng.EXPORTS))
     for name in declared:

@@ -1,0 +1,44 @@
+"""Developer/CI tool (>= 2 GPUs, torchrun): the peer-memory force exchange against the unsharded result.
+   torchrun --nproc-per-node 2 tools/p2p_check.py [workload]"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+import autoforce_b200 as ab
+from autoforce_b200 import synth
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+w = synth.WORKLOADS[wl]
+model = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"])
+pos, cell, numbers = synth.fcc(w["rep"], w["Zs"], 0.1, 0)
+N = len(pos)
+eng = ab.SgprEngine(model, species=w["Zs"], device=local)
+E0, F0, W0, _ = eng.predict(pos, numbers, cell, True)            # unsharded reference on this GPU
+px = eng.peer_exchange(N)
+z_t = torch.as_tensor(numbers.astype(np.int32), device=dev)
+ok = True
+rng = np.random.default_rng(5)
+for it in range(4):                                              # several steps: buffer alternation
+    p = pos + (rng.normal(0, 0.02, pos.shape) if it else 0.0)
+    Er, Fr, Wr, _ = eng.predict(p, numbers, cell, True)
+    E, F, W, owned = px.step(torch.as_tensor(p, device=dev), z_t, cell, True)
+    torch.cuda.synchronize()
+    owned = owned.cpu().numpy().astype(bool)
+    F = F.cpu().numpy()
+    dE = abs(float(E) - Er) / N
+    dW = np.abs(W.cpu().numpy() - Wr).max()
+    dF = np.abs(F[owned] - Fr[owned]).max()
+    cnt = torch.tensor([int(owned.sum())], device=dev)
+    dist.all_reduce(cnt)
+    good = dE < 1e-11 and dW < 1e-8 and dF < 1e-10 and int(cnt.item()) == N and np.all(F[~owned] == 0)
+    ok &= good
+    print(f"rank {rank} step {it}: dE/N={dE:.2e} dW={dW:.2e} dF={dF:.2e} owned={int(owned.sum())} total_owned={int(cnt.item())} {'OK' if good else 'FAIL'}", flush=True)
+eng.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

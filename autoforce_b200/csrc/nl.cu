@@ -667,6 +667,48 @@ __global__ void species_rows_kernel(int na, const int* __restrict__ active, cons
     }
 }
 
+// Contiguous owned range [c0, c1) of the cell order (no halo): species-major local rows follow directly from
+// the two scans of cell_sort -- count of species-s atoms before a cell index c:
+//   before_s(c) = (rstartT[s][bin(c)] - rstartT[s][0]) + clamp(c - cstart[bin(c)][s], 0, cnt[bin(c)][s])
+__global__ void contig_species_kernel(int64_t N, int c0, int c1, int S, int ncell, const int* __restrict__ abin,
+                                      const int* __restrict__ cstart, const int* __restrict__ rstartT,
+                                      int* __restrict__ row_first_d, int* __restrict__ before0) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int s = 0; s < S; ++s) {
+        int b[2];
+        for (int e = 0; e < 2; ++e) {
+            const int c = e == 0 ? c0 : c1;
+            if (c >= N) {
+                b[e] = rstartT[s * ncell + ncell - 1] - rstartT[s * ncell] +
+                       (cstart[(ncell - 1) * S + s + 1] - cstart[(ncell - 1) * S + s]);
+            } else {
+                const int bin = abin[c];
+                const int lo = cstart[bin * S + s], hi = cstart[bin * S + s + 1];
+                b[e] = rstartT[s * ncell + bin] - rstartT[s * ncell] + max(0, min(c, hi) - lo);
+            }
+        }
+        before0[s] = b[0];
+        row_first_d[s] = acc;
+        acc += b[1] - b[0];
+    }
+    row_first_d[S] = acc;
+}
+__global__ void contig_rows_kernel(int c0, int n_own, int S, int ncell, const AtomRec* __restrict__ atoms,
+                                   const int* __restrict__ abin, const int* __restrict__ cstart,
+                                   const int* __restrict__ rstartT, const int* __restrict__ row_first_d,
+                                   const int* __restrict__ before0, int* __restrict__ rowof,
+                                   unsigned char* __restrict__ row_owned) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_own) return;
+    const int c = c0 + k;
+    const int s = meta_species(atoms[c].meta), bin = abin[c];
+    const int global_rank = rstartT[s * ncell + bin] - rstartT[s * ncell] + (c - cstart[bin * S + s]);
+    const int row = row_first_d[s] + (global_rank - before0[s]);
+    rowof[c] = row;
+    row_owned[row] = 1;
+}
+
 // Owned range of the cell order + exact one-cutoff halo (atoms that have an owned atom as a
 // neighbour).  Active list = owned ++ halo; rows are species-major over the active list.
 int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
@@ -678,7 +720,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     h->n_owned = n_own;
     SGPR_TRY(h->owned.ensure(2 * ((size_t)N + 1)));
     SGPR_TRY(h->active_list.ensure(sizeof(int) * ((size_t)N + 1)));
-    SGPR_TRY(h->shard_tmp.ensure(sizeof(int) * (2 * ((size_t)N + 2) + SGPR_MAX_SPECIES + 2)));
+    SGPR_TRY(h->shard_tmp.ensure(sizeof(int) * (2 * ((size_t)N + 2) + 2 * SGPR_MAX_SPECIES + 4)));
     SGPR_TRY(h->row_owned.ensure((size_t)N + 1));
     SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * S + 1)));
     SGPR_TRY(h->nl_masks.ensure(sizeof(unsigned) * kMaskSlots * ((size_t)N + 1)));
@@ -711,6 +753,22 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     // species-major rows over the active list
     SGPR_CUDA(cudaMemsetAsync(row_first_d, 0, sizeof(int) * (SGPR_MAX_SPECIES + 1), st));
     const int nblkA = (na + 1 + T - 1) / T;
+    if (!with_halo) {
+        // contiguous active set: two small kernels instead of S x (flag, scan, assign)
+        const int nkeys = g.ncell * S;
+        const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
+        int* before0 = row_first_d + SGPR_MAX_SPECIES + 1;
+        contig_species_kernel<<<1, 32, 0, st>>>(N, c0, c1, S, g.ncell, h->rowof.as<int>(), h->cstart.as<int>(), rstartT,
+                                                row_first_d, before0);
+        if (n_own > 0)
+            contig_rows_kernel<<<(n_own + T - 1) / T, T, 0, st>>>(c0, n_own, S, g.ncell, h->atoms.as<AtomRec>(),
+                                                                 h->rowof.as<int>(), h->cstart.as<int>(), rstartT,
+                                                                 row_first_d, before0, rowof,
+                                                                 h->row_owned.as<unsigned char>());
+        h->stats.kernel_launches += 3;
+        SGPR_CUDA(cudaGetLastError());
+        return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs);
+    }
     for (int s = 0; s < S; ++s) {
         species_flag_kernel<<<nblkA, T, 0, st>>>(na, active, h->atoms.as<AtomRec>(), s, flag);
         size_t tmp = 0;

@@ -279,6 +279,15 @@ static int upload(DevBuf& b, const void* src, size_t bytes) {
     return SGPR_OK;
 }
 
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int upload_weights(sgpr_context* h, const double* mu_h, const double* mean_w_h, const double* choli_h,
                           const double* vscale_h, const int64_t* ind_first_h) {
     const int M = h->M, S = h->S;
@@ -542,6 +551,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->i8_tr = (trs && atoi(trs) == 8) ? 8 : 7;
         if (h->use_i8) {
             st = i8_prepare_model(h, false);
+            if (st == SGPR_OK) st = i8_prepare_covloss(h);
             if (st != SGPR_OK) {
                 delete h;
                 return st;
@@ -565,7 +575,7 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
@@ -585,6 +595,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
     SGPR_CUDA(cudaDeviceSynchronize());
     SGPR_TRY(upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr));
     if (mu_h && h->use_i8) SGPR_TRY(i8_prepare_model(h, true));
+    if (choli_h && h->use_i8) SGPR_TRY(i8_prepare_covloss(h));
     return SGPR_OK;
 }
 
@@ -593,7 +604,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
 // =====================================================================================
 static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                        const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false,
-                       bool with_halo = true) {
+                       bool with_halo = true, bool with_k8 = false) {
     h->use_i8_now = i8 && h->use_i8;
     h->stats.i8_ops = 0.0;
     h->fwd_valid = false;
@@ -620,7 +631,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     h->stats.n_pairs = n_pairs;
     if (h->timing) cudaEventRecord(h->ev[1], st);
     SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)h->n_active + 1) * h->dp.ldp));
-    if (h->use_i8_now) SGPR_TRY(i8_ensure_step_buffers(h, (size_t)h->n_active));
+    if (h->use_i8_now) SGPR_TRY(i8_ensure_step_buffers(h, (size_t)h->n_active, with_k8));
     SGPR_TRY(descriptor_forward_atoms(h, *g, st));
     if (h->timing) cudaEventRecord(h->ev[2], st);
     return SGPR_OK;
@@ -648,8 +659,8 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
-    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/beta_d == nullptr,
-                         /*with_halo=*/peer_f_h == nullptr));
+    SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/true,
+                         /*with_halo=*/peer_f_h == nullptr, /*with_k8=*/beta_d != nullptr));
     PeerForces peers{};
     if (peer_f_h) {
         peers.world = world;
@@ -685,9 +696,9 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)grid_g + nblk_x), st));
     SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
     if (!peer_f_h) SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
-    if (beta_d) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
+    if (beta_d && !h->use_i8_now) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
     if (h->use_i8_now)
-        SGPR_TRY(i8_kernel_matrix(h, st));
+        SGPR_TRY(i8_kernel_matrix(h, st, beta_d != nullptr));
     else
         SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
     row_energy_kernel<<<grid_g, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows,
@@ -717,10 +728,13 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     if (h->timing) cudaEventRecord(h->ev[4], st);
     h->stats.covloss_flops = 0.0;
     if (beta_d) {
-        const int n_part = gemm_covloss_parts(h);
+        const int n_part = h->use_i8_now ? i8_covloss_parts(h) : gemm_covloss_parts(h);
         SGPR_TRY(h->cpart.ensure(sizeof(double) * (size_t)n_part * nrows));
         SGPR_CUDA(cudaMemsetAsync(beta_d, 0, sizeof(double) * (size_t)N, st));
-        SGPR_TRY(gemm_covloss(h, (int64_t)nrows, st));
+        if (h->use_i8_now)
+            SGPR_TRY(i8_covloss(h, (int64_t)nrows, st));
+        else
+            SGPR_TRY(gemm_covloss(h, (int64_t)nrows, st));
         if (h->n_active > 0) {
             SGPR_TRY(h->misc.ensure(sizeof(int) * SGPR_MAX_SPECIES));
             SGPR_CUDA(cudaMemcpyAsync(h->misc.p, h->dp.central_enabled, sizeof(int) * SGPR_MAX_SPECIES,
@@ -812,21 +826,32 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_han
     SGPR_TRY(h->stage_pos.ensure(nb_pos + 8));
     SGPR_TRY(h->stage_z.ensure(nb_z + 8));
     SGPR_TRY(h->stage_out.ensure(nb_out + (size_t)N + 64));
-    memcpy(pin_pos, pos_h, nb_pos);
-    memcpy(pin_z, Z_h, nb_z);
-    SGPR_CUDA(cudaMemcpyAsync(h->stage_pos.p, pin_pos, nb_pos, cudaMemcpyHostToDevice, st));
-    SGPR_CUDA(cudaMemcpyAsync(h->stage_z.p, pin_z, nb_z, cudaMemcpyHostToDevice, st));
+    // page-locked caller buffers are copied by the DMA engine directly; pageable ones go through the
+    // handle's pinned staging area (one host memcpy each way)
+    const bool pos_pinned = N > 0 && is_pinned_host(pos_h), z_pinned = N > 0 && is_pinned_host(Z_h);
+    const bool f_pinned = N > 0 && is_pinned_host(F_h);
+    if (!pos_pinned) memcpy(pin_pos, pos_h, nb_pos);
+    if (!z_pinned) memcpy(pin_z, Z_h, nb_z);
+    SGPR_CUDA(cudaMemcpyAsync(h->stage_pos.p, pos_pinned ? pos_h : pin_pos, nb_pos, cudaMemcpyHostToDevice, st));
+    SGPR_CUDA(cudaMemcpyAsync(h->stage_z.p, z_pinned ? (const void*)Z_h : (const void*)pin_z, nb_z, cudaMemcpyHostToDevice, st));
     double* out_d = h->stage_out.as<double>();  // [E(1) pad(6) W(9) F(3N) beta(N)]
     double* beta_d = beta_h ? out_d + 16 + 3 * (size_t)N : nullptr;
     uint8_t* own_d = owned_h ? (uint8_t*)(out_d + 16 + (beta_h ? 4 : 3) * (size_t)N) : nullptr;
     SGPR_TRY(sgpr_predict(h, N, h->stage_pos.as<double>(), h->stage_z.as<int32_t>(), cell_h, pbc_h, rank, world, st,
                           out_d, out_d + 16, out_d + 7, beta_d, own_d));
-    SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
+    if (f_pinned) {
+        SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaMemcpyAsync(F_h, out_d + 16, nb_pos, cudaMemcpyDeviceToHost, st));
+        if (beta_h)
+            SGPR_CUDA(cudaMemcpyAsync(pin_out + 16 + 3 * (size_t)N, beta_d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    } else {
+        SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
+    }
     if (owned_h) SGPR_CUDA(cudaMemcpyAsync(pin_own, own_d, (size_t)N, cudaMemcpyDeviceToHost, st));
     SGPR_CUDA(cudaStreamSynchronize(st));
     E_h[0] = pin_out[0];
     memcpy(W_h, pin_out + 7, sizeof(double) * 9);
-    memcpy(F_h, pin_out + 16, nb_pos);
+    if (!f_pinned) memcpy(F_h, pin_out + 16, nb_pos);
     if (owned_h) memcpy(owned_h, pin_own, (size_t)N);
     if (beta_h) memcpy(beta_h, pin_out + 16 + 3 * (size_t)N, sizeof(double) * (size_t)N);
     return SGPR_OK;

@@ -83,16 +83,31 @@ __device__ __forceinline__ void digits(double x, signed char* d) {   // most sig
 template <int NS>
 __global__ void slice_rows_kernel(const double* __restrict__ X, long long ldx, int rows, int K, int Kpad, double scale,
                                   const double* __restrict__ col_scale, signed char* __restrict__ out,
-                                  long long slice_stride) {
+                                  long long slice_stride, const double* __restrict__ row_div = nullptr) {
     const long long total = (long long)rows * Kpad;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Kpad), k = (int)(idx - (long long)r * Kpad);
         signed char d[NS];
         double x = 0.0;
         if (k < K) x = X[(long long)r * ldx + k] * scale * (col_scale ? col_scale[k] : 1.0);
+        if (row_div) x /= row_div[r];   // power of two: exact
         digits<NS>(x, d);
 #pragma unroll
         for (int t = 0; t < NS; ++t) out[(long long)t * slice_stride + (long long)r * Kpad + k] = d[t];
+    }
+}
+
+// power of two >= max |row| (1 for an all-zero row); one warp per row
+__global__ void row_pow2_kernel(const double* __restrict__ X, long long ldx, int rows, int K, double* __restrict__ rs) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    double m = 0.0;
+    for (int k = lane; k < K; k += 32) m = fmax(m, fabs(X[(long long)r * ldx + k]));
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);   // m = f 2^e, f in [0.5, 1)
+        rs[r] = m > 0.0 ? ldexp(1.0, e) : 1.0;
     }
 }
 
@@ -102,6 +117,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
     const double* mu[kMaxSpecies];       // per problem: mu of the species' inducing block
     double* erow_part[kMaxSpecies];      // + r0
     signed char* g8[kMaxSpecies];        // + r0 * Mp   (slice 0)
+    signed char* k8[kMaxSpecies];        // + r0 * Mp; digits of k^xi for the covloss GEMM (nullptr: not wanted)
     int erow_ld;
     int Mp;
     long long g8_slice;                  // bytes between slices
@@ -159,6 +175,37 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
         }
         // energy partial of this 16-column chunk
         erow_part[p][(long long)(col0 >> 4) * erow_ld + row] = e;
+        if (k8[p] != nullptr && col0 < Mp) {   // K = k^xi, the A operand of the covloss GEMM
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = digit_bytes<kNS>(col0 + j < N ? pw[j] * v[j] : 0.0);
+#pragma unroll
+            for (int t = 0; t < kNS; ++t) {
+                const int b = kNS - 1 - t;
+                int4 w;
+                w.x = (int)gather_byte(u + 0, b);
+                w.y = (int)gather_byte(u + 4, b);
+                w.z = (int)gather_byte(u + 8, b);
+                w.w = (int)gather_byte(u + 12, b);
+                *reinterpret_cast<int4*>(k8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+            }
+        }
+    }
+};
+
+struct Epi3 {   // covloss: per-row partial sums of squares of b = K . choli^T  (calculator/active.py:781-783)
+    const double* rs[kMaxSpecies];       // power-of-two scales of the choli rows (= output columns)
+    double* part[kMaxSpecies];           // + r0
+    int part_ld;
+    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+        if (row >= M) return;
+        const double* r = rs[p];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const double t = col0 + j < N ? v[j] * r[col0 + j] : 0.0;
+            s = fma(t, t, s);
+        }
+        part[p][(long long)(col0 >> 4) * part_ld + row] = s;
     }
 };
 
@@ -185,8 +232,7 @@ int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi&
     constexpr int STAGES = 3;
     auto kern = i8gemm_kernel<kNS, TR, STAGES, Epi>;
     const size_t smem = smem_bytes<kNS, STAGES>();
-    static bool attr_done[2][16] = {};
-    bool& done = attr_done[sizeof(Epi) == sizeof(Epi1) ? 0 : 1][TR];
+    static bool done = false;   // per instantiation
     if (!done) {
         SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
@@ -243,9 +289,33 @@ int i8_prepare_model(sgpr_context* h, bool weights_only) {
     return SGPR_OK;
 }
 
-// buffers written by the descriptor kernel (q_hat digits) and by GEMM 1 (k^(xi-1) digits)
-int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows) {
+// digit slices of choli for the covloss GEMM: per central species s the rows k of choli[:, columns of s]
+// (h->choli_t), each divided by its own power-of-two bound so that small rows keep their relative accuracy
+int i8_prepare_covloss(sgpr_context* h) {
+    const int M = h->M, S = h->S;
+    if (M == 0 || !h->has_choli) return SGPR_OK;
+    SGPR_TRY(h->crs.ensure(sizeof(double) * (size_t)S * M));
+    SGPR_TRY(h->c8.ensure((size_t)S * kNS * M * h->i8_mp + 64));
+    SGPR_CUDA(cudaMemset(h->c8.p, 0, (size_t)S * kNS * M * h->i8_mp));
+    for (int s = 0; s < S; ++s) {
+        const int Ms = h->m_first[s + 1] - h->m_first[s];
+        if (Ms == 0) continue;
+        const double* X = h->choli_t.as<double>() + (size_t)s * M * h->ld_zt;
+        double* rs = h->crs.as<double>() + (size_t)s * M;
+        row_pow2_kernel<<<(M + 7) / 8, 256>>>(X, h->ld_zt, M, Ms, rs);
+        slice_rows_kernel<kNS><<<h->sm_count * 4, 256>>>(X, h->ld_zt, M, Ms, h->i8_mp, 1.0, nullptr,
+                                                         h->c8.as<signed char>() + (size_t)s * kNS * M * h->i8_mp,
+                                                         (long long)M * h->i8_mp, rs);
+        SGPR_CUDA(cudaGetLastError());
+    }
+    SGPR_CUDA(cudaDeviceSynchronize());
+    return SGPR_OK;
+}
+
+// buffers written by the descriptor kernel (q_hat digits) and by GEMM 1 (k^(xi-1) and, for covloss, k^xi digits)
+int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows, bool with_k8) {
     const size_t cap = n_rows + 1;
+    if (with_k8) SGPR_TRY(h->k8.ensure((size_t)kNS * std::max(h->i8_cap_rows, cap + cap / 4) * h->i8_mp + 64));
     if (cap > h->i8_cap_rows) {
         const size_t c = cap + cap / 4;
         SGPR_TRY(h->p8.ensure((size_t)kNS * c * h->i8_kp1 + 64));
@@ -272,27 +342,37 @@ static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Pr
             P.Kpad = h->i8_kp1;
             SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>() + (size_t)r0 * h->i8_kp1, kNS, P.M, P.Kpad, (long long)h->i8_cap_rows, BM));
             SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * h->i8_kp1, kNS, P.N, P.Kpad, (long long)h->M, BN));
-        } else {
+        } else if (which == 2) {
             P.M = r1 - r0;
             P.N = dp.D;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
             SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
             SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, kNS, dp.D, h->i8_mp, (long long)dp.D, BN));
+        } else {
+            P.M = r1 - r0;
+            P.N = h->M;
+            P.Kpad = ((m1 - m0) + 63) / 64 * 64;
+            SGPR_TRY(make_map(&P.mapA, h->k8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapB, h->c8.as<signed char>() + (size_t)s * kNS * h->M * h->i8_mp, kNS, h->M, h->i8_mp, (long long)h->M, BN));
         }
         prob_species[cm.n_prob] = s;
         cm.tile_start[cm.n_prob + 1] = cm.tile_start[cm.n_prob] + ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN);
         cm.n_prob++;
         probs.push_back(P);
-        const int npairs = h->i8_tr == 8 ? 26 : 21;
-        h->stats.gemm_flops += 2.0 * P.M * (double)P.N * (which == 1 ? dp.D : (m1 - m0));
-        h->stats.i8_ops += 2.0 * P.M * (double)P.N * P.Kpad * npairs;
+        if (which == 3) {
+            h->stats.covloss_flops += 2.0 * P.M * (double)P.N * (m1 - m0);
+        } else {
+            const int npairs = h->i8_tr == 8 ? 26 : 21;
+            h->stats.gemm_flops += 2.0 * P.M * (double)P.N * (which == 1 ? dp.D : (m1 - m0));
+            h->stats.i8_ops += 2.0 * P.M * (double)P.N * P.Kpad * npairs;
+        }
     }
     return SGPR_OK;
 }
 
 static int upload_problems(sgpr_context* h, int slot, const std::vector<Problem>& probs, cudaStream_t st, const Problem** out) {
-    SGPR_TRY(h->i8_probs.ensure(sizeof(Problem) * 2 * kMaxSpecies));
-    if (!h->i8_probs_pinned) SGPR_CUDA(cudaMallocHost(&h->i8_probs_pinned, sizeof(Problem) * 2 * kMaxSpecies));
+    SGPR_TRY(h->i8_probs.ensure(sizeof(Problem) * 3 * kMaxSpecies));
+    if (!h->i8_probs_pinned) SGPR_CUDA(cudaMallocHost(&h->i8_probs_pinned, sizeof(Problem) * 3 * kMaxSpecies));
     Problem* pin = (Problem*)h->i8_probs_pinned + slot * kMaxSpecies;
     Problem* dev = h->i8_probs.as<Problem>() + slot * kMaxSpecies;
     for (size_t i = 0; i < probs.size(); ++i) pin[i] = probs[i];
@@ -301,7 +381,7 @@ static int upload_problems(sgpr_context* h, int slot, const std::vector<Problem>
     return SGPR_OK;
 }
 
-int i8_kernel_matrix(sgpr_context* h, cudaStream_t st) {
+int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
     Common cm;
     std::vector<Problem> probs;
     int ps[kMaxSpecies];
@@ -315,6 +395,7 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st) {
         e.mu[p] = h->mu.as<double>() + m0;
         e.erow_part[p] = h->erow_part.as<double>() + r0;
         e.g8[p] = h->g8.as<signed char>() + (size_t)r0 * h->i8_mp;
+        e.k8[p] = store_k8 ? h->k8.as<signed char>() + (size_t)r0 * h->i8_mp : nullptr;
     }
     e.erow_ld = (int)h->n_active + 1;
     e.Mp = h->i8_mp;
@@ -337,6 +418,27 @@ int i8_back_projection(sgpr_context* h, cudaStream_t st) {
     e.ldp = h->dp.ldp;
     e.mumax = h->i8_mumax;
     return h->i8_tr == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+}
+
+// Covloss GEMM on tcgen05: b = K . choli^T per central species, reduced on the fly to per-row partial sums of
+// squares (h->cpart [i8_covloss_parts, n_rows]).  Always 26 slice products (t + u <= 8): choli is not normalised.
+int i8_covloss_parts(sgpr_context* h) { return ((h->M + BN - 1) / BN) * (BN / 16); }
+
+int i8_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st) {
+    Common cm;
+    std::vector<Problem> probs;
+    int ps[kMaxSpecies];
+    SGPR_TRY(build_problems(h, 3, cm, probs, ps));
+    if (cm.n_prob == 0) return SGPR_OK;
+    const Problem* probs_d = nullptr;
+    SGPR_TRY(upload_problems(h, 2, probs, st, &probs_d));
+    Epi3 e{};
+    for (int p = 0; p < cm.n_prob; ++p) {
+        e.rs[p] = h->crs.as<double>() + (size_t)ps[p] * h->M;
+        e.part[p] = h->cpart.as<double>() + h->row_first[ps[p]];
+    }
+    e.part_ld = (int)n_rows;
+    return launch<8>(h, cm, probs_d, e, st);
 }
 
 }  // namespace sgpr

@@ -132,13 +132,14 @@ struct sgpr_context {
     sgpr::DevBuf ttab;          // [D] kappa*nnl*(1 + [a==b]) per packed entry
     // ---- tcgen05 int8-sliced GEMM path (i8gemm.cu)
     bool use_i8 = false;        // GEMMs on tcgen05 (int8 digit slices) instead of FP64 DMMA
-    bool use_i8_now = false;    // ... for the current call (covloss / compat calls use the DMMA path)
+    bool use_i8_now = false;    // ... for the current call (compat / K-matrix calls use the DMMA path)
     int i8_tr = 7;              // truncation t + u <= i8_tr (7: 21 slice products, 8: 26)
     int i8_kp1 = 0, i8_mp = 0;  // K paddings (multiples of 64) of GEMM 1 (D) and GEMM 2 (max M_s)
     size_t i8_cap_rows = 0;     // row capacity of p8 / g8 (slice stride)
     double i8_mumax = 1.0;      // power of two >= max xi |mu|
     sgpr::DevBuf z8, zt8;       // static digit slices: z_hat [6][M][kp1], (xi mu z_hat^T / mumax) [S][6][D][mp]
     sgpr::DevBuf p8, g8;        // per-step digit slices: q_hat [6][cap][kp1], k^(xi-1) [6][cap][mp]
+    sgpr::DevBuf k8, c8, crs;   // covloss: k^xi digits [6][cap][mp], choli digits [S][6][M][mp], choli row scales [S][M]
     sgpr::DevBuf i8_probs;      // device copies of the tensor-map problem descriptors
     void* i8_probs_pinned = nullptr;
     sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
@@ -207,9 +208,12 @@ int gemm_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
 
 // ---- i8gemm.cu --------------------------------------------------------------------
 int i8_prepare_model(sgpr_context* h, bool weights_only);
-int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows);
+int i8_prepare_covloss(sgpr_context* h);
+int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows, bool with_k8 = false);
 int i8_energy_parts(int Ms);
-int i8_kernel_matrix(sgpr_context* h, cudaStream_t st);
+int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8 = false);
+int i8_covloss_parts(sgpr_context* h);
+int i8_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
 int i8_back_projection(sgpr_context* h, cudaStream_t st);
 int gemm_back_projection(sgpr_context* h, cudaStream_t st);
 

@@ -182,6 +182,9 @@ class _CovProxy:
 _Cov = _CovProxy
 
 
+_PINNED_KEEPALIVE = []
+
+
 class SgprEngine:
     """One handle on one CUDA device.  Host-side mirror of the C ABI."""
 
@@ -252,15 +255,32 @@ class SgprEngine:
         return c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ hot path
-    def predict(self, pos, numbers, cell, pbc, rank=0, world=1, want_beta=False):
+    @staticmethod
+    def pinned(shape, dtype=np.float64):
+        """Page-locked host array (numpy view of a pinned torch tensor).  predict() copies such buffers with the
+        DMA engine directly; ordinary (pageable) arrays take one extra host memcpy each way."""
+        import torch
+
+        t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+        a = t.numpy()
+        _PINNED_KEEPALIVE.append(t)
+        return a
+
+    def predict(self, pos, numbers, cell, pbc, rank=0, world=1, want_beta=False, out_forces=None):
         """Host numpy in, host numpy out (H2D/D2H inside): E, F[N,3], W[3,3], owned[N]
-        (+ beta[N], the covloss of calculator/active.py:781-804, when want_beta)."""
+        (+ beta[N], the covloss of calculator/active.py:781-804, when want_beta).  ``out_forces`` may be a
+        caller-owned (ideally pinned()) float64 [N,3] array that receives F."""
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
         Z = np.ascontiguousarray(numbers, dtype=np.int32).reshape(-1)
         N = len(Z)
         cell_h, pbc_h = self._geom(cell, pbc)
         E = np.zeros(1)
-        F = np.zeros((N, 3))
+        if out_forces is not None:
+            if out_forces.dtype != np.float64 or out_forces.shape != (N, 3) or not out_forces.flags.c_contiguous:
+                raise ValueError("out_forces must be a C-contiguous float64 [N,3] array")
+            F = out_forces
+        else:
+            F = np.empty((N, 3))
         W = np.zeros(9)
         owned = np.zeros(N, dtype=np.uint8)
         beta = np.zeros(N) if want_beta else None

@@ -210,8 +210,11 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             exchange, px = "halo", None
-    pin_pos = torch.empty((N, 3), dtype=torch.float64).pin_memory() if px is not None else None
-    pin_F = torch.empty((N, 3), dtype=torch.float64).pin_memory() if px is not None else None
+    # host buffers of the end-to-end leg are page-locked (inputs and the force output)
+    pin_variants = [torch.from_numpy(p).pin_memory() for p in pos_variants]
+    pin_F = torch.empty((N, 3), dtype=torch.float64).pin_memory()
+    pin_F_np = pin_F.numpy()
+    pin_Z = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).pin_memory()
     dev_pos = torch.empty((N, 3), dtype=torch.float64, device=dev) if px is not None else None
 
     def step_device(it):
@@ -226,14 +229,14 @@ def main():
 
     def step_host(it):
         if px is not None:   # host buffers in and out around the peer-memory step
-            pin_pos.copy_(torch.from_numpy(pos_variants[it % len(pos_variants)]))
-            dev_pos.copy_(pin_pos, non_blocking=True)
+            dev_pos.copy_(pin_variants[it % len(pin_variants)], non_blocking=True)
             E, F, W, owned = px.step(dev_pos, z_d, cell, pbc)
             pin_F.copy_(F, non_blocking=True)
             Eh = float(E.item())   # D2H of the reduced energy: synchronises the step
             torch.cuda.current_stream().synchronize()
             return Eh
-        E, F, W, owned = eng.predict(pos_variants[it % len(pos_variants)], numbers, cell, pbc, rank=rank, world=world)
+        E, F, W, owned = eng.predict(pin_variants[it % len(pin_variants)].numpy(), pin_Z.numpy(), cell, pbc, rank=rank,
+                                     world=world, out_forces=pin_F_np)
         if world > 1:
             t = torch.tensor([E] + list(W.reshape(-1)), dtype=torch.float64, device=dev)
             dist.all_reduce(t)
@@ -357,7 +360,7 @@ def main():
                 eng_c.close()
                 mb = sum(tb) / len(tb)
                 line["covloss"] = {"ms_per_step": mb, "tflops": fl / (mb * 1e-3) / 1e12, "flops_per_step": fl,
-                                   "note": "extra device time per step when beta is requested; FP64 DMMA GEMM K.choli^T + row sum of squares"}
+                                   "note": "extra device time per step when beta is requested; tcgen05 int8 digit-slice GEMM K.choli^T (26 slice products) + row sum of squares"}
             except Exception as ex:  # pragma: no cover
                 line["covloss"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:

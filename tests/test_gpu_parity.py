@@ -190,8 +190,7 @@ def test_covloss_matches_reference(case):
     assert np.array_equal(np.isnan(beta), np.isnan(ref))
     # the sqrt next to the clamp amplifies rounding: compare beta^2
     assert np.abs(beta[fin] ** 2 - ref[fin] ** 2).max() < 1e-9
-    # asking for beta must not change E/F/W (the covloss call runs the float64 DMMA GEMMs, the plain call the
-    # tcgen05 int8-sliced ones: equal to ~1e-12 relative, not bit-identical)
+    # asking for beta must not change E/F/W (same tcgen05 GEMMs; the covloss GEMM is an extra launch)
     E0, F0, W0, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
     assert abs(E - E0) < 1e-10 * max(1.0, abs(E0)) and np.abs(W - W0).max() < 1e-9 and np.abs(F - F0).max() < 1e-10
     # sharded: each rank fills the betas of the atoms it owns
@@ -236,3 +235,25 @@ def test_differentiable_cov_matches_reference_autograd(case):
     p[i, k] -= 2 * d
     Lm = float((eng.kernel_matrix(p, g["numbers"], g["cell"], g["meta"]["pbc"]).cpu() * w).sum())
     assert abs((Lp - Lm) / (2 * d) - float(gx[i, k])) < 1e-6 * max(1.0, abs(float(gx[i, k])))
+
+
+@pytest.mark.gpu
+def test_pinned_host_buffers_take_the_direct_dma_path():
+    """sgpr_predict_host copies page-locked caller buffers without staging: same results as pageable ones."""
+    import autoforce_b200 as ab
+
+    g = load_golden("lipso108")
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    E0, F0, W0, own0 = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    pos = ab.SgprEngine.pinned(g["pos"].shape)
+    pos[...] = g["pos"]
+    Z = ab.SgprEngine.pinned((len(g["numbers"]),), np.int32)
+    Z[...] = g["numbers"]
+    F = ab.SgprEngine.pinned(g["pos"].shape)
+    F[...] = np.nan
+    E1, F1, W1, own1 = eng.predict(pos, Z, g["cell"], g["meta"]["pbc"], out_forces=F)
+    # (forces are scattered with atomics: equal to rounding, not bitwise)
+    assert F1 is F and abs(E1 - E0) < 1e-10 and np.abs(F - F0).max() < 1e-11 and np.abs(W1 - W0).max() < 1e-9
+    assert np.array_equal(own0, own1)
+    with pytest.raises(ValueError):
+        eng.predict(pos, Z, g["cell"], g["meta"]["pbc"], out_forces=np.zeros((3, 3)))

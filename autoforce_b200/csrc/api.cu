@@ -336,6 +336,117 @@ static int upload_weights(sgpr_context* h, const double* mu_h, const double* mea
     return SGPR_OK;
 }
 
+// Inducing set (a10): group the LCEs by central species, evaluate Z_hat with the atom kernels, build the per-species
+// transposes.  Keeps host copies of the environments so that sgpr_append_inducing can extend the set.
+static int set_inducing(sgpr_context* h, int M, const int32_t* ind_Z, const int64_t* ind_first, const double* ind_r,
+                        const int32_t* ind_b) {
+    // inducing set, grouped by central species
+    DescParams& dp = h->dp;
+    const int S = h->S;
+    h->M = M;
+    std::vector<int> sp_of(M);
+    for (int m = 0; m < M; ++m) {
+        const int z = ind_Z[m];
+        if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+            set_error("inducing LCE %d: species Z=%d not in the species table", m, z);
+            return SGPR_ERR_SPECIES;
+        }
+        sp_of[m] = h->z_to_species[z];
+    }
+    h->ind_perm.resize(M);
+    for (int m = 0; m < M; ++m) h->ind_perm[m] = m;
+    std::stable_sort(h->ind_perm.begin(), h->ind_perm.end(), [&](int a, int b) { return sp_of[a] < sp_of[b]; });
+    for (int s = 0; s <= SGPR_MAX_SPECIES; ++s) h->m_first[s] = 0;
+    for (int m = 0; m < M; ++m) h->m_first[sp_of[m] + 1]++;
+    for (int s = 0; s < SGPR_MAX_SPECIES; ++s) h->m_first[s + 1] += h->m_first[s];
+    int maxMs = 0;
+    for (int s = 0; s < S; ++s) maxMs = std::max(maxMs, h->m_first[s + 1] - h->m_first[s]);
+    h->ld_zt = std::max(16, (maxMs + 15) & ~15);
+    h->ldg = h->ld_zt;
+    h->ind_sp.resize(M);
+    h->ind_lone.resize(M);
+    std::vector<int> row_of(M);
+    for (int p = 0; p < M; ++p) {
+        const int m = h->ind_perm[p];
+        row_of[m] = p;
+        h->ind_sp[p] = sp_of[m];
+        h->ind_lone[p] = (ind_first[m + 1] == ind_first[m]) ? 1 : 0;
+    }
+    SGPR_TRY(upload(h->ind_perm_d, h->ind_perm.data(), sizeof(int) * M));
+    {
+        std::vector<unsigned char> on(SGPR_MAX_SPECIES, 0);
+        for (int s = 0; s < S; ++s) on[s] = (dp.central_enabled[s] && h->m_first[s + 1] > h->m_first[s]) ? 1 : 0;
+        SGPR_TRY(upload(h->sp_on, on.data(), SGPR_MAX_SPECIES));
+    }
+    // environments -> device, evaluate Z_hat with the atom kernels
+    SGPR_TRY(h->zhat.ensure(sizeof(double) * ((size_t)M + 1) * dp.ldp));
+    SGPR_CUDA(cudaMemset(h->zhat.p, 0, sizeof(double) * ((size_t)M + 1) * dp.ldp));
+    if (M > 0) {
+        const int64_t nnz = ind_first[M];
+        std::vector<unsigned char> esp((size_t)nnz + 1);
+        for (int64_t k = 0; k < nnz; ++k) {
+            const int z = ind_b[k];
+            if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+                set_error("inducing neighbour species Z=%d not in the species table", z);
+                    return SGPR_ERR_SPECIES;
+            }
+            esp[k] = (unsigned char)h->z_to_species[z];
+        }
+        std::vector<long long> first(M + 1);
+        for (int m = 0; m <= M; ++m) first[m] = ind_first[m];
+        DevBuf b_first, b_r, b_sp, b_row;
+        SGPR_TRY(upload(b_first, first.data(), sizeof(long long) * (M + 1)));
+        SGPR_TRY(upload(b_r, ind_r, sizeof(double) * 3 * nnz));
+        SGPR_TRY(upload(b_sp, esp.data(), nnz));
+        SGPR_TRY(upload(b_row, row_of.data(), sizeof(int) * M));
+        int st = descriptor_forward_env(h, M, b_first.as<long long>(), b_r.as<double>(), b_sp.as<unsigned char>(),
+                                        b_row.as<int>(), h->zhat.as<double>(), 0);
+        if (st == SGPR_OK && cudaDeviceSynchronize() != cudaSuccess) {
+            set_error("inducing descriptor kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = SGPR_ERR_CUDA;
+        }
+        b_first.release();
+        b_r.release();
+        b_sp.release();
+        b_row.release();
+        if (st != SGPR_OK) return st;
+    }
+    // transposed copies per species for the back projection
+    SGPR_TRY(h->zhat_t.ensure(sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
+    SGPR_CUDA(cudaMemset(h->zhat_t.p, 0, sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
+    for (int s = 0; s < S; ++s) {
+        h->zt_off[s] = (size_t)s * dp.D * h->ld_zt;
+        const int Ms = h->m_first[s + 1] - h->m_first[s];
+        if (Ms == 0) continue;
+        dim3 grid((dp.D + 31) / 32, (h->ld_zt + 31) / 32), block(32, 8);
+        transpose_zhat_kernel<<<grid, block>>>(dp.D, dp.ldp, h->m_first[s], Ms, h->ld_zt, h->zhat.as<double>(),
+                                               h->zhat_t.as<double>() + h->zt_off[s]);
+    }
+    SGPR_CUDA(cudaDeviceSynchronize());
+    {   // caller's order copies for the lone-lone kernel term
+        std::vector<int> sp_orig(M + 1);
+        std::vector<unsigned char> lone_orig(M + 1);
+        for (int p = 0; p < M; ++p) {
+            sp_orig[h->ind_perm[p]] = h->ind_sp[p];
+            lone_orig[h->ind_perm[p]] = h->ind_lone[p];
+        }
+        SGPR_TRY(upload(h->ind_sp_d, sp_orig.data(), sizeof(int) * M));
+        SGPR_TRY(upload(h->ind_lone_d, lone_orig.data(), M));
+    }
+    {   // host copies (no-op when called with the copies themselves)
+        const int64_t nnz = M > 0 ? ind_first[M] : 0;
+        std::vector<int32_t> zc(ind_Z, ind_Z + M), bc(ind_b, ind_b + nnz);
+        std::vector<int64_t> fc(ind_first, ind_first + (M > 0 ? M + 1 : 0));
+        std::vector<double> rc(ind_r, ind_r + 3 * nnz);
+        if (M == 0) fc.assign(1, 0);
+        h->ind_Z_host.swap(zc);
+        h->ind_b_host.swap(bc);
+        h->ind_first_host.swap(fc);
+        h->ind_r_host.swap(rc);
+    }
+    return SGPR_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_model_desc* d, sgpr_handle* out) {
     if (!d || !out) {
         set_error("null argument");
@@ -440,102 +551,12 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         SGPR_TRY(upload(h->ttab, ttab.data(), sizeof(double) * dp.ldp));
     }
 
-    // inducing set, grouped by central species
-    const int M = d->M;
-    h->M = M;
-    std::vector<int> sp_of(M);
-    for (int m = 0; m < M; ++m) {
-        const int z = d->ind_Z_h[m];
-        if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
-            set_error("inducing LCE %d: species Z=%d not in the species table", m, z);
-            delete h;
-            return SGPR_ERR_SPECIES;
-        }
-        sp_of[m] = h->z_to_species[z];
-    }
-    h->ind_perm.resize(M);
-    for (int m = 0; m < M; ++m) h->ind_perm[m] = m;
-    std::stable_sort(h->ind_perm.begin(), h->ind_perm.end(), [&](int a, int b) { return sp_of[a] < sp_of[b]; });
-    for (int s = 0; s <= SGPR_MAX_SPECIES; ++s) h->m_first[s] = 0;
-    for (int m = 0; m < M; ++m) h->m_first[sp_of[m] + 1]++;
-    for (int s = 0; s < SGPR_MAX_SPECIES; ++s) h->m_first[s + 1] += h->m_first[s];
-    int maxMs = 0;
-    for (int s = 0; s < S; ++s) maxMs = std::max(maxMs, h->m_first[s + 1] - h->m_first[s]);
-    h->ld_zt = std::max(16, (maxMs + 15) & ~15);
-    h->ldg = h->ld_zt;
-    h->ind_sp.resize(M);
-    h->ind_lone.resize(M);
-    std::vector<int> row_of(M);
-    for (int p = 0; p < M; ++p) {
-        const int m = h->ind_perm[p];
-        row_of[m] = p;
-        h->ind_sp[p] = sp_of[m];
-        h->ind_lone[p] = (d->ind_first_h[m + 1] == d->ind_first_h[m]) ? 1 : 0;
-    }
-    SGPR_TRY(upload(h->ind_perm_d, h->ind_perm.data(), sizeof(int) * M));
     {
-        std::vector<unsigned char> on(SGPR_MAX_SPECIES, 0);
-        for (int s = 0; s < S; ++s) on[s] = (dp.central_enabled[s] && h->m_first[s + 1] > h->m_first[s]) ? 1 : 0;
-        SGPR_TRY(upload(h->sp_on, on.data(), SGPR_MAX_SPECIES));
-    }
-    // environments -> device, evaluate Z_hat with the atom kernels
-    SGPR_TRY(h->zhat.ensure(sizeof(double) * ((size_t)M + 1) * dp.ldp));
-    SGPR_CUDA(cudaMemset(h->zhat.p, 0, sizeof(double) * ((size_t)M + 1) * dp.ldp));
-    if (M > 0) {
-        const int64_t nnz = d->ind_first_h[M];
-        std::vector<unsigned char> esp((size_t)nnz + 1);
-        for (int64_t k = 0; k < nnz; ++k) {
-            const int z = d->ind_b_h[k];
-            if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
-                set_error("inducing neighbour species Z=%d not in the species table", z);
-                delete h;
-                return SGPR_ERR_SPECIES;
-            }
-            esp[k] = (unsigned char)h->z_to_species[z];
-        }
-        std::vector<long long> first(M + 1);
-        for (int m = 0; m <= M; ++m) first[m] = d->ind_first_h[m];
-        DevBuf b_first, b_r, b_sp, b_row;
-        SGPR_TRY(upload(b_first, first.data(), sizeof(long long) * (M + 1)));
-        SGPR_TRY(upload(b_r, d->ind_r_h, sizeof(double) * 3 * nnz));
-        SGPR_TRY(upload(b_sp, esp.data(), nnz));
-        SGPR_TRY(upload(b_row, row_of.data(), sizeof(int) * M));
-        int st = descriptor_forward_env(h, M, b_first.as<long long>(), b_r.as<double>(), b_sp.as<unsigned char>(),
-                                        b_row.as<int>(), h->zhat.as<double>(), 0);
-        if (st == SGPR_OK && cudaDeviceSynchronize() != cudaSuccess) {
-            set_error("inducing descriptor kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-            st = SGPR_ERR_CUDA;
-        }
-        b_first.release();
-        b_r.release();
-        b_sp.release();
-        b_row.release();
-        if (st != SGPR_OK) {
+        const int st_ind = set_inducing(h, d->M, d->ind_Z_h, d->ind_first_h, d->ind_r_h, d->ind_b_h);
+        if (st_ind != SGPR_OK) {
             delete h;
-            return st;
+            return st_ind;
         }
-    }
-    // transposed copies per species for the back projection
-    SGPR_TRY(h->zhat_t.ensure(sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
-    SGPR_CUDA(cudaMemset(h->zhat_t.p, 0, sizeof(double) * (size_t)S * dp.D * h->ld_zt + 8));
-    for (int s = 0; s < S; ++s) {
-        h->zt_off[s] = (size_t)s * dp.D * h->ld_zt;
-        const int Ms = h->m_first[s + 1] - h->m_first[s];
-        if (Ms == 0) continue;
-        dim3 grid((dp.D + 31) / 32, (h->ld_zt + 31) / 32), block(32, 8);
-        transpose_zhat_kernel<<<grid, block>>>(dp.D, dp.ldp, h->m_first[s], Ms, h->ld_zt, h->zhat.as<double>(),
-                                               h->zhat_t.as<double>() + h->zt_off[s]);
-    }
-    SGPR_CUDA(cudaDeviceSynchronize());
-    {   // caller's order copies for the lone-lone kernel term
-        std::vector<int> sp_orig(M + 1);
-        std::vector<unsigned char> lone_orig(M + 1);
-        for (int p = 0; p < M; ++p) {
-            sp_orig[h->ind_perm[p]] = h->ind_sp[p];
-            lone_orig[h->ind_perm[p]] = h->ind_lone[p];
-        }
-        SGPR_TRY(upload(h->ind_sp_d, sp_orig.data(), sizeof(int) * M));
-        SGPR_TRY(upload(h->ind_lone_d, lone_orig.data(), M));
     }
     std::vector<double> zeros(SGPR_MAX_SPECIES, 0.0), infs(SGPR_MAX_SPECIES, INFINITY);
     int st = upload_weights(h, d->mu_h, d->mean_w_h ? d->mean_w_h : zeros.data(), d->choli_h,
@@ -596,6 +617,57 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
     SGPR_TRY(upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr));
     if (mu_h && h->use_i8) SGPR_TRY(i8_prepare_model(h, true));
     if (choli_h && h->use_i8) SGPR_TRY(i8_prepare_covloss(h));
+    return SGPR_OK;
+}
+
+// Extend the inducing set (regression/gppotential.py:888-940 add_inducing / calculator/active.py:842-929
+// update_inducing): new LCEs are appended after the existing ones (caller's order), all model-side operands are
+// rebuilt, and the weights -- whose sizes change with M -- are replaced in the same call.
+extern "C" __attribute__((visibility("default"))) int sgpr_append_inducing(sgpr_handle h, int32_t n_new, const int32_t* ind_Z_h,
+                                    const int64_t* ind_first_h, const double* ind_r_h, const int32_t* ind_b_h,
+                                    const double* mu_h, const double* choli_h) {
+    if (!h || n_new < 0 || !mu_h || (n_new > 0 && (!ind_Z_h || !ind_first_h))) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    SGPR_CUDA(cudaSetDevice(h->device));
+    SGPR_CUDA(cudaDeviceSynchronize());
+    const int M0 = h->M, M1 = M0 + n_new;
+    const int64_t nnz0 = h->ind_first_host.empty() ? 0 : h->ind_first_host[M0];
+    const int64_t nnz_new = n_new > 0 ? ind_first_h[n_new] - ind_first_h[0] : 0;
+    if (nnz_new < 0 || (nnz_new > 0 && (!ind_r_h || !ind_b_h))) {
+        set_error("bad CSR of the new inducing environments");
+        return SGPR_ERR_INVALID;
+    }
+    std::vector<int32_t> Z(h->ind_Z_host), b(h->ind_b_host);
+    std::vector<int64_t> first(h->ind_first_host);
+    std::vector<double> r(h->ind_r_host);
+    if (first.empty()) first.assign(1, 0);
+    const std::vector<int32_t> Z0(Z), b0(b);
+    const std::vector<int64_t> first0(first);
+    const std::vector<double> r0(r);
+    for (int m = 0; m < n_new; ++m) {
+        Z.push_back(ind_Z_h[m]);
+        first.push_back(nnz0 + (ind_first_h[m + 1] - ind_first_h[0]));
+    }
+    const int64_t o = n_new > 0 ? ind_first_h[0] : 0;
+    b.insert(b.end(), ind_b_h + o, ind_b_h + o + nnz_new);
+    r.insert(r.end(), ind_r_h + 3 * o, ind_r_h + 3 * (o + nnz_new));
+    int st = set_inducing(h, M1, Z.data(), first.data(), r.data(), b.data());
+    if (st != SGPR_OK) {   // e.g. an unknown species: keep the old model usable
+        const std::string msg = sgpr_last_error();
+        set_inducing(h, M0, Z0.data(), first0.data(), r0.data(), b0.data());
+        set_error("%s", msg.c_str());
+        return st;
+    }
+    h->has_choli = false;
+    h->fwd_valid = false;
+    h->i8_cap_rows = 0;   // the K padding of the per-step digit buffers follows max M_s
+    SGPR_TRY(upload_weights(h, mu_h, nullptr, choli_h, nullptr, nullptr));
+    if (h->use_i8) {
+        SGPR_TRY(i8_prepare_model(h, false));
+        SGPR_TRY(i8_prepare_covloss(h));
+    }
     return SGPR_OK;
 }
 

@@ -118,6 +118,9 @@ struct sgpr_context {
     std::vector<unsigned char> ind_lone;     // sorted inducing p has no neighbours
     std::vector<double> mean_w, vscale, mu_host;
     bool has_choli = false;
+    std::vector<int32_t> ind_Z_host, ind_b_host;   // inducing environments as given (for sgpr_append_inducing)
+    std::vector<int64_t> ind_first_host;
+    std::vector<double> ind_r_host;
     // ---- model (device)
     sgpr::DevBuf zhat;        // [M, ldp]  packed normalised descriptors, rows grouped by species
     sgpr::DevBuf zhat_t;      // [S][D, ld_zt]  per-species transposes

@@ -45,6 +45,7 @@ EXPORTS = {
     "sgpr_last_error": (c_char_p, []),
     "sgpr_abi_version": (c_int32, []),
     "sgpr_set_weights": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_append_inducing": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_predict": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_predict_host": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
@@ -404,6 +405,41 @@ class SgprEngine:
         a3, p3 = arr(choli, M * M)
         a4, p4 = arr(vs, len(self.species))
         _check(self.lib, self.lib.sgpr_set_weights(self._h, p1, p2, p3, p4))
+
+    def append_inducing(self, envs, mu, choli=None):
+        """Add inducing LCEs ``[(Z, r[nn,3], b[nn]), ...]`` after the existing ones and install the refitted
+        weights ``mu [M+n]`` (and ``choli [M+n, M+n]``): what ``model.add_inducing(loc)`` + ``make_munu`` do in
+        the reference (regression/gppotential.py:888-940, 548-601).  All new species must already be in the
+        engine's species table (pass ``species=`` when constructing the engine)."""
+        n = len(envs)
+        Z = np.ascontiguousarray([int(e[0]) for e in envs], dtype=np.int32)
+        rs = [np.asarray(e[1], dtype=np.float64).reshape(-1, 3) for e in envs]
+        bs = [np.asarray(e[2], dtype=np.int32).reshape(-1) for e in envs]
+        for r, b in zip(rs, bs):
+            if len(r) != len(b):
+                raise ValueError("environment with mismatched r / b lengths")
+        first = np.zeros(n + 1, dtype=np.int64)
+        first[1:] = np.cumsum([len(b) for b in bs])
+        r = np.ascontiguousarray(np.concatenate(rs) if n else np.zeros((0, 3)))
+        b = np.ascontiguousarray(np.concatenate(bs) if n else np.zeros(0, dtype=np.int32))
+        M1 = self.model.M + n
+        mu = np.ascontiguousarray(mu, dtype=np.float64).reshape(-1)
+        if mu.size != M1:
+            raise ValueError(f"mu must have {M1} entries")
+        ch = None
+        if choli is not None:
+            ch = np.ascontiguousarray(choli, dtype=np.float64)
+            if ch.shape != (M1, M1):
+                raise ValueError(f"choli must be [{M1},{M1}]")
+        _check(self.lib, self.lib.sgpr_append_inducing(self._h, n, _ptr(Z), _ptr(first), _ptr(r), _ptr(b), _ptr(mu),
+                                                       _ptr(ch) if ch is not None else None))
+        m = self.model
+        m.ind_first = np.concatenate([m.ind_first, m.ind_first[-1] + first[1:]])
+        m.ind_Z = np.concatenate([m.ind_Z, Z])
+        m.ind_r = np.concatenate([m.ind_r, r])
+        m.ind_b = np.concatenate([m.ind_b, b])
+        m.mu = mu
+        m.choli = ch
 
     def enable_timing(self, on=True):
         _check(self.lib, self.lib.sgpr_enable_timing(self._h, 1 if on else 0))

@@ -96,6 +96,14 @@ int sgpr_abi_version(void);
 int sgpr_set_weights(sgpr_handle h, const double* mu_h, const double* mean_w_h,
                      const double* choli_h, const double* vscale_h);
 
+/* Append n_new inducing LCEs (CSR like sgpr_model_desc: ind_first_h [n_new+1], ind_r_h / ind_b_h indexed by
+ * it) after the existing ones and replace the weights, whose sizes follow M: mu_h [M+n_new], choli_h
+ * [(M+n_new)^2] or NULL (covloss unavailable until sgpr_set_weights provides one).  Replaces
+ * PosteriorPotential.add_inducing (regression/gppotential.py:888-940) as driven by
+ * ActiveCalculator.update_inducing (calculator/active.py:842-929).  On error the old model stays in place. */
+int sgpr_append_inducing(sgpr_handle h, int32_t n_new, const int32_t* ind_Z_h, const int64_t* ind_first_h,
+                         const double* ind_r_h, const int32_t* ind_b_h, const double* mu_h, const double* choli_h);
+
 /* ---- the hot path ---------------------------------------------------------------- */
 
 /* One ActiveCalculator.calculate() in prediction mode (calculator/active.py:425-611):

@@ -257,3 +257,42 @@ def test_pinned_host_buffers_take_the_direct_dma_path():
     assert np.array_equal(own0, own1)
     with pytest.raises(ValueError):
         eng.predict(pos, Z, g["cell"], g["meta"]["pbc"], out_forces=np.zeros((3, 3)))
+
+
+@pytest.mark.parametrize("name", ["lipso108", "cu108_sesoap"])
+def test_append_inducing_matches_a_model_built_in_one_go(name):
+    """sgpr_append_inducing (add_inducing + make_munu, regression/gppotential.py:888-940): a handle built from the
+    first inducing LCEs and then extended gives the golden E/F/stress/beta of the full model."""
+    import dataclasses
+
+    import autoforce_b200 as ab
+
+    g = load_golden(name)
+    full = model_from_golden(g)
+    M = full.M
+    k = max(1, M // 3)
+    f = full.ind_first
+    part = dataclasses.replace(full, ind_Z=full.ind_Z[:k], ind_first=f[: k + 1], ind_r=full.ind_r[: f[k]], ind_b=full.ind_b[: f[k]],
+                               mu=full.mu[:k], choli=None)
+    eng = ab.SgprEngine(part, species=g["meta"]["species"])
+    envs = [(int(full.ind_Z[m]), full.ind_r[f[m] : f[m + 1]], full.ind_b[f[m] : f[m + 1]]) for m in range(k, M)]
+    # an unknown species is refused and leaves the old model in place
+    E_part, *_ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    with pytest.raises(RuntimeError):
+        eng.append_inducing([(99, np.zeros((0, 3)), np.zeros(0, dtype=np.int32))], np.zeros(k + 1))
+    assert abs(eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])[0] - E_part) < 1e-9 * max(1.0, abs(E_part))
+    # two appends: one LCE, then the rest (intermediate weights are placeholders)
+    eng.append_inducing(envs[:1], np.zeros(k + 1))
+    eng.append_inducing(envs[1:], full.mu, full.choli)
+    assert eng.model.M == M and np.array_equal(eng.model.ind_first, full.ind_first)
+    E, F, W, owned, beta = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"], want_beta=True)
+    N = len(g["numbers"])
+    assert abs(E - float(g["energy"])) < TOL_E_PER_ATOM * N
+    assert np.abs(F - g["forces"]).max() < TOL_F
+    assert np.abs(stress_of(W, g["cell"]) - g["stress"]).max() < TOL_S
+    ref = o.predict(oracle_model(g), g["pos"], g["cell"], g["meta"]["pbc"], g["numbers"], want_beta=True)["beta"]
+    fin = np.isfinite(ref)
+    assert np.abs(beta[fin] ** 2 - ref[fin] ** 2).max() < 1e-9
+    Kmat = eng.kernel_matrix(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"]).cpu().numpy()
+    assert np.abs(Kmat - g["K"]).max() < 1e-12
+    eng.close()

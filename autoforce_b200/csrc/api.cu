@@ -207,6 +207,36 @@ __global__ void final_reduce_kernel(int n_e, const double* __restrict__ epart, i
     }
 }
 
+// One inducing LCE as the cotangent of the kernel matrix (training-time kernels, similarity/universal.py:124-183):
+// rows of its central species get  g = xi k^(xi-1) z_hat  and  e = k^xi  (so that q_hat . g = xi e), all others zero.
+__global__ void column_seed_kernel(int n_rows, int r0, int r1, int D, int ldp, const double* __restrict__ phat,
+                                   const double* __restrict__ z, double xi, int xi_int, double* __restrict__ gvec,
+                                   double* __restrict__ erow) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+        double* g = gvec + (size_t)r * ldp;
+        if (r < r0 || r >= r1) {
+            for (int e = lane; e < ldp; e += 32) g[e] = 0.0;
+            if (lane == 0) erow[r] = 0.0;
+            continue;
+        }
+        const double* q = phat + (size_t)r * ldp;
+        double k = 0.0;
+        for (int e = lane; e < D; e += 32) k = fma(q[e], z[e], k);
+        for (int o = 16; o; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+        double pw = 1.0;
+        if (xi_int >= 1) {
+            for (int t = 1; t < xi_int; ++t) pw *= k;
+        } else {
+            pw = pow(k, xi - 1.0);
+        }
+        const double c = xi * pw;
+        for (int e = lane; e < ldp; e += 32) g[e] = e < D ? c * z[e] : 0.0;
+        if (lane == 0) erow[r] = pw * k;
+    }
+}
+
 __global__ void row_to_orig_kernel(int64_t N, const AtomRec* __restrict__ atoms, const int* __restrict__ rowof,
                                    int* __restrict__ orig_of_row) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1034,6 +1064,61 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_
             gcell_h[k * 3 + b] = g.pbc[k] ? c : 0.0;
         }
     SGPR_CUDA(cudaGetLastError());
+    return SGPR_OK;
+}
+
+// Training-time kernels of the structure of the LAST sgpr_kernel_forward against inducing LCEs m0 <= m < m1
+// (caller's order): the Jacobian of Ke[m] = sum_i K[i,m], one backward pass per LCE with a rank-1 cotangent.
+extern "C" __attribute__((visibility("default"))) int sgpr_kernel_jacobian(sgpr_handle h, int32_t m0, int32_t m1, void* stream, double* J_d, double* W_d) {
+    if (!h || !J_d || !W_d) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    if (!h->fwd_valid) {
+        set_error("sgpr_kernel_jacobian needs a preceding sgpr_kernel_forward on this handle");
+        return SGPR_ERR_INVALID;
+    }
+    if (m0 < 0 || m1 > h->M || m0 > m1) {
+        set_error("inducing range [%d, %d) outside [0, %d)", m0, m1, h->M);
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    const int64_t N = h->last_N;
+    const Geom g = h->last_geom;
+    const size_t nrows = (size_t)h->n_active + 1;
+    const int nblk_b = backward_grid(h), nblk_x = 64;
+    SGPR_TRY(h->gvec.ensure(sizeof(double) * nrows * h->dp.ldp));
+    SGPR_TRY(h->erow.ensure(sizeof(double) * nrows));
+    SGPR_TRY(h->epart.ensure(sizeof(double) * (16 + 9 * nblk_x)));
+    SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
+    SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
+    h->use_i8_now = false;
+    std::vector<int> pos_of(h->M);
+    for (int p = 0; p < h->M; ++p) pos_of[h->ind_perm[p]] = p;
+    double* scratch = h->epart.as<double>();
+    for (int m = m0; m < m1; ++m) {
+        const int p = pos_of[m], s = h->ind_sp[p];
+        const int r0 = h->row_first[s], r1 = h->row_first[s + 1];
+        double* Jm = J_d + (size_t)(m - m0) * 3 * (size_t)N;
+        double* Wm = W_d + (size_t)(m - m0) * 9;
+        if (N == 0 || r1 == r0 || !h->dp.central_enabled[s]) {
+            if (N > 0) SGPR_CUDA(cudaMemsetAsync(Jm, 0, sizeof(double) * 3 * (size_t)N, st));
+            SGPR_CUDA(cudaMemsetAsync(Wm, 0, sizeof(double) * 9, st));
+            continue;
+        }
+        SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
+        SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+        column_seed_kernel<<<std::min<int64_t>((h->n_active + 7) / 8, h->sm_count * 8), 256, 0, st>>>(
+            (int)h->n_active, r0, r1, h->dp.D, h->dp.ldp, h->phat.as<double>(), h->zhat.as<double>() + (size_t)p * h->dp.ldp,
+            h->xi, h->xi_int, h->gvec.as<double>(), h->erow.as<double>());
+        SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
+        vjp_finish_kernel<<<nblk_x, 128, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(), Jm, scratch + 16);
+        final_reduce_kernel<<<1, 256, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), scratch, Wm);
+        h->stats.kernel_launches += 3;
+    }
+    SGPR_CUDA(cudaGetLastError());
+    SGPR_CUDA(cudaStreamSynchronize(st));
     return SGPR_OK;
 }
 

@@ -55,6 +55,7 @@ EXPORTS = {
     "sgpr_p2p_collect": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_forward": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_kernel_jacobian": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "sgpr_neighbors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "sgpr_descriptors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -336,6 +337,23 @@ class SgprEngine:
         _check(self.lib, self.lib.sgpr_kernel_backward(self._h, c_void_p(gK.data_ptr()), self._stream(), c_void_p(gpos.data_ptr()),
                                                        _ptr(gcell)))
         return gpos, gcell.reshape(3, 3)
+
+    def kernel_jacobian(self, pos, numbers, cell, pbc, m0=0, m1=None):
+        """Training-time kernels of one structure against the inducing set (regression/gppotential.py:63-77):
+        returns (K [N,M] device tensor, Kf [3N, m1-m0], Kv [6, m1-m0]) with Kf = forces_energy = -leftgrad and
+        Kv = virial_energy (xx,yy,zz,yz,xz,xy; not divided by the volume); Ke = K.sum(0)."""
+        import torch
+
+        K = self.kernel_matrix(pos, numbers, cell, pbc)
+        N = K.shape[0]
+        m1 = self.model.M if m1 is None else m1
+        J = torch.zeros((m1 - m0, N, 3), dtype=torch.float64, device=K.device)
+        W = torch.zeros((m1 - m0, 9), dtype=torch.float64, device=K.device)
+        _check(self.lib, self.lib.sgpr_kernel_jacobian(self._h, m0, m1, self._stream(), c_void_p(J.data_ptr()),
+                                                       c_void_p(W.data_ptr())))
+        Kf = -J.reshape(m1 - m0, 3 * N).t().contiguous()
+        Kv = W[:, [0, 4, 8, 5, 2, 1]].t().contiguous()
+        return K, Kf, Kv
 
     def cov(self, xyz, lll, numbers, pbc):
         """Differentiable kernel matrix: ``cov = model.gp.kern(atoms, model.X)`` (calculator/active.py:464) as a

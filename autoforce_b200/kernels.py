@@ -69,15 +69,21 @@ class _SoapKernelBase:
 
     def __call__(self, first, second, operation="func"):
         """first: structure with .positions/.cell/.pbc/.numbers; second: list of
-        (Z, r[nn,3], b[nn]) local chemical environments.  Returns K[len(first), len(second)]."""
-        if operation != "func":
-            raise NotImplementedError("only operation='func' is on the prediction path")
+        (Z, r[nn,3], b[nn]) local chemical environments.  ``operation`` as in similarity/similarity.py:17-31:
+        "func" -> K [N, M];  "leftgrad" -> d(sum_i K[i,m])/d xyz [3N, M];  "virial" -> [6, M]
+        (similarity/universal.py:109-183; true derivatives, see include/sgpr_b200.h sgpr_kernel_jacobian)."""
+        if operation not in ("func", "leftgrad", "virial"):
+            raise NotImplementedError(f"operation={operation!r}: only func / leftgrad / virial are implemented")
         from .engine import SgprEngine
 
         model = self._base_model(second)
         eng = SgprEngine(model, species=np.unique(first.numbers))
         try:
-            return eng.kernel_matrix(first.positions, first.numbers, np.asarray(first.cell), first.pbc).cpu().numpy()
+            args = (first.positions, first.numbers, np.asarray(first.cell), first.pbc)
+            if operation == "func":
+                return eng.kernel_matrix(*args).cpu().numpy()
+            _, Kf, Kv = eng.kernel_jacobian(*args)
+            return -Kf.cpu().numpy() if operation == "leftgrad" else Kv.cpu().numpy()
         finally:
             eng.close()
 

@@ -164,6 +164,18 @@ int sgpr_kernel_forward(sgpr_handle h, int64_t N, const double* pos_d, const int
 int sgpr_kernel_backward(sgpr_handle h, const double* gK_d, void* stream, double* gpos_d,
                          double* gcell_h);
 
+/* Training-time kernels of the structure of the LAST sgpr_kernel_forward against the inducing LCEs
+ * m0 <= m < m1 (caller's order), i.e. what EnergyForceKernel.forces_energy / virial_energy
+ * (regression/gppotential.py:66-77) build from SimilarityKernel "leftgrad" / "virial"
+ * (similarity/universal.py:124-183):
+ *   J_d [(m1-m0), N, 3] = d (sum_i K[i,m]) / d xyz       (leftgrad; forces_energy = -J)
+ *   W_d [(m1-m0), 9]    = sum_pairs r (x) dK/dr, row-major 3x3, NOT divided by the volume
+ *                         (virial_energy = W.flat[[0,4,8,5,2,1]])
+ * These are the true derivatives (they agree with torch.autograd through the reference's forward pass);
+ * the reference's hand-written leftgrad drops contributions when an atom occurs twice in one environment
+ * (index assignment g[j] += f, universal.py:148) -- see tests/golden/make_golden_train.py. */
+int sgpr_kernel_jacobian(sgpr_handle h, int32_t m0, int32_t m1, void* stream, double* J_d, double* W_d);
+
 /* ---- parity hooks (used by tests; same kernels as the hot path) --------------------- */
 
 /* Neighbour list as ASE's NeighborList(N*[rc/2], skin=0, self_interaction=False,

@@ -577,6 +577,68 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
     return out
 
 
+def kernel_jacobian(model, pos, cell, pbc, numbers, chunk=256, scatter_quirk=False):
+    """Training-time kernels of ONE structure against the inducing set, as ``EnergyForceKernel`` builds them
+    (regression/gppotential.py:63-77 over similarity/universal.py:109-183):
+
+      Ke [M]     = energy_energy([atoms], X)  = sum_i K[i,m]
+      Kf [3N, M] = forces_energy([atoms], X)  = -leftgrad = -d Ke[m] / d xyz
+      Kv [6, M]  = virial_energy([atoms], X)  = sum_pairs r (x) dk/dr, picked [0,4,8,5,2,1] (xx,yy,zz,yz,xz,xy),
+                   NOT divided by the volume (universal.py:155-183)
+
+    i.e. the prediction backward pass with mu replaced by each unit vector e_m in turn.
+
+    ``scatter_quirk=True`` reproduces the reference's hand-written ``leftgrad`` instead of the true derivative:
+    ``g[j] += f`` (universal.py:148) is an index assignment, so when the same atom j occurs more than once in an
+    environment (periodic images in a cell narrower than 2 rc) only the LAST of its contributions survives.
+    The reference's autograd forces (calculator/active.py:587-611) do not have this defect."""
+    pos = np.asarray(pos, dtype=float).reshape(-1, 3)
+    numbers = np.asarray(numbers, dtype=np.int64)
+    cell = np.asarray(cell, dtype=float).reshape(3, 3)
+    N, M = len(pos), model.M
+    species = model.species_table(extra=numbers)
+    first, J, S = neighbor_list(pos, cell, pbc, model.rc)
+    Zh, lone_m = inducing_descriptors(model, species, chunk)
+    Ke = np.zeros(M)
+    G = np.zeros((M, N, 3))     # d Ke[m] / d xyz
+    W = np.zeros((M, 3, 3))
+    xi = model.xi
+    for k0 in range(0, N, chunk):
+        idx = np.arange(k0, min(N, k0 + chunk))
+        envs_r, envs_b, envs_j = [], [], []
+        for i in idx:
+            sl = slice(first[i], first[i + 1])
+            envs_r.append(displacements(pos, cell, i, J[sl], S[sl]))
+            envs_b.append(numbers[J[sl]])
+            envs_j.append(J[sl])
+        R, Zb, mask = pad_environments(envs_r, envs_b)
+        P, aux = descriptor_batch(model, species, R, Zb, mask, want_aux=True)
+        lone_c = ~mask.any(axis=1)
+        K, dot, valid = kernel_from_descriptors(model, P, numbers[idx], lone_c, Zh, lone_m)
+        Ke += K.sum(axis=0)
+        Gm = np.where(valid, xi * _powxi(dot, xi - 1), 0.0)
+        Zflat = Zh.reshape(M, -1)
+        for m in range(M):
+            if not Gm[:, m].any():
+                continue
+            g = (Gm[:, m : m + 1] * Zflat[m][None, :]).reshape(P.shape)
+            dR = descriptor_backward(model, P, aux, g)       # dk/dr per pair
+            for b, i in enumerate(idx):
+                nn = len(envs_j[b])
+                if nn == 0:
+                    continue
+                gb = dR[b, :nn]
+                G[m, i] -= gb.sum(axis=0)                     # universal.py:147-148: g[i] -= f ; g[j] += f
+                if scatter_quirk:
+                    G[m][envs_j[b]] += gb                     # non-accumulating, like torch's g[j] += f
+                else:
+                    np.add.at(G[m], envs_j[b], gb)
+                W[m] += envs_r[b].T @ gb
+    Kf = -G.reshape(M, 3 * N).T
+    Kv = W.reshape(M, 9)[:, [0, 4, 8, 5, 2, 1]].T
+    return Ke, Kf, Kv
+
+
 def covloss(model, K, numbers, alpha=None):
     """calculator/active.py:781-804.  ``alpha`` = self kernel k(x,x) per atom: the
     reference divides by it whenever it is not identically 1 (active.py:784-791), which

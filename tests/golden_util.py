@@ -9,7 +9,19 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if not n.endswith("_train")]
+
+
+def train_cases():
+    """Cases with training-time kernels (tests/golden/make_golden_train.py)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*_train.npz")))
+    return [n[: -len("_train")] for n in names]
+
+
+def load_train(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + "_train.npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
 
 
 def load_golden(name):

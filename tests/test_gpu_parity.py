@@ -9,7 +9,7 @@ Everything on this path computes in float64, so the asserts below are far tighte
 import numpy as np
 import pytest
 
-from golden_util import golden_cases, golden_radii, load_golden, oracle_model
+from golden_util import golden_cases, golden_radii, load_golden, load_train, oracle_model, train_cases
 from oracle import sgpr_oracle as o
 
 pytestmark = pytest.mark.gpu
@@ -296,3 +296,45 @@ def test_append_inducing_matches_a_model_built_in_one_go(name):
     Kmat = eng.kernel_matrix(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"]).cpu().numpy()
     assert np.abs(Kmat - g["K"]).max() < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("name", train_cases())
+def test_training_kernels_match_reference_autograd(name):
+    """sgpr_kernel_jacobian: Kf = forces_energy, Kv = virial_energy of the structure against the inducing set
+    (regression/gppotential.py:66-77) equal the derivatives torch.autograd takes through the reference's own
+    forward pass (tests/golden/make_golden_train.py), and the oracle's."""
+    import autoforce_b200 as ab
+
+    g, t = load_golden(name), load_train(name)
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    K, Kf, Kv = eng.kernel_jacobian(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    K, Kf, Kv = K.cpu().numpy(), Kf.cpu().numpy(), Kv.cpu().numpy()
+    N, M = len(g["numbers"]), len(g["mu"])
+    assert Kf.shape == (3 * N, M) and Kv.shape == (6, M)
+    assert np.abs(K.sum(axis=0) - t["Ke"]).max() < 1e-11
+    assert np.abs(Kf - t["Kf_autograd"]).max() < 1e-9
+    assert np.abs(Kv - t["Kv_autograd"]).max() < 1e-8
+    assert np.abs(Kv - t["Kv_analytic"]).max() < 1e-6
+    # a sub-range of inducing LCEs gives the same columns; forces = Kf @ mu
+    _, Kf2, Kv2 = eng.kernel_jacobian(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"], m0=1, m1=min(M, 4))
+    assert np.abs(Kf2.cpu().numpy() - Kf[:, 1 : min(M, 4)]).max() < 1e-12 and np.abs(Kv2.cpu().numpy() - Kv[:, 1 : min(M, 4)]).max() < 1e-11
+    assert np.abs(Kf @ g["mu"] - g["forces"].reshape(-1)).max() < TOL_F
+    eng.close()
+
+
+def test_similarity_kernel_operations():
+    """kern(atoms, X, operation=...) of similarity/similarity.py:17-31 for func / leftgrad / virial."""
+    import types
+
+    import autoforce_b200 as ab
+
+    g, t = load_golden("cu108_sesoap"), load_train("cu108_sesoap")
+    k = g["meta"]["kernel"]
+    kern = ab.SeSoapKernel(k["lmax"], k["nmax"], k["xi"], k["rc"], radii=ab.DefaultRadii())
+    atoms = types.SimpleNamespace(positions=g["pos"], numbers=g["numbers"], cell=g["cell"], pbc=g["meta"]["pbc"])
+    X = [(int(z), r, b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    assert np.abs(kern(atoms, X) - g["K"]).max() < 1e-12
+    assert np.abs(-kern(atoms, X, operation="leftgrad") - t["Kf_autograd"]).max() < 1e-9
+    assert np.abs(kern(atoms, X, operation="virial") - t["Kv_autograd"]).max() < 1e-8
+    with pytest.raises(NotImplementedError):
+        kern(atoms, X, operation="gradgrad")

@@ -338,3 +338,24 @@ def test_similarity_kernel_operations():
     assert np.abs(kern(atoms, X, operation="virial") - t["Kv_autograd"]).max() < 1e-8
     with pytest.raises(NotImplementedError):
         kern(atoms, X, operation="gradgrad")
+
+
+def test_lammps_fix_external_callback_drives_the_gpu_path():
+    """cl/lmp.py:42-71 with the B200 calculator: forces by tag, global energy and virial handed to the fix."""
+    import autoforce_b200 as ab
+    from autoforce_b200 import lammps_driver as ld
+    from test_lammps_driver import FakeLammps
+
+    g = load_golden("cu108_sesoap")
+    cell = np.asarray(g["cell"], dtype=float)
+    assert np.allclose(cell, np.triu(cell))          # LAMMPS box convention
+    lmp = FakeLammps(cell, g["pos"], [1] * len(g["numbers"]))
+    calc = ab.B200Calculator(model_from_golden(g))
+    cb = ld.FixExternalCallback(lmp, calc, "metal", {1: int(g["numbers"][0])})
+    tag = np.random.default_rng(0).permutation(len(g["numbers"])) + 1
+    fext = np.zeros((len(tag), 3))
+    cb(None, 0, len(tag), tag, None, fext)
+    assert np.abs(fext - g["forces"][tag - 1]).max() < TOL_F
+    assert abs(lmp.energy[1] - float(g["energy"])) < TOL_E_PER_ATOM * len(tag)
+    vol = abs(np.linalg.det(cell))
+    assert np.allclose(lmp.virial[1], -g["stress"][[0, 1, 2, 5, 4, 3]] * vol, rtol=1e-6, atol=1e-9)

@@ -523,6 +523,222 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
     }
 }
 
+// ---------------------------------------------------------------------------------
+// neighbour search, one BLOCK per bin (the path for all but tiny systems): every atom of a bin walks the
+// same stencil, so the block gathers the candidates of the stencil once into shared memory -- already
+// shifted to the right periodic image -- and its warps then test their atoms against that tile without
+// touching global memory.  Same two passes, masks, pair order and exact accept rule as neighbor_kernel:
+// the shared-memory test decides everything except d^2 within 1e-11 of rc^2, which goes through
+// pair_test (the reference's rounding sequence).
+// ---------------------------------------------------------------------------------
+constexpr int kBinThreads = 256, kBinCap = 1024, kRunChunk = 128;
+
+template <bool FILL, int NS>
+__global__ void __launch_bounds__(kBinThreads) neighbor_bin_kernel(int c_begin, int c_end, int env0,
+                                                                   const AtomRec* __restrict__ atoms,
+                                                                   const int* __restrict__ cstart, Geom g, int S,
+                                                                   int* __restrict__ nl_cnt,
+                                                                   const long long* __restrict__ nl_first,
+                                                                   PairRec* __restrict__ pairs, unsigned char* __restrict__ mark,
+                                                                   unsigned* __restrict__ masks, int* __restrict__ nl_run) {
+    __shared__ double xs[kBinCap], ys[kBinCap], zs[kBinCap];
+    __shared__ int pj[kBinCap];
+    __shared__ unsigned code[kBinCap];       // bin shift (3 x int8) | species << 24
+    __shared__ int run_beg[kRunChunk], run_pre[kRunChunk + 1];
+    __shared__ unsigned run_sh[kRunChunk];
+    const int bin = blockIdx.x;
+    const int lo = max(cstart[bin * S], c_begin), hi = min(cstart[(bin + 1) * S], c_end);
+    if (lo >= hi) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kBinThreads / 32;
+    const int bz = bin % g.nb[2], by = (bin / g.nb[2]) % g.nb[1], bx = bin / (g.nb[2] * g.nb[1]);
+    const int zlo = bz - g.reach[2], zhi = bz + g.reach[2];
+    const bool merged = (zlo >= 0 && zhi < g.nb[2]);   // z stencil contiguous in cell order: one run per column
+    const int nyr = 2 * g.reach[1] + 1, nzr = merged ? 1 : 2 * g.reach[2] + 1;
+    const int nruns = (2 * g.reach[0] + 1) * nyr * nzr;
+    const double rc2 = g.rc * g.rc;
+    const double fast_lo = rc2 * (1.0 - 1e-11), fast_hi = rc2 * (1.0 + 1e-11);
+    const double rc2_lo = rc2 * (1.0 - 1e-14), rc2_hi = rc2 * (1.0 + 1e-14);
+    int slot_base = 0, tile_no = 0;
+    for (int r0 = 0; r0 < nruns; r0 += kRunChunk) {
+        const int nr = min(kRunChunk, nruns - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr; t += kBinThreads) {
+            const int r = r0 + t;
+            const int iz = r % nzr, iy = (r / nzr) % nyr, ix = r / (nzr * nyr);
+            int nx, sx, ny, sy, nz = zlo, sz = 0, nz_last = zhi;
+            bool ok = wrap_bin(bx + ix - g.reach[0], g.nb[0], g.pbc[0], nx, sx) &&
+                      wrap_bin(by + iy - g.reach[1], g.nb[1], g.pbc[1], ny, sy);
+            if (ok && !merged) {
+                ok = wrap_bin(bz + iz - g.reach[2], g.nb[2], g.pbc[2], nz, sz);
+                nz_last = nz;
+            }
+            int beg = 0, len = 0;
+            if (ok) {
+                const int col = (nx * g.nb[1] + ny) * g.nb[2];
+                beg = cstart[(col + nz) * S];
+                len = cstart[(col + nz_last) * S + S] - beg;
+            }
+            run_beg[t] = beg;
+            run_pre[t + 1] = len;
+            run_sh[t] = (unsigned)(sx & 0xff) | ((unsigned)(sy & 0xff) << 8) | ((unsigned)(sz & 0xff) << 16);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            run_pre[0] = 0;
+            for (int t = 0; t < nr; ++t) run_pre[t + 1] += run_pre[t];
+        }
+        __syncthreads();
+        const int total = run_pre[nr];
+        for (int t0 = 0; t0 < total; t0 += kBinCap) {
+            const int n = min(kBinCap, total - t0);
+            const bool last_tile = (r0 + kRunChunk >= nruns) && (t0 + kBinCap >= total);
+            if (t0 > 0) __syncthreads();   // the previous tile is still being read
+            for (int q = threadIdx.x; q < n; q += kBinThreads) {
+                const int gq = t0 + q;
+                int a = 0, b = nr;          // last run with run_pre[a] <= gq
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (run_pre[mid] <= gq) a = mid;
+                    else b = mid;
+                }
+                const int p = run_beg[a] + (gq - run_pre[a]);
+                const AtomRec aj = atoms[p];
+                const unsigned sh = run_sh[a];
+                double s0, s1, s2;
+                shift_vec(g, (int)(signed char)(sh & 0xff) - meta_w(aj.meta, 0), (int)(signed char)((sh >> 8) & 0xff) - meta_w(aj.meta, 1),
+                          (int)(signed char)((sh >> 16) & 0xff) - meta_w(aj.meta, 2), s0, s1, s2);
+                xs[q] = aj.x + s0;
+                ys[q] = aj.y + s1;
+                zs[q] = aj.z + s2;
+                pj[q] = p;
+                code[q] = sh | ((unsigned)meta_species(aj.meta) << 24);
+            }
+            __syncthreads();
+            for (int c = lo + warp; c < hi; c += NW) {
+                const int wid = c - c_begin + env0;
+                const AtomRec ai = atoms[c];
+                double w0, w1, w2;
+                shift_vec(g, meta_w(ai.meta, 0), meta_w(ai.meta, 1), meta_w(ai.meta, 2), w0, w1, w2);
+                const double xi = ai.x - w0, yi = ai.y - w1, zi = ai.z - w2;   // the atom's image inside the box
+                unsigned long long pc0 = 0ull, pc1 = 0ull;
+                int count[NS];
+                long long base[NS];
+                unsigned mk0 = 0u, mk1 = 0u;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) count[s] = 0;
+                if (FILL) {
+                    long long o = nl_first[wid];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        base[s] = o;
+                        if (s < S) {
+                            o += nl_cnt[(long long)wid * S + s];
+                            if (tile_no > 0) count[s] = nl_run[(long long)wid * S + s];
+                        }
+                    }
+                    mk0 = masks[(size_t)wid * kMaskSlots + lane];
+                    mk1 = masks[(size_t)wid * kMaskSlots + 32 + lane];
+                }
+                for (int b0 = 0; b0 < n; b0 += 32) {
+                    const int q = b0 + lane;
+                    const int slot = slot_base + (b0 >> 5);
+                    const bool valid = q < n;
+                    const unsigned cd = valid ? code[q] : 0u;
+                    const int sp = (int)(cd >> 24);
+                    bool acc = false;
+                    if (FILL && slot < kMaskSlots) {
+                        const unsigned m_all = slot < 32 ? __shfl_sync(0xffffffffu, mk0, slot) : __shfl_sync(0xffffffffu, mk1, slot - 32);
+                        acc = (m_all >> lane) & 1u;
+                    } else if (valid) {
+                        const double dx = xs[q] - xi, dy = ys[q] - yi, dz = zs[q] - zi;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        const int p = pj[q];
+                        acc = d2 < fast_lo;
+                        if (p == c && (cd & 0xffffffu) == 0u) {
+                            acc = false;                       // the atom itself (zero image shift)
+                        } else if (!acc && d2 <= fast_hi) {     // borderline: the reference's exact rounding sequence
+                            const AtomRec aj = atoms[p];
+                            const int sx = (int)(signed char)(cd & 0xff), sy = (int)(signed char)((cd >> 8) & 0xff),
+                                      sz = (int)(signed char)((cd >> 16) & 0xff);
+                            double sh0, sh1, sh2;
+                            shift_vec(g, sx, sy, sz, sh0, sh1, sh2);
+                            acc = pair_test(g, ai, aj, sx, sy, sz, sh0, sh1, sh2, rc2_lo, rc2_hi, false);
+                        }
+                    }
+                    if (!FILL) {
+                        if (acc) {
+                            if (mark) mark[pj[q]] = 1;   // atoms whose environment the owner needs (halo)
+                            const unsigned long long one = 1ull << (16 * (sp & 3));
+                            if (NS <= 4 || sp < 4) pc0 += one;
+                            else pc1 += one;
+                        }
+                        if (slot < kMaskSlots) {
+                            const unsigned m_all = __ballot_sync(0xffffffffu, acc);
+                            if (lane == 0) masks[(size_t)wid * kMaskSlots + slot] = m_all;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            const unsigned m = __ballot_sync(0xffffffffu, acc && sp == s);
+                            if (acc && sp == s) {
+                                PairRec pr;
+                                pr.j = pj[q];
+                                pr.sb[0] = (signed char)(cd & 0xff);
+                                pr.sb[1] = (signed char)((cd >> 8) & 0xff);
+                                pr.sb[2] = (signed char)((cd >> 16) & 0xff);
+                                pr.sp = (unsigned char)sp;
+                                pairs[base[s] + count[s] + __popc(m & ((1u << lane) - 1u))] = pr;
+                            }
+                            count[s] += __popc(m);
+                        }
+                    }
+                }
+                if (!FILL) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        pc0 += __shfl_xor_sync(0xffffffffu, pc0, o);
+                        if (NS > 4) pc1 += __shfl_xor_sync(0xffffffffu, pc1, o);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (s < S) {
+                                const int v = (int)(((s < 4 ? pc0 : pc1) >> (16 * (s & 3))) & 0xffffull);
+                                int* dst = nl_cnt + (long long)wid * S + s;
+                                *dst = tile_no > 0 ? *dst + v : v;
+                            }
+                    }
+                } else if (!last_tile && lane == 0) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (s < S) nl_run[(long long)wid * S + s] = count[s];
+                }
+            }
+            slot_base += (n + 31) >> 5;
+            ++tile_no;
+        }
+    }
+}
+
+template <bool FILL>
+static void launch_neighbor_bins(cudaStream_t st, int S, int c_begin, int c_end, int env0, const AtomRec* atoms,
+                                 const int* cstart, const Geom& g, int* nl_cnt, const long long* nl_first, PairRec* pairs,
+                                 unsigned char* mark, unsigned* masks, int* nl_run) {
+    const int nblk = g.ncell, T = kBinThreads;
+    if (S <= 1)
+        neighbor_bin_kernel<FILL, 1><<<nblk, T, 0, st>>>(c_begin, c_end, env0, atoms, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks, nl_run);
+    else if (S <= 2)
+        neighbor_bin_kernel<FILL, 2><<<nblk, T, 0, st>>>(c_begin, c_end, env0, atoms, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks, nl_run);
+    else if (S <= 4)
+        neighbor_bin_kernel<FILL, 4><<<nblk, T, 0, st>>>(c_begin, c_end, env0, atoms, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks, nl_run);
+    else
+        neighbor_bin_kernel<FILL, 8><<<nblk, T, 0, st>>>(c_begin, c_end, env0, atoms, cstart, g, S, nl_cnt, nl_first, pairs, mark, masks, nl_run);
+}
+
+// the block-per-bin kernels need enough bins to fill the machine; tiny systems keep one warp per environment
+static bool use_bin_kernels(const sgpr_context* h, const Geom& g) { return h->nl_mode == 2 || (g.ncell >= 64 && h->nl_mode != 1); }
+
 template <bool FILL>
 static void launch_neighbor(int nblk, int T, cudaStream_t st, int S, int env0, int n_env, const int* active,
                             const AtomRec* atoms, const int* abin, const int* cstart, const Geom& g, int* nl_cnt,
@@ -546,8 +762,16 @@ __global__ void row_total_kernel(int n, int S, const int* __restrict__ nl_cnt, l
     tot[i] = t;
 }
 
-static int launch_count(sgpr_context* h, int env0, int n_env, const Geom& g, unsigned char* mark, cudaStream_t st) {
+// contig_c0 >= 0: environments env0 .. env0+n_env-1 are the atoms contig_c0 .. of the cell order
+static int launch_count(sgpr_context* h, int env0, int n_env, const Geom& g, unsigned char* mark, cudaStream_t st,
+                        int contig_c0) {
     if (n_env <= 0) return SGPR_OK;
+    if (contig_c0 >= 0 && use_bin_kernels(h, g)) {
+        launch_neighbor_bins<false>(st, h->S, contig_c0, contig_c0 + n_env, env0, h->atoms.as<AtomRec>(), h->cstart.as<int>(), g,
+                                    h->nl_cnt.as<int>(), nullptr, nullptr, mark, h->nl_masks.as<unsigned>(), nullptr);
+        h->stats.kernel_launches += 1;
+        return SGPR_OK;
+    }
     const int T = 256;
     const int nblk = (int)(((int64_t)n_env * 32 + T - 1) / T);
     launch_neighbor<false>(nblk, T, st, h->S, env0, n_env, h->active_all ? nullptr : h->active_list.as<int>(),
@@ -571,7 +795,7 @@ static int check_err_flags(const int* err) {
 
 // row totals -> exclusive scan -> (sync: pair count, error flags, species row ranges) -> fill
 static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int* row_first_src, int row_first_pitch,
-                     int64_t* n_pairs) {
+                     int64_t* n_pairs, int contig_c0, int n_contig) {
     const int S = h->S;
     const int na = (int)h->n_active;
     SGPR_TRY(h->nl_first.ensure(sizeof(long long) * 2 * ((size_t)na + 1)));
@@ -591,9 +815,17 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
     SGPR_TRY(check_err_flags(err));
     for (int s = 0; s <= S; ++s) h->row_first[s] = rf[s];
     SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
-    if (na > 0) {
-        const int nblk = (int)(((int64_t)na * 32 + T - 1) / T);
-        launch_neighbor<true>(nblk, T, st, S, 0, na, h->active_all ? nullptr : h->active_list.as<int>(),
+    int done = 0;   // environments 0 .. n_contig-1 are a contiguous range of the cell order: block-per-bin fill
+    if (n_contig > 0 && use_bin_kernels(h, g)) {
+        SGPR_TRY(h->nl_run.ensure(sizeof(int) * ((size_t)n_contig * S + 1)));
+        launch_neighbor_bins<true>(st, S, contig_c0, contig_c0 + n_contig, 0, h->atoms.as<AtomRec>(), h->cstart.as<int>(), g,
+                                   h->nl_cnt.as<int>(), first, h->nl_pairs.as<PairRec>(), nullptr,
+                                   h->nl_masks.as<unsigned>(), h->nl_run.as<int>());
+        done = n_contig;
+    }
+    if (na > done) {
+        const int nblk = (int)(((int64_t)(na - done) * 32 + T - 1) / T);
+        launch_neighbor<true>(nblk, T, st, S, done, na - done, h->active_all ? nullptr : h->active_list.as<int>(),
                               h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->nl_cnt.as<int>(), first,
                               h->nl_pairs.as<PairRec>(), nullptr, h->nl_masks.as<unsigned>());
     }
@@ -611,10 +843,10 @@ int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, i
     h->n_active = N;
     SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * h->S + 1)));
     SGPR_TRY(h->nl_masks.ensure(sizeof(unsigned) * kMaskSlots * ((size_t)N + 1)));
-    SGPR_TRY(launch_count(h, 0, (int)N, g, nullptr, st));
+    SGPR_TRY(launch_count(h, 0, (int)N, g, nullptr, st, 0));
     const int nkeys = g.ncell * h->S;
     const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
-    return nl_finish(h, g, st, rstartT, (int)sizeof(int) * g.ncell, n_pairs);
+    return nl_finish(h, g, st, rstartT, (int)sizeof(int) * g.ncell, n_pairs, 0, (int)N);
 }
 
 // ---------------------------------------------------------------------------------
@@ -735,7 +967,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     const int nblkN = (int)((N + 1 + T - 1) / T);
     shard_init_kernel<<<nblkN, T, 0, st>>>(N, c0, c1, owned, mark, active, rowof);
     h->n_active = n_own;
-    SGPR_TRY(launch_count(h, 0, n_own, g, with_halo ? mark : nullptr, st));
+    SGPR_TRY(launch_count(h, 0, n_own, g, with_halo ? mark : nullptr, st, c0));
     int n_halo = 0;
     if (with_halo) {
         halo_flag_kernel<<<nblkN, T, 0, st>>>(N, owned, mark, flag);
@@ -749,7 +981,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     }
     const int na = n_own + n_halo;
     h->n_active = na;
-    SGPR_TRY(launch_count(h, n_own, n_halo, g, nullptr, st));
+    SGPR_TRY(launch_count(h, n_own, n_halo, g, nullptr, st, -1));
     // species-major rows over the active list
     SGPR_CUDA(cudaMemsetAsync(row_first_d, 0, sizeof(int) * (SGPR_MAX_SPECIES + 1), st));
     const int nblkA = (na + 1 + T - 1) / T;
@@ -767,7 +999,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
                                                                  h->row_owned.as<unsigned char>());
         h->stats.kernel_launches += 3;
         SGPR_CUDA(cudaGetLastError());
-        return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs);
+        return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own);
     }
     for (int s = 0; s < S; ++s) {
         species_flag_kernel<<<nblkA, T, 0, st>>>(na, active, h->atoms.as<AtomRec>(), s, flag);
@@ -780,7 +1012,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     }
     h->stats.kernel_launches += 5 + 4 * S;
     SGPR_CUDA(cudaGetLastError());
-    return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs);
+    return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own);
 }
 
 }  // namespace sgpr

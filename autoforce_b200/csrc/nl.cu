@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) neighbor_kernel(int env0, int n_env, cons
 constexpr int kBinThreads = 256, kBinCap = 1024, kRunChunk = 128;
 
 template <bool FILL, int NS>
-__global__ void __launch_bounds__(kBinThreads) neighbor_bin_kernel(int c_begin, int c_end, int env0,
+__global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begin, int c_end, int env0,
                                                                    const AtomRec* __restrict__ atoms,
                                                                    const int* __restrict__ cstart, Geom g, int S,
                                                                    int* __restrict__ nl_cnt,
@@ -615,86 +615,57 @@ __global__ void __launch_bounds__(kBinThreads) neighbor_bin_kernel(int c_begin, 
                 code[q] = sh | ((unsigned)meta_species(aj.meta) << 24);
             }
             __syncthreads();
+            // accept bits of an environment: one 64-bit word per lane, bit k = candidate (slot k, this lane)
+            const int nb_tile = (n + 31) >> 5;
+            const int nb_masked = max(0, min(nb_tile, kMaskSlots - slot_base));   // batches of this tile covered by the word
             for (int c = lo + warp; c < hi; c += NW) {
                 const int wid = c - c_begin + env0;
                 const AtomRec ai = atoms[c];
+                unsigned long long* my_word = reinterpret_cast<unsigned long long*>(masks) + (size_t)wid * 32 + lane;
+                unsigned long long accw = 0ull;
+                long long first_pair = 0;
+                int cnt_s[NS];
+                if (FILL) {
+                    accw = *my_word;
+                    first_pair = nl_first[wid];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) cnt_s[s] = s < S ? nl_cnt[(long long)wid * S + s] : 0;
+                } else if (tile_no > 0 && slot_base < kMaskSlots) {
+                    accw = *my_word;
+                }
                 double w0, w1, w2;
                 shift_vec(g, meta_w(ai.meta, 0), meta_w(ai.meta, 1), meta_w(ai.meta, 2), w0, w1, w2);
                 const double xi = ai.x - w0, yi = ai.y - w1, zi = ai.z - w2;   // the atom's image inside the box
-                unsigned long long pc0 = 0ull, pc1 = 0ull;
-                int count[NS];
-                long long base[NS];
-                unsigned mk0 = 0u, mk1 = 0u;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) count[s] = 0;
-                if (FILL) {
-                    long long o = nl_first[wid];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        base[s] = o;
-                        if (s < S) {
-                            o += nl_cnt[(long long)wid * S + s];
-                            if (tile_no > 0) count[s] = nl_run[(long long)wid * S + s];
-                        }
-                    }
-                    mk0 = masks[(size_t)wid * kMaskSlots + lane];
-                    mk1 = masks[(size_t)wid * kMaskSlots + 32 + lane];
-                }
-                for (int b0 = 0; b0 < n; b0 += 32) {
-                    const int q = b0 + lane;
-                    const int slot = slot_base + (b0 >> 5);
-                    const bool valid = q < n;
-                    const unsigned cd = valid ? code[q] : 0u;
-                    const int sp = (int)(cd >> 24);
-                    bool acc = false;
-                    if (FILL && slot < kMaskSlots) {
-                        const unsigned m_all = slot < 32 ? __shfl_sync(0xffffffffu, mk0, slot) : __shfl_sync(0xffffffffu, mk1, slot - 32);
-                        acc = (m_all >> lane) & 1u;
-                    } else if (valid) {
-                        const double dx = xs[q] - xi, dy = ys[q] - yi, dz = zs[q] - zi;
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        const int p = pj[q];
-                        acc = d2 < fast_lo;
-                        if (p == c && (cd & 0xffffffu) == 0u) {
-                            acc = false;                       // the atom itself (zero image shift)
-                        } else if (!acc && d2 <= fast_hi) {     // borderline: the reference's exact rounding sequence
-                            const AtomRec aj = atoms[p];
-                            const int sx = (int)(signed char)(cd & 0xff), sy = (int)(signed char)((cd >> 8) & 0xff),
-                                      sz = (int)(signed char)((cd >> 16) & 0xff);
-                            double sh0, sh1, sh2;
-                            shift_vec(g, sx, sy, sz, sh0, sh1, sh2);
-                            acc = pair_test(g, ai, aj, sx, sy, sz, sh0, sh1, sh2, rc2_lo, rc2_hi, false);
-                        }
-                    }
-                    if (!FILL) {
-                        if (acc) {
+                // distance test of candidate q (shared-memory tile); exact rounding sequence only near rc
+                auto test = [&](int q) -> bool {
+                    const double dx = xs[q] - xi, dy = ys[q] - yi, dz = zs[q] - zi;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    const unsigned cd = code[q];
+                    const int p = pj[q];
+                    if (p == c && (cd & 0xffffffu) == 0u) return false;   // the atom itself (zero image shift)
+                    if (d2 < fast_lo) return true;
+                    if (d2 > fast_hi) return false;
+                    const AtomRec aj = atoms[p];
+                    const int sx = (int)(signed char)(cd & 0xff), sy = (int)(signed char)((cd >> 8) & 0xff),
+                              sz = (int)(signed char)((cd >> 16) & 0xff);
+                    double sh0, sh1, sh2;
+                    shift_vec(g, sx, sy, sz, sh0, sh1, sh2);
+                    return pair_test(g, ai, aj, sx, sy, sz, sh0, sh1, sh2, rc2_lo, rc2_hi, false);
+                };
+                if (!FILL) {
+                    unsigned long long pc0 = 0ull, pc1 = 0ull;   // packed per-lane counters, 16 bits per species
+                    for (int b = 0; b < nb_tile; ++b) {
+                        const int q = b * 32 + lane;
+                        if (q < n && test(q)) {
+                            const int sp = (int)(code[q] >> 24);
                             if (mark) mark[pj[q]] = 1;   // atoms whose environment the owner needs (halo)
                             const unsigned long long one = 1ull << (16 * (sp & 3));
                             if (NS <= 4 || sp < 4) pc0 += one;
                             else pc1 += one;
-                        }
-                        if (slot < kMaskSlots) {
-                            const unsigned m_all = __ballot_sync(0xffffffffu, acc);
-                            if (lane == 0) masks[(size_t)wid * kMaskSlots + slot] = m_all;
-                        }
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            const unsigned m = __ballot_sync(0xffffffffu, acc && sp == s);
-                            if (acc && sp == s) {
-                                PairRec pr;
-                                pr.j = pj[q];
-                                pr.sb[0] = (signed char)(cd & 0xff);
-                                pr.sb[1] = (signed char)((cd >> 8) & 0xff);
-                                pr.sb[2] = (signed char)((cd >> 16) & 0xff);
-                                pr.sp = (unsigned char)sp;
-                                pairs[base[s] + count[s] + __popc(m & ((1u << lane) - 1u))] = pr;
-                            }
-                            count[s] += __popc(m);
+                            if (b < nb_masked) accw |= 1ull << (slot_base + b);
                         }
                     }
-                }
-                if (!FILL) {
+                    if (nb_masked > 0) *my_word = accw;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         pc0 += __shfl_xor_sync(0xffffffffu, pc0, o);
@@ -709,10 +680,81 @@ __global__ void __launch_bounds__(kBinThreads) neighbor_bin_kernel(int c_begin, 
                                 *dst = tile_no > 0 ? *dst + v : v;
                             }
                     }
-                } else if (!last_tile && lane == 0) {
+                } else {
+                    // pairs of one species are contiguous; inside a species: tile, then lane, then slot
+                    long long start[NS];
+                    {
+                        long long o = first_pair;
 #pragma unroll
-                    for (int s = 0; s < NS; ++s)
-                        if (s < S) nl_run[(long long)wid * S + s] = count[s];
+                        for (int s = 0; s < NS; ++s) {
+                            start[s] = o + ((tile_no > 0 && s < S) ? nl_run[(long long)wid * S + s] : 0);
+                            o += cnt_s[s];
+                        }
+                    }
+                    auto emit = [&](int q, unsigned long long& run0, unsigned long long& run1) {
+                        const unsigned cd = code[q];
+                        const int sp = (int)(cd >> 24);
+                        long long b = 0;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (sp == s) b = start[s];
+                        unsigned long long& run = (NS <= 4 || sp < 4) ? run0 : run1;
+                        const int r = (int)((run >> (16 * (sp & 3))) & 0xffffull);
+                        run += 1ull << (16 * (sp & 3));
+                        PairRec pr;
+                        pr.j = pj[q];
+                        pr.sb[0] = (signed char)(cd & 0xff);
+                        pr.sb[1] = (signed char)((cd >> 8) & 0xff);
+                        pr.sb[2] = (signed char)((cd >> 16) & 0xff);
+                        pr.sp = (unsigned char)sp;
+                        pairs[b + r] = pr;
+                    };
+                    // this lane's accepted candidates of the tile: stored bits, recomputed beyond the word's reach
+                    unsigned long long wt = nb_masked > 0 ? (accw >> slot_base) : 0ull;
+                    if (nb_masked < 64) wt &= (1ull << nb_masked) - 1ull;
+                    unsigned long long pc0 = 0ull, pc1 = 0ull;
+                    for (unsigned long long t = wt; t; t &= t - 1) {
+                        const int sp = (int)(code[(__ffsll((long long)t) - 1) * 32 + lane] >> 24);
+                        const unsigned long long one = 1ull << (16 * (sp & 3));
+                        if (NS <= 4 || sp < 4) pc0 += one;
+                        else pc1 += one;
+                    }
+                    for (int b = nb_masked; b < nb_tile; ++b) {   // rare: more than kMaskSlots batches
+                        const int q = b * 32 + lane;
+                        if (q < n && test(q)) {
+                            const int sp = (int)(code[q] >> 24);
+                            const unsigned long long one = 1ull << (16 * (sp & 3));
+                            if (NS <= 4 || sp < 4) pc0 += one;
+                            else pc1 += one;
+                        }
+                    }
+                    // exclusive prefix over lanes (16-bit fields cannot carry: totals < 65536)
+                    unsigned long long in0 = pc0, in1 = pc1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned long long u0 = __shfl_up_sync(0xffffffffu, in0, o);
+                        const unsigned long long u1 = NS > 4 ? __shfl_up_sync(0xffffffffu, in1, o) : 0ull;
+                        if (lane >= o) {
+                            in0 += u0;
+                            in1 += u1;
+                        }
+                    }
+                    unsigned long long run0 = in0 - pc0, run1 = in1 - pc1;
+                    const unsigned long long tot0 = __shfl_sync(0xffffffffu, in0, 31);
+                    const unsigned long long tot1 = NS > 4 ? __shfl_sync(0xffffffffu, in1, 31) : 0ull;
+                    for (unsigned long long t = wt; t; t &= t - 1) emit((__ffsll((long long)t) - 1) * 32 + lane, run0, run1);
+                    for (int b = nb_masked; b < nb_tile; ++b) {
+                        const int q = b * 32 + lane;
+                        if (q < n && test(q)) emit(q, run0, run1);
+                    }
+                    if (!last_tile && lane == 0) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (s < S) {
+                                const int prev = tile_no > 0 ? nl_run[(long long)wid * S + s] : 0;
+                                nl_run[(long long)wid * S + s] = prev + (int)(((s < 4 ? tot0 : tot1) >> (16 * (s & 3))) & 0xffffull);
+                            }
+                    }
                 }
             }
             slot_base += (n + 31) >> 5;

@@ -99,8 +99,17 @@ __device__ __forceinline__ double pspec_entry(const DescParams& dp, const double
 // ---------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------
-// Phase-B ownership: lane -> (n tile, lm tile) of TN x TL components; per neighbour it loads
-// TN radial values + TL harmonics from shared memory for TN*TL FMAs.
+// D(8x8) += A(8x4, row) . B(4x8, col) on the FP64 tensor cores.  Fragments: A[lane>>2][lane&3], B[lane&3][lane>>2],
+// D[lane>>2][2*(lane&3) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// Phase B (expansion coefficients c[s][n][lm] = sum_j f_n(j) Y_lm(j)): one small GEMM per neighbour species on the
+// FP64 tensor cores -- M = lm (8-row tiles), N = n (8-column tiles), K = neighbours of the species (4 per step),
+// fragments read from the chunk buffer.  (TN, TL only shape the chunk-buffer rows.)
 template <int LMAX, int TN, int TL, bool ENV>
 __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                            const int* __restrict__ row_of,
@@ -115,9 +124,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
     double* c_s = smem + (size_t)warp * per_warp_doubles;
     double* buf = c_s + ((dp.csize + 1) & ~1);          // [32][stride]: f[0..nb) | pad | Y[0..L2) | pad
     int* sp_s = reinterpret_cast<int*>(buf + 32 * stride);
-    const int nLt = (dp.L2 + TL - 1) / TL;
-    const int lm0 = (lane % nLt) * TL, n0 = (lane / nLt) * TN;
-    const bool lane_on = n0 < dp.nb;
+    const int g8 = lane >> 2, t4 = lane & 3;   // DMMA fragment coordinates
     const int sp_stride = dp.nb * dp.L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
     const int L = dp.lmax + 1;
     const int npairs = dp.A * (dp.A + 1) / 2;
@@ -150,21 +157,24 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
         const bool flag = __any_sync(0xffffffffu, hit);
         __syncwarp();
         int cur_s = -1;
-        double acc[TN][TL];
+        constexpr int MT = ((LMAX + 1) * (LMAX + 1) + 7) / 8, NT = (kMaxNB + 7) / 8;
+        double acc[MT][NT][2];
 #pragma unroll
-        for (int a = 0; a < TN; ++a)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int b = 0; b < TL; ++b) acc[a][b] = 0.0;
+            for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         auto flush = [&](int sp) {
-            if (lane_on) {
 #pragma unroll
-                for (int a = 0; a < TN; ++a)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int b = 0; b < TL; ++b) {
-                        if (n0 + a < dp.nb && lm0 + b < dp.L2) c_s[sp * sp_stride + (n0 + a) * dp.L2p + lm0 + b] += acc[a][b];
-                        acc[a][b] = 0.0;
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int lm = mt * 8 + g8, n = nt * 8 + 2 * t4;
+                    if (lm < dp.L2) {
+                        if (n < dp.nb) c_s[sp * sp_stride + n * dp.L2p + lm] += acc[mt][nt][0];
+                        if (n + 1 < dp.nb) c_s[sp * sp_stride + (n + 1) * dp.L2p + lm] += acc[mt][nt][1];
                     }
-            }
+                    acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+                }
         };
         for (long long k0 = beg; k0 < end; k0 += 32) {
             const long long k = k0 + lane;
@@ -197,24 +207,33 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
             }
             __syncwarp();
             const int cnt = (int)min((long long)32, end - k0);
-            for (int jj = 0; jj < cnt; ++jj) {
-                const int s = sp_s[jj];
-                if (s != cur_s) {   // warp-uniform; rows are ordered by neighbour species
+            for (int j0 = 0; j0 < cnt;) {
+                // run of equal species starting at j0 (atoms: rows are ordered by species; inducing LCEs: any order)
+                const int s = sp_s[j0];
+                const unsigned diff = __ballot_sync(0xffffffffu, lane > j0 && lane < cnt && sp_s[lane] != s);
+                const int j1 = diff ? __ffs(diff) - 1 : cnt;
+                if (s != cur_s) {
                     if (cur_s >= 0) flush(cur_s);
                     cur_s = s;
                 }
-                if (lane_on) {
+                for (int kk = j0; kk < j1; kk += 4) {
+                    const int jj = kk + t4;
+                    const bool ok = jj < j1;
                     const double* row = buf + jj * stride;
-                    double fv[TN], yv[TL];
+                    double bv[NT];
 #pragma unroll
-                    for (int a = 0; a < TN; ++a) fv[a] = row[n0 + a];
+                    for (int nt = 0; nt < NT; ++nt) bv[nt] = (ok && nt * 8 + g8 < dp.nb) ? row[nt * 8 + g8] : 0.0;
 #pragma unroll
-                    for (int b = 0; b < TL; ++b) yv[b] = row[nbp + lm0 + b];
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (mt * 8 < dp.L2) {
+                            const double av = (ok && mt * 8 + g8 < dp.L2) ? row[nbp + mt * 8 + g8] : 0.0;
 #pragma unroll
-                    for (int a = 0; a < TN; ++a)
-#pragma unroll
-                        for (int b = 0; b < TL; ++b) acc[a][b] += fv[a] * yv[b];
+                            for (int nt = 0; nt < NT; ++nt)
+                                if (nt * 8 < dp.nb) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bv[nt]);
+                        }
+                    }
                 }
+                j0 = j1;
             }
             __syncwarp();
         }
@@ -346,18 +365,35 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
         __syncwarp();
         // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm],  tri(a,b) = rs(min) + |a-b|, rs(x) = x A - x(x-1)/2
-        for (int o = lane; o < dp.A * dp.L2; o += 32) {
-            const int a = o / dp.L2, lm = o - a * dp.L2;
-            const double* Tl = T_s + c_l_of_lm[lm];
-            const double* cl = c_s + lm;
-            double s = 0.0;
-            int rs = 0;
-            for (int b = 0; b < a; ++b) {          // pairs (b, a), b < a
-                s += Tl[(rs + a - b) * L] * cl[b * dp.L2p];
-                rs += dp.A - b;
+        // = per l one symmetric [A x A] . [A x (2l+1)] product on the FP64 tensor cores (M = a, N = m, K = b)
+        {
+            const int g8 = lane >> 2, t4 = lane & 3;
+            for (int l = 0; l < L; ++l) {
+                const int nm = 2 * l + 1, lm0 = l * l;
+                for (int nn0 = 0; nn0 < nm; nn0 += 8) {
+                    const bool nB_ok = nn0 + g8 < nm;
+                    const double* cl = c_s + lm0 + nn0 + g8;
+                    for (int m0 = 0; m0 < dp.A; m0 += 8) {
+                        const int a = m0 + g8;
+                        const bool a_ok = a < dp.A;
+                        double d0 = 0.0, d1 = 0.0;
+                        for (int kk = 0; kk < dp.A; kk += 4) {
+                            const int b = kk + t4;
+                            const bool b_ok = b < dp.A;
+                            const int lo = min(a, b), hi = max(a, b);
+                            const int tri = lo * dp.A - ((lo * (lo - 1)) >> 1) + (hi - lo);
+                            const double av = (a_ok && b_ok) ? T_s[tri * L + l] : 0.0;
+                            const double bv = (nB_ok && b_ok) ? cl[b * dp.L2p] : 0.0;
+                            dmma884(d0, d1, av, bv);
+                        }
+                        const int n = nn0 + 2 * t4;
+                        if (a_ok) {
+                            if (n < nm) D_s[a * dp.L2p + lm0 + n] = d0;
+                            if (n + 1 < nm) D_s[a * dp.L2p + lm0 + n + 1] = d1;
+                        }
+                    }
+                }
             }
-            for (int b = a; b < dp.A; ++b) s += Tl[(rs + b - a) * L] * cl[b * dp.L2p];   // pairs (a, b), rs == rs(a)
-            D_s[a * dp.L2p + lm] = s;
         }
         __syncwarp();
         double Fx = 0.0, Fy = 0.0, Fz = 0.0;

@@ -1,10 +1,12 @@
 // Developer tool (GPU box): correctness + speed of the tcgen05 int8-sliced GEMM vs float64.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I autoforce_b200/csrc tools/i8gemm_test.cu -o tools/i8gemm_test.bin
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I autoforce_b200/csrc -I tools tools/i8gemm_test.cu -o tools/i8gemm_test.bin -lcuda
+//   stages 63 / 62 select the experimental A-in-TMEM kernel (tools/i8gemm_ta_kernel.cuh)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "i8gemm_kernel.cuh"
+#include "i8gemm_ta_kernel.cuh"
 using namespace sgpr::i8g;
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -23,7 +25,7 @@ static int make_map(CUtensorMap* m, void* base, int ns, int rows, int Kpad, int 
     cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)ns};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_64B, getenv("PROMO") ? (CUtensorMapL2promotion)atoi(getenv("PROMO")) : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
     return (int)r;
 }
@@ -93,6 +95,14 @@ int main(int argc, char** argv) {
     Problem P;
     P.M = M; P.N = N; P.Kpad = Kpad;
     if (make_map(&P.mapA, dA, ns, M, Kpad, BM) || make_map(&P.mapB, dB, ns, N, Kpad, BN)) return 1;
+    ProblemTA PT;
+    PT.mapA = P.mapA; PT.mapB = P.mapB; PT.M = M; PT.N = N; PT.Kpad = Kpad;
+    PT.A = (const signed char*)dA;
+    PT.a_slice = (long long)M * Kpad;
+    PT.a_ld = Kpad;
+    ProblemTA* dPT;
+    cudaMalloc(&dPT, sizeof(ProblemTA));
+    cudaMemcpy(dPT, &PT, sizeof(ProblemTA), cudaMemcpyHostToDevice);
     Problem* dP;
     cudaMalloc(&dP, sizeof(Problem));
     cudaMemcpy(dP, &P, sizeof(Problem), cudaMemcpyHostToDevice);
@@ -102,8 +112,12 @@ int main(int argc, char** argv) {
     cm.tile_start[1] = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     StoreEpi epi{dC, N};
     void (*kern)(const Common, const Problem*, StoreEpi) = nullptr;
+    void (*kern_ta)(const Common, const ProblemTA*, StoreEpi) = nullptr;
     size_t smem = 0;
-    if (ns == 6 && tr == 8 && stages == 31) { kern = i8gemm_kernel<6, 8, 3, StoreEpi, 1>; smem = smem_bytes<6, 3>(); }
+    int nthreads = NTHREADS;
+    if (ns == 6 && tr == 7 && stages == 63) { kern_ta = i8gemm_ta_kernel<6, 7, 3, StoreEpi, 3>; smem = smem_bytes_ta<6, 3, 3>(); nthreads = NTHREADS_TA; }
+    else if (ns == 6 && tr == 7 && stages == 62) { kern_ta = i8gemm_ta_kernel<6, 7, 4, StoreEpi, 2>; smem = smem_bytes_ta<6, 4, 2>(); nthreads = NTHREADS_TA; }
+    else if (ns == 6 && tr == 8 && stages == 31) { kern = i8gemm_kernel<6, 8, 3, StoreEpi, 1>; smem = smem_bytes<6, 3>(); }
     else if (ns == 6 && tr == 8 && stages == 32) { kern = i8gemm_kernel<6, 8, 3, StoreEpi, 2>; smem = smem_bytes<6, 3>(); }
     else if (ns == 6 && tr == 8 && stages == 2) { kern = i8gemm_kernel<6, 8, 2, StoreEpi>; smem = smem_bytes<6, 2>(); }
     else if (ns == 6 && tr == 8) { kern = i8gemm_kernel<6, 8, 3, StoreEpi>; smem = smem_bytes<6, 3>(); }
@@ -112,10 +126,13 @@ int main(int argc, char** argv) {
     else if (ns == 5 && tr == 7) { kern = i8gemm_kernel<5, 7, 3, StoreEpi>; smem = smem_bytes<5, 3>(); }
     else if (ns == 5 && tr == 6) { kern = i8gemm_kernel<5, 6, 4, StoreEpi>; smem = smem_bytes<5, 4>(); }
     else { printf("unsupported scheme\n"); return 1; }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kern_ta ? cudaFuncSetAttribute(kern_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     printf("smem %zu bytes: %s\n", smem, cudaGetErrorString(e));
     int grid = std::min(prop.multiProcessorCount, cm.tile_start[1]);
-    kern<<<grid, NTHREADS, smem>>>(cm, dP, epi);
+    if (getenv("GRID")) grid = std::min(grid, atoi(getenv("GRID")));
+    if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
+    else kern<<<grid, nthreads, smem>>>(cm, dP, epi);
     e = cudaDeviceSynchronize();
     printf("kernel: %s\n", cudaGetErrorString(e));
     if (e != cudaSuccess) return 1;
@@ -137,7 +154,10 @@ int main(int argc, char** argv) {
     cudaEventCreate(&e1);
     cudaEventRecord(e0);
     const int reps = 5;
-    for (int r = 0; r < reps; ++r) kern<<<grid, NTHREADS, smem>>>(cm, dP, epi);
+    for (int r = 0; r < reps; ++r) {
+        if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
+        else kern<<<grid, nthreads, smem>>>(cm, dP, epi);
+    }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
     double* buf = c_s + ((dp.csize + 1) & ~1);          // [32][stride]: f[0..nb) | pad | Y[0..L2) | pad
     int* sp_s = reinterpret_cast<int*>(buf + 32 * stride);
     const int g8 = lane >> 2, t4 = lane & 3;   // DMMA fragment coordinates
+    const bool all_species = dp.A <= 8 * ((kMaxNB + 7) / 8);
     const int sp_stride = dp.nb * dp.L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
     const int L = dp.lmax + 1;
     const int npairs = dp.A * (dp.A + 1) / 2;
@@ -207,6 +208,32 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
             }
             __syncwarp();
             const int cnt = (int)min((long long)32, end - k0);
+            if (all_species) {
+                // S*nb <= 8*NT: ONE product for all neighbour species, columns (s, n); B[j][(s, n)] = [s == s_j] f_n(j)
+                for (int kk = 0; kk < cnt; kk += 4) {
+                    const int jj = kk + t4;
+                    const bool ok = jj < cnt;
+                    const double* row = buf + jj * stride;
+                    const int sj = ok ? sp_s[jj] : -1;
+                    double bv[NT];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const int col = nt * 8 + g8, cs = col / dp.nb;
+                        bv[nt] = (cs == sj) ? row[col - cs * dp.nb] : 0.0;
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (mt * 8 < dp.L2) {
+                            const double av = (ok && mt * 8 + g8 < dp.L2) ? row[nbp + mt * 8 + g8] : 0.0;
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+                                if (nt * 8 < dp.A) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bv[nt]);
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             for (int j0 = 0; j0 < cnt;) {
                 // run of equal species starting at j0 (atoms: rows are ordered by species; inducing LCEs: any order)
                 const int s = sp_s[j0];
@@ -237,7 +264,20 @@ __global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g
             }
             __syncwarp();
         }
-        if (cur_s >= 0) flush(cur_s);
+        if (all_species) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int lm = mt * 8 + g8, col = nt * 8 + 2 * t4;   // column (s, n) = row s*nb + n of c
+                    if (lm < dp.L2) {
+                        if (col < dp.A) c_s[col * dp.L2p + lm] = acc[mt][nt][0];
+                        if (col + 1 < dp.A) c_s[(col + 1) * dp.L2p + lm] = acc[mt][nt][1];
+                    }
+                }
+        } else if (cur_s >= 0) {
+            flush(cur_s);
+        }
         __syncwarp();
         // power spectrum: lanes over pairs (a <= b), all l of a pair from one pass over c_a, c_b;
         // norm over ALL blocks (sesoap.py:249-251); packed row out

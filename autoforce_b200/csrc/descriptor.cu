@@ -386,7 +386,24 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
 #pragma unroll
     for (int q = 0; q < 9; ++q) Wacc[q] = 0.0;
 
-    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
+    // row of the environment after next (one iteration of lead time so that the prefetch below never waits on it)
+    const int env_stride = gridDim.x * nwarps;
+    auto row_of_env = [&](int e) -> int { return e < n_env ? row_of[src.active ? src.active[e] : e] : -1; };
+    int r_ahead = row_of_env(blockIdx.x * nwarps + warp + env_stride);
+    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += env_stride) {
+        // pull the next environment's inputs (dE/dq_hat row, q_hat row, expansion coefficients) towards the SM
+        // while this one is processed: the prologue below is otherwise a pure DRAM-latency stall
+        if (r_ahead >= 0) {
+            const char* p0 = reinterpret_cast<const char*>(tvec + (size_t)r_ahead * dp.ldp);
+            const char* p1 = reinterpret_cast<const char*>(phat + (size_t)r_ahead * dp.ldp);
+            const char* p2 = reinterpret_cast<const char*>(cbuf + (size_t)(env + env_stride) * dp.csize);
+            for (int o = lane * 128; o < dp.D * 8; o += 32 * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
+            }
+            for (int o = lane * 128; o < dp.csize * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + o));
+        }
+        r_ahead = row_of_env(env + 2 * env_stride);
         const int c = src.active ? src.active[env] : env;
         const AtomRec ai = src.atoms[c];
         const int si = meta_species(ai.meta);

@@ -14,7 +14,8 @@
 // Kernel structure (one CTA per SM, persistent over tiles): warp 0 = TMA producer (one 3-D bulk
 // tensor copy per operand per stage brings all NS slices of a 128 x 64 B / 64 x 64 B K-chunk,
 // SWIZZLE_64B), warp 1 = single-thread tcgen05.mma issuer (2 k-steps x pairs per stage, accumulators
-// in TMEM: (TR-1) x 64 columns), warps 2-5 = epilogue (tcgen05.ld -> float64 -> fused epilogue).
+// in TMEM: (TR-1) x 64 columns), warps 2-9 = epilogue (tcgen05.ld -> float64 -> fused epilogue; each warp
+// owns 32 TMEM lanes x 32 columns).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -25,7 +26,7 @@ namespace i8g {
 
 constexpr int BM = 128, BN = 64, BKB = 64;     // tile; BKB = K bytes (= int8 elements) per stage
 constexpr int MAXS = 7;                        // max slices
-constexpr int NTHREADS = 192;                  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int NTHREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);               // one arrive per epilogue warp
+        mbar_init(tmem_empty, 8);               // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -315,9 +316,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5 own TMEM lanes 32*(warp%4)..+31) =====================
-        const int q = warp & 3;
+        // ===================== epilogue: warps 2..9; TMEM lanes 32*(warp%4)..+31, column half (warp-2)/4 ==========
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int row_in_tile = q * 32 + lane;
+        constexpr int HC = BN / 2;                     // columns per epilogue warp
         uint32_t tphase = 0;
         for (int gt = blockIdx.x; gt < n_tiles; gt += gridDim.x) {
             int pi = 0;
@@ -329,13 +331,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
             mbar_wait(tmem_full, tphase);
             tc_fence_after();
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * HC;
             // drain the accumulators into float64 registers, hand TMEM back to the MMA warp, and only
             // then run the (expensive) fused epilogue: it overlaps with the next tile's main loop
-            double v[BN];
+            double v[HC];
             if (DEBUG_SKIP != 2) {
 #pragma unroll
-                for (int cc = 0; cc < BN; cc += 8) combine8<SC::NG>(lane_addr + cc, v + cc);
+                for (int cc = 0; cc < HC; cc += 8) combine8<SC::NG>(lane_addr + cc, v + cc);
             }
             tc_fence_before();
             __syncwarp();
@@ -343,11 +345,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             tphase ^= 1;
             if (DEBUG_SKIP == 0) {
 #pragma unroll
-                for (int cc = 0; cc < BN; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + cc, v + cc, P.M, P.N);
+                for (int cc = 0; cc < HC; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, P.M, P.N);
             } else if (DEBUG_SKIP == 1) {
                 double s = 0;
-                for (int j = 0; j < BN; ++j) s += v[j];
-                if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN, v, P.M, P.N);
+                for (int j = 0; j < HC; ++j) s += v[j];
+                if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC, v, P.M, P.N);
             }
         }
     }

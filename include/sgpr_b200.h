@@ -118,7 +118,7 @@ int sgpr_append_inducing(sgpr_handle h, int32_t n_new, const int32_t* ind_Z_h, c
  *   rank, world    atom sharding: this call evaluates the local energies of its share
  *                  of the atoms (contiguous range in the internal cell order) and the
  *                  forces on exactly those atoms; (0,1) = everything.
- *   E_d    [1]     sum of owned local energies + (rank 0 only) the mean
+ *   E_d    [1]     sum of the owned atoms' local energies + the mean terms of the owned atoms
  *   F_d    [N,3]   forces on owned atoms, 0 elsewhere
  *   W_d    [9]     un-normalised pair virial sum_i r_ij (x) dE_i/dr_ij of owned
  *                  environments, index [a*3+b] = r_a g_b; stress = (W/V).flat[[0,4,8,5,2,1]]

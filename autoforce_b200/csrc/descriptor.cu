@@ -111,7 +111,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // FP64 tensor cores -- M = lm (8-row tiles), N = n (8-column tiles), K = neighbours of the species (4 per step),
 // fragments read from the chunk buffer.  (TN, TL only shape the chunk-buffer rows.)
 template <int LMAX, int TN, int TL, bool ENV>
-__global__ void __launch_bounds__(256) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
+__global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                            const int* __restrict__ row_of,
                                                            const unsigned* __restrict__ ptab,
                                                            const double* __restrict__ nnlk, double* __restrict__ phat,
@@ -593,7 +593,7 @@ struct Launch {
 Launch plan_forward(const DescParams& dp, int stride) {
     // c block + 32 neighbour rows + 32 species ints
     int per_warp = ((dp.csize + 1) & ~1) + 32 * stride + 16;
-    int warps = 8;
+    int warps = 4;
     while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
     return {warps, (size_t)warps * per_warp * 8, per_warp};
 }

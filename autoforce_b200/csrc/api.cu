@@ -252,7 +252,7 @@ __global__ void orig_to_row_kernel(int64_t N, const AtomRec* __restrict__ atoms,
 
 __global__ void lone_k_kernel(int n_active, const int* __restrict__ active, const AtomRec* __restrict__ atoms,
                               const long long* __restrict__ nl_first, int M, const int* __restrict__ ind_sp,
-                              const unsigned char* __restrict__ ind_lone, double* __restrict__ K) {
+                              const unsigned char* __restrict__ ind_lone, double* __restrict__ K, double lone_w) {
     // K[i,m] += 1 when both LCEs have no neighbours and the same species (similarity.py:94-103)
     for (int env = blockIdx.x; env < n_active; env += gridDim.x) {
         if (nl_first[env + 1] != nl_first[env]) continue;
@@ -260,7 +260,7 @@ __global__ void lone_k_kernel(int n_active, const int* __restrict__ active, cons
         const int sp = meta_species(atoms[c].meta);
         const int i = meta_orig(atoms[c].meta);
         for (int m = threadIdx.x; m < M; m += blockDim.x)
-            if (ind_lone[m] && ind_sp[m] == sp) K[(size_t)i * M + m] += 1.0;
+            if (ind_lone[m] && ind_sp[m] == sp) K[(size_t)i * M + m] += lone_w;
     }
 }
 
@@ -328,7 +328,7 @@ static int upload_weights(sgpr_context* h, const double* mu_h, const double* mea
         SGPR_TRY(upload(h->mu, mus.data(), sizeof(double) * M));
         std::vector<double> lone(SGPR_MAX_SPECIES, 0.0);
         for (int p = 0; p < M; ++p)
-            if (h->ind_lone[p]) lone[h->ind_sp[p]] += mus[p];
+            if (h->ind_lone[p]) lone[h->ind_sp[p]] += h->lone_w * mus[p];
         SGPR_TRY(upload(h->lone_mu, lone.data(), sizeof(double) * SGPR_MAX_SPECIES));
     }
     if (mean_w_h) {
@@ -355,7 +355,8 @@ static int upload_weights(sgpr_context* h, const double* mu_h, const double* mea
                     c[((size_t)s * M + k) * h->ld_zt + (p - m0)] = v;
                     if (h->ind_lone[p]) lone_sum += v;
                 }
-                clone[s] += lone_sum * lone_sum;  // c of a neighbour-less atom (K row = lone indicator)
+                // c / alpha of a neighbour-less atom: K row = lone_w x lone indicator, self kernel alpha = lone_w
+                clone[s] += h->lone_w * lone_sum * lone_sum;
             }
         }
         SGPR_TRY(upload(h->choli_t, c.data(), sizeof(double) * c.size()));
@@ -556,6 +557,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         dp.nbr_enabled[s] = d->neighbor_enabled[s] ? 1 : 0;
     }
     h->xi = d->xi;
+    h->lone_w = d->lone_weight > 0 ? d->lone_weight : 1.0;
     h->xi_int = (d->xi == std::floor(d->xi) && d->xi >= 1 && d->xi <= 64) ? (int)d->xi : -1;
     SGPR_TRY(upload(h->ztab, h->z_to_species, sizeof(int) * 128));
     SGPR_TRY(h->errflag.ensure(sizeof(int) * 4));
@@ -989,7 +991,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_forward(sgpr_h
         if (any) {
             lone_k_kernel<<<h->sm_count, 128, 0, st>>>((int)h->n_active, nullptr, h->atoms.as<AtomRec>(),
                                                        h->nl_first.as<long long>(), h->M, h->ind_sp_d.as<int>(),
-                                                       h->ind_lone_d.as<unsigned char>(), K_d);
+                                                       h->ind_lone_d.as<unsigned char>(), K_d, h->lone_w);
         }
         h->stats.kernel_launches += 2;
     }

@@ -117,6 +117,7 @@ struct sgpr_context {
     std::vector<int> ind_sp;                 // species of sorted inducing p
     std::vector<unsigned char> ind_lone;     // sorted inducing p has no neighbours
     std::vector<double> mean_w, vscale, mu_host;
+    double lone_w = 1.0;        // weight of the lone-lone kernel term (number of similarity kernels)
     bool has_choli = false;
     std::vector<int32_t> ind_Z_host, ind_b_host;   // inducing environments as given (for sgpr_append_inducing)
     std::vector<int64_t> ind_first_host;

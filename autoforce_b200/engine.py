@@ -26,7 +26,7 @@ class sgpr_model_desc(ctypes.Structure):
         ("n_species", c_int32), ("species_Z", c_int32 * MAX_SPECIES), ("radii", c_double * MAX_SPECIES),
         ("central_enabled", c_int32 * MAX_SPECIES), ("neighbor_enabled", c_int32 * MAX_SPECIES), ("M", c_int32), ("ind_first_h", c_void_p), ("ind_r_h", c_void_p),
         ("ind_b_h", c_void_p), ("ind_Z_h", c_void_p), ("mu_h", c_void_p), ("mean_w_h", c_void_p),
-        ("choli_h", c_void_p), ("vscale_h", c_void_p), ("device", c_int32),
+        ("choli_h", c_void_p), ("vscale_h", c_void_p), ("device", c_int32), ("lone_weight", c_double),
     ]
 
 
@@ -215,6 +215,7 @@ class SgprEngine:
             d.neighbor_enabled[s] = 1 if model.is_neighbour(z) else 0
             mean_w[s] = model.mean_w.get(z, 0.0)
             vscale[s] = model.vscale.get(z, np.inf)
+        d.lone_weight = float(getattr(model, "lone_weight", 1.0))
         d.M = model.M
         self._keep = (model.ind_first, model.ind_r, model.ind_b, model.ind_Z, model.mu, mean_w, vscale, model.choli)
         d.ind_first_h, d.ind_r_h, d.ind_b_h = _ptr(model.ind_first), _ptr(model.ind_r), _ptr(model.ind_b)

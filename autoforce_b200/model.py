@@ -37,6 +37,7 @@ class SgprModel:
     mu: np.ndarray = None             # [M]
     mean_w: dict = field(default_factory=dict)   # Z -> weights[Z] + _weights[Z]
     choli: np.ndarray = None          # [M,M] or None
+    lone_weight: float = 1.0          # kernels in the list (each adds the lone-lone term, similarity.py:41-43,94-103)
     vscale: dict = field(default_factory=dict)   # Z -> _vscale[Z]
 
     # ------------------------------------------------------------------ basics
@@ -112,6 +113,7 @@ class SgprModel:
                 raise NotImplementedError("SubSeSoapKernels with different hyper-parameters need one engine each")
             a_only = tuple(int(k.a) for k in kerns)
             b_only = tuple(int(z) for z in k0.b)
+        lone_weight = float(len(kerns))
         k = kerns[0]
         cname = type(k).__name__
         desc = k.descriptor
@@ -149,13 +151,14 @@ class SgprModel:
             normalize=bool(desc.normalize), radii=radii, default_radius=default, a_not=a_not, a_only=a_only, b_only=b_only,
             mu=np.asarray(model.mu.detach().cpu().numpy(), dtype=float), mean_w=mean_w,
             choli=None if choli is None else np.asarray(choli.detach().cpu().numpy(), dtype=float), vscale=vscale,
+            lone_weight=lone_weight,
         )
 
     # ------------------------------------------------------------------ flat file format
     def save(self, path):
         meta = dict(format="autoforce_b200.sgpr_model", version=1, lmax=self.lmax, nmax=self.nmax, xi=self.xi, rc=self.rc,
                     kind=self.kind, normalize=self.normalize, radii={str(k): v for k, v in self.radii.items()},
-                    default_radius=self.default_radius, a_not=list(self.a_not), a_only=list(self.a_only), b_only=list(self.b_only),
+                    default_radius=self.default_radius, a_not=list(self.a_not), a_only=list(self.a_only), b_only=list(self.b_only), lone_weight=self.lone_weight,
                     mean_w={str(k): v for k, v in self.mean_w.items()}, vscale={str(k): v for k, v in self.vscale.items()})
         arrays = dict(ind_Z=self.ind_Z, ind_first=self.ind_first, ind_r=self.ind_r, ind_b=self.ind_b, mu=self.mu)
         if self.choli is not None:
@@ -173,7 +176,7 @@ class SgprModel:
                    a_not=tuple(meta["a_not"]), a_only=tuple(meta.get("a_only", ())), b_only=tuple(meta.get("b_only", ())),
                    ind_Z=z["ind_Z"], ind_first=z["ind_first"], ind_r=z["ind_r"],
                    ind_b=z["ind_b"], mu=z["mu"], mean_w=meta["mean_w"], choli=z["choli"] if "choli" in z.files else None,
-                   vscale=meta["vscale"])
+                   vscale=meta["vscale"], lone_weight=float(meta.get("lone_weight", 1.0)))
 
 
 def _subse_exponent(k):

@@ -79,6 +79,10 @@ typedef struct {
     const double*  vscale_h;      /* [n_species] model._vscale[Z] (inf where unseen,
                                      calculator/active.py:797-803), or NULL            */
     int32_t device;               /* CUDA device ordinal                              */
+    double  lone_weight;          /* number of similarity kernels in model.gp.kern.kernels: each adds the
+                                     lone-atoms term (similarity/similarity.py:41-43,94-103), so two
+                                     neighbour-less LCEs of one species have k = lone_weight (1 for a single
+                                     kernel, n for default_kernel(species=[...n...])); 0 is read as 1      */
 } sgpr_model_desc;
 
 /* ---- life cycle ------------------------------------------------------------------ */

@@ -60,6 +60,7 @@ class OracleModel:
     a_only: tuple = ()  # if non-empty: the central species of the SubSeSoapKernels (similarity/sesoap.py:27-43)
     b_only: tuple = ()  # if non-empty: neighbour species that enter the descriptor (SubSeSoap `numbers`)
     default_radius: float = 1.0
+    lone_weight: float = 1.0  # kernels in the list: each adds the lone-lone term (similarity/similarity.py:41-43,94-103)
 
     @property
     def M(self):
@@ -490,14 +491,14 @@ def _powxi(k, xi):
 
 
 def kernel_from_descriptors(model, P, Zc, lone_c, Zh, lone_m):
-    """K[i,m] = delta(Z_i,Z_m) (p_i . z_m)^xi + [both lone, same Z]."""
+    """K[i,m] = delta(Z_i,Z_m) (p_i . z_m)^xi + lone_weight [both lone, same Z]."""
     B, M = len(P), len(Zh)
     dot = P.reshape(B, -1) @ Zh.reshape(M, -1).T
     same = Zc[:, None] == np.asarray(model.ind_Z)[None, :]
     ok_c = ~model.excluded_centres(Zc) & ~lone_c
     ok_m = ~model.excluded_centres(model.ind_Z) & ~lone_m
     K = np.where(same & ok_c[:, None] & ok_m[None, :], _powxi(dot, model.xi), 0.0)
-    K = K + (same & lone_c[:, None] & lone_m[None, :])
+    K = K + model.lone_weight * (same & lone_c[:, None] & lone_m[None, :])
     return K, dot, same & ok_c[:, None] & ok_m[None, :]
 
 
@@ -542,7 +543,7 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
         e_local[k0 : k0 + len(idx)] = K @ mu
         # self kernel k(x,x) (active.py:785-788): 1 for a normalised descriptor, 0 for an
         # excluded centre, 1 for a neighbour-less atom (similarity.py:94-103)
-        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, 1.0, np.where(model.excluded_centres(numbers[idx]), 0.0, 1.0))
+        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, model.lone_weight, np.where(model.excluded_centres(numbers[idx]), 0.0, 1.0))
         if Kout is not None:
             Kout[k0 : k0 + len(idx)] = K
         xi = model.xi

@@ -135,6 +135,19 @@ def case_inputs(name):
         sp, sc, sn = fcc(3, [3, 8, 16], 0.15, 117, a0=3.9)
         envs = [e for e in pick_inducing(sp, sc, True, sn, 5.0, 15, 18) if e[0] in (3, 8)]
         pbc = [True] * 3
+    elif name == "subse_lone":
+        # SubSeSoapKernel list + neighbour-less atoms: every kernel of the list adds the lone-lone term
+        # (similarity.py:41-43,94-103), so k(lone, lone) = number of kernels
+        kern = dict(kind="subsesoap", lmax=2, nmax=2, xi=4, rc=4.0, species=[3, 8])
+        pos, cell, num = fcc((2, 2, 2), [3, 8], 0.1, 19, a0=3.9)
+        cell = cell + np.diag([30.0, 0.0, 0.0])
+        pos = np.vstack([pos, [[20.0, 1.0, 1.0]], [[30.0, 5.0, 2.0]]])
+        num = np.concatenate([num, [3, 8]])
+        sp, sc, sn = fcc(2, [3, 8], 0.15, 119, a0=3.9)
+        envs = [e for e in pick_inducing(sp, sc, True, sn, 4.0, 10, 20)]
+        envs.append((3, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
+        envs.append((8, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
+        pbc = [True] * 3
     else:
         raise KeyError(name)
     M = len(envs)
@@ -149,7 +162,7 @@ def case_inputs(name):
 
 CASES = [
     "cu108_sesoap", "cu108_perfect", "lipso108", "tric_oh", "universal_2sp", "cluster_lone", "slab_ttf", "highres_l6n8", "anot_xi2",
-    "subse_3sp",
+    "subse_3sp", "subse_lone",
 ]
 
 
@@ -198,6 +211,7 @@ def run_case(name):
                 vscale={str(z): v for z, v in c["vscale"].items()}, species=[int(z) for z in species],
                 unit=(float(kern.descriptor.unit) if k["kind"] == "universal" else None),
                 a_only=(k["species"] if k["kind"] == "subsesoap" else []), b_only=(k["species"] if k["kind"] == "subsesoap" else []),
+                lone_weight=(len(k["species"]) if k["kind"] == "subsesoap" else 1),
                 generator="tests/golden/make_golden.py", reference="theforce v2021.09", ref_seconds=round(dt, 2))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),

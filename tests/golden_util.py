@@ -53,6 +53,7 @@ def oracle_model(g, big=False):
         mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()}, choli=g["choli"],
         vscale={int(z): v for z, v in g["meta"]["vscale"].items()}, a_not=tuple(k.get("a_not", ())),
         a_only=tuple(g["meta"].get("a_only", ())), b_only=tuple(g["meta"].get("b_only", ())),
+        lone_weight=float(g["meta"].get("lone_weight", 1)),
     )
 
 
@@ -67,4 +68,5 @@ def b200_model(g, big=False):
         radii=radii, default_radius=default, a_not=tuple(k.get("a_not", ())), a_only=tuple(g["meta"].get("a_only", ())),
         b_only=tuple(g["meta"].get("b_only", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
         mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
-        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()})
+        choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()},
+        lone_weight=float(g["meta"].get("lone_weight", 1)))

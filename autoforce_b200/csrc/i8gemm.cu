@@ -309,6 +309,31 @@ int i8_prepare_covloss(sgpr_context* h) {
         SGPR_CUDA(cudaGetLastError());
     }
     SGPR_CUDA(cudaDeviceSynchronize());
+    // K extent per (species, 64-column tile): choli = L^-1 is lower triangular (regression/gppotential.py:588), so
+    // for output columns k only inducing LCEs m <= k contribute; chunks beyond the last non-zero are never loaded
+    {
+        const int ntn = (M + BN - 1) / BN;
+        std::vector<double> host((size_t)S * M * h->ld_zt);
+        SGPR_CUDA(cudaMemcpy(host.data(), h->choli_t.p, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
+        std::vector<int> nk((size_t)S * ntn, 0);
+        for (int s = 0; s < S; ++s) {
+            const int Ms = h->m_first[s + 1] - h->m_first[s];
+            for (int tn = 0; tn < ntn; ++tn) {
+                int ext = 0;
+                for (int k = tn * BN; k < std::min(M, (tn + 1) * BN); ++k) {
+                    const double* row = host.data() + ((size_t)s * M + k) * h->ld_zt;
+                    for (int p = Ms - 1; p >= ext; --p)
+                        if (row[p] != 0.0) {
+                            ext = p + 1;
+                            break;
+                        }
+                }
+                nk[(size_t)s * ntn + tn] = (ext + BKB - 1) / BKB;   // 0: the tile is identically zero
+            }
+        }
+        SGPR_TRY(h->cov_nk.ensure(sizeof(int) * nk.size()));
+        SGPR_CUDA(cudaMemcpy(h->cov_nk.p, nk.data(), sizeof(int) * nk.size(), cudaMemcpyHostToDevice));
+    }
     return SGPR_OK;
 }
 
@@ -336,6 +361,7 @@ static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Pr
         const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
         if (r1 == r0 || m1 == m0 || !dp.central_enabled[s]) continue;
         Problem P;
+        P.nk_tn = nullptr;
         if (which == 1) {
             P.M = r1 - r0;
             P.N = m1 - m0;
@@ -354,12 +380,15 @@ static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Pr
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
             SGPR_TRY(make_map(&P.mapA, h->k8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
             SGPR_TRY(make_map(&P.mapB, h->c8.as<signed char>() + (size_t)s * kNS * h->M * h->i8_mp, kNS, h->M, h->i8_mp, (long long)h->M, BN));
+            const int ntn = (h->M + BN - 1) / BN;
+            if (h->cov_nk.p) P.nk_tn = h->cov_nk.as<int>() + (size_t)s * ntn;
         }
         prob_species[cm.n_prob] = s;
         cm.tile_start[cm.n_prob + 1] = cm.tile_start[cm.n_prob] + ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN);
         cm.n_prob++;
         probs.push_back(P);
         if (which == 3) {
+            // algorithmic flops of the dense product; the zero part of a triangular choli is skipped, not counted less
             h->stats.covloss_flops += 2.0 * P.M * (double)P.N * (m1 - m0);
         } else {
             const int npairs = h->i8_tr == 8 ? 26 : 21;

@@ -134,6 +134,9 @@ struct Problem {
     CUtensorMap mapA;    // int8 [NS][rowsA][Kpad], box {64, 128, NS}
     CUtensorMap mapB;    // int8 [NS][rowsB][Kpad], box {64,  64, NS}
     int M, N, Kpad;      // Kpad multiple of 64 (zero padded)
+    const int* nk_tn;    // optional [ceil(N/64)]: K chunks (of 64) that can be non-zero for column tile tn; nullptr =
+                         // Kpad / 64 for every tile.  Lets a triangular B (choli) skip its zero part; 0 = the tile
+                         // is identically zero: no loads, no MMAs, the epilogue runs on zeros.
 };
 
 struct Common {
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             const int tile = gt - cm.tile_start[pi];
             const int tiles_n = (P.N + BN - 1) / BN;
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-            const int nk = P.Kpad / BKB;
+            const int nk = P.nk_tn ? P.nk_tn[tn] : P.Kpad / BKB;
             for (int kt = 0; kt < nk; ++kt) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -276,7 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
                 int pi = 0;
                 for (int q = 1; q < cm.n_prob; ++q)
                     if (gt >= cm.tile_start[q]) pi = q;
-                const int nk = probs[pi].Kpad / BKB;
+                const Problem& P = probs[pi];
+                const int nk = P.nk_tn ? P.nk_tn[(gt - cm.tile_start[pi]) % ((P.N + BN - 1) / BN)] : P.Kpad / BKB;
+                if (nk == 0) continue;                  // identically zero tile: nothing to accumulate
                 mbar_wait(tmem_empty, tphase ^ 1);      // epilogue has drained the accumulators
                 tc_fence_after();
                 for (int kt = 0; kt < nk; ++kt) {
@@ -329,12 +334,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             const int tile = gt - cm.tile_start[pi];
             const int tiles_n = (P.N + BN - 1) / BN;
             const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+            double v[HC];
+            if (P.nk_tn && P.nk_tn[tn] == 0) {         // identically zero tile (see Problem::nk_tn)
+#pragma unroll
+                for (int j = 0; j < HC; ++j) v[j] = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < HC; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, P.M, P.N);
+                continue;
+            }
             mbar_wait(tmem_full, tphase);
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * HC;
             // drain the accumulators into float64 registers, hand TMEM back to the MMA warp, and only
             // then run the (expensive) fused epilogue: it overlaps with the next tile's main loop
-            double v[HC];
             if (DEBUG_SKIP != 2) {
 #pragma unroll
                 for (int cc = 0; cc < HC; cc += 8) combine8<SC::NG>(lane_addr + cc, v + cc);

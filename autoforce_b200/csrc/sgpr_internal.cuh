@@ -145,6 +145,7 @@ struct sgpr_context {
     double i8_mumax = 1.0;      // power of two >= max xi |mu|
     sgpr::DevBuf z8, zt8;       // static digit slices: z_hat [6][M][kp1], (xi mu z_hat^T / mumax) [S][6][D][mp]
     sgpr::DevBuf p8, g8;        // per-step digit slices: q_hat [6][cap][kp1], k^(xi-1) [6][cap][mp]
+    sgpr::DevBuf cov_nk;        // [S][ceil(M/64)] non-zero K chunks of choli per column tile (triangular skip)
     sgpr::DevBuf k8, c8, crs;   // covloss: k^xi digits [6][cap][mp], choli digits [S][6][M][mp], choli row scales [S][M]
     sgpr::DevBuf i8_probs;      // device copies of the tensor-map problem descriptors
     void* i8_probs_pinned = nullptr;

@@ -37,7 +37,8 @@ def cut_environments(pos, cell, pbc, numbers, rc, indices, first, J, S):
 def synth_model(Zs, M, seed, lmax=3, nmax=3, xi=4, rc=6.0, kind="sesoap", src_rep=5, mu_scale=0.1, with_choli=False,
                 neighbors_fn=None):
     """Frozen model: M inducing LCEs drawn per-species-balanced from fcc(src_rep, Zs, 0.15, seed+100),
-    mu ~ N(0,1)*mu_scale, mean weight -3.0 per species, choli = 0.5 I, vscale = 1.
+    mu ~ N(0,1)*mu_scale, mean weight -3.0 per species, vscale = 1, choli = 0.5 I (with_choli=True) or a
+    dense lower-triangular matrix (with_choli="tril").
     ``neighbors_fn(pos, cell, pbc, rc) -> (first, j, S)`` overrides the GPU neighbour hook
     (the CPU arm of bench.py passes the oracle's, so that it needs no GPU)."""
     rng = np.random.default_rng(seed)
@@ -63,8 +64,13 @@ def synth_model(Zs, M, seed, lmax=3, nmax=3, xi=4, rc=6.0, kind="sesoap", src_re
     envs = cut_environments(pos, cell, True, numbers, rc, sel, first, J, S)
     Mtot = len(envs)
     mu = rng.normal(0, 1, Mtot) * mu_scale
-    return SgprModel.from_envs(envs, mu=mu, mean_w={z: -3.0 for z in Zs}, vscale={z: 1.0 for z in Zs},
-                               choli=(0.5 * np.eye(Mtot)) if with_choli else None, **base)
+    choli = None
+    if with_choli == "tril":
+        # dense lower-triangular like the reference's choli = L^-1 (regression/gppotential.py:588)
+        choli = 0.5 * np.eye(Mtot) + np.tril(np.random.default_rng(seed + 7).normal(0, 0.02 / np.sqrt(Mtot), (Mtot, Mtot)), -1)
+    elif with_choli:
+        choli = 0.5 * np.eye(Mtot)
+    return SgprModel.from_envs(envs, mu=mu, mean_w={z: -3.0 for z in Zs}, vscale={z: 1.0 for z in Zs}, choli=choli, **base)
 
 
 WORKLOADS = {

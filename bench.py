@@ -347,7 +347,7 @@ def main():
             # covloss (calculator/active.py:781-804) runs every prediction step in the reference but is not part
             # of the metric: reported separately, same structure, model with choli = 0.5 I
             try:
-                model_c = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli=True)
+                model_c = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli="tril")
                 eng_c = ab.SgprEngine(model_c, species=w["Zs"], device=local_rank)
                 eng_c.enable_timing(True)
                 tb, fl = [], 0.0
@@ -360,7 +360,7 @@ def main():
                 eng_c.close()
                 mb = sum(tb) / len(tb)
                 line["covloss"] = {"ms_per_step": mb, "tflops": fl / (mb * 1e-3) / 1e12, "flops_per_step": fl,
-                                   "note": "extra device time per step when beta is requested; tcgen05 int8 digit-slice GEMM K.choli^T (26 slice products) + row sum of squares"}
+                                   "note": "extra device time per step when beta is requested; tcgen05 int8 digit-slice GEMM K.choli^T (26 slice products; dense lower-triangular synthetic choli like the reference's L^-1, whose zero K-chunks are skipped; flops counted for the dense product) + row sum of squares"}
             except Exception as ex:  # pragma: no cover
                 line["covloss"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:

@@ -107,7 +107,7 @@ def speed(workload="c2", steps=5):
               f"nl={s['ms_nl']:.3f} desc={s['ms_desc']:.3f} gemm={s['ms_gemm']:.3f} force={s['ms_force']:.3f} total={s['ms_total']:.3f} ms "
               f"gemm TF/s={s['gemm_flops'] / max(s['ms_gemm'], 1e-9) / 1e9:.2f}", flush=True)
     if os.environ.get("BETA"):
-        model2 = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli=True)
+        model2 = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], with_choli=os.environ.get("CHOLI", "tril") if os.environ.get("CHOLI", "tril") != "eye" else True)
         eng2 = ab.SgprEngine(model2, species=w["Zs"])
         eng2.enable_timing(True)
         for it in range(3):

@@ -43,7 +43,8 @@ def _as_model(covariance):
 class B200Calculator(_AseCalculator):
     implemented_properties = ["energy", "forces", "stress", "free_energy"]
 
-    def __init__(self, covariance, calculator=None, process_group=None, device=None, gather_forces=True, logfile=None, **kw):
+    def __init__(self, covariance, calculator=None, process_group=None, device=None, gather_forces=True, logfile=None,
+                 covloss=False, ediff=0.04, on_uncertain=None, **kw):
         if _AseCalculator is not object:
             super().__init__()
         if calculator is not None:
@@ -51,6 +52,16 @@ class B200Calculator(_AseCalculator):
                 "on-the-fly training stays on the reference path: use theforce's ActiveCalculator with the "
                 "GPU kernel plugged in (INTEGRATION.md); B200Calculator is the prediction-mode drop-in")
         self.model = _as_model(covariance)
+        # prediction-mode uncertainty (calculator/active.py:492-499): covloss=True evaluates beta = get_covloss() every
+        # step on the device, records its maximum in ``covlog`` and hands structures with max(beta) > ediff to
+        # ``on_uncertain(atoms, beta)`` (the reference appends them to active_uncertain.traj)
+        self.covloss = bool(covloss)
+        if self.covloss and self.model.choli is None:
+            raise ValueError("covloss=True needs a model with choli")
+        self.ediff = float(ediff)
+        self.on_uncertain = on_uncertain
+        self.covlog = ""
+        self.beta = None
         self.process_group = process_group
         self.gather_forces = gather_forces
         self.results = {}
@@ -100,6 +111,33 @@ class B200Calculator(_AseCalculator):
             F = ft.cpu().numpy()
         return E, W, F
 
+    def _gather_beta(self, dist, beta, device_index):
+        import torch
+
+        backend = dist.get_backend(self.process_group)
+        dev = torch.device("cuda", device_index) if backend == "nccl" else torch.device("cpu")
+        b = torch.as_tensor(np.nan_to_num(beta, nan=0.0, posinf=0.0), device=dev)
+        bad = torch.as_tensor((~np.isfinite(beta)).astype(np.float64) * np.where(np.isnan(beta), 1.0, 2.0), device=dev)
+        dist.all_reduce(b, group=self.process_group)
+        dist.all_reduce(bad, group=self.process_group)
+        out = b.cpu().numpy()
+        flag = bad.cpu().numpy()
+        out[flag == 1.0] = np.nan
+        out[flag == 2.0] = np.inf
+        return out
+
+    def get_covloss(self):
+        """beta of the last structure (calculator/active.py:781-804); evaluates it if the step did not."""
+        if self.beta is None:
+            if self.atoms is None:
+                raise RuntimeError("no structure has been calculated yet")
+            prev, self.covloss = self.covloss, True
+            try:
+                self.calculate(self.atoms)
+            finally:
+                self.covloss = prev
+        return self.beta
+
     # ------------------------------------------------------------------ the call
     def calculate(self, atoms=None, properties=("energy",), system_changes=_all_changes):
         if atoms is not None:
@@ -111,9 +149,15 @@ class B200Calculator(_AseCalculator):
         pbc = np.broadcast_to(np.asarray(a.pbc), (3,))
         eng = self._get_engine(numbers)
         dist, rank, world = self._dist()
-        E, F, W, owned = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world)
+        if self.covloss:
+            E, F, W, owned, beta = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world, want_beta=True)
+        else:
+            E, F, W, owned = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world)
+            beta = None
         if world > 1:
             E, W, F = self._reduce(dist, E, W, F, getattr(eng, "device", 0))
+            if beta is not None:   # every rank filled the betas of the atoms it owns (zeros elsewhere)
+                beta = self._gather_beta(dist, beta, getattr(eng, "device", 0))
         vol = abs(np.linalg.det(cell))
         if vol == 0.0:
             vol = -2.0  # calculator/active.py:606-609
@@ -125,6 +169,12 @@ class B200Calculator(_AseCalculator):
             "free_energy": np.array(E, dtype=np.float64),
         }
         self.owned = owned
+        self.beta = beta
+        if beta is not None:
+            covloss_max = float(np.max(beta)) if len(beta) else 0.0   # like torch.max: NaN / inf propagate
+            self.covlog = f"{covloss_max}"
+            if covloss_max > self.ediff and self.on_uncertain is not None and rank == 0:
+                self.on_uncertain(a, beta)
         self.maximum_force = float(np.abs(F).max()) if F.size else 0.0
         self.step += 1
         return self.results

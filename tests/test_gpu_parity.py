@@ -359,3 +359,30 @@ def test_lammps_fix_external_callback_drives_the_gpu_path():
     assert abs(lmp.energy[1] - float(g["energy"])) < TOL_E_PER_ATOM * len(tag)
     vol = abs(np.linalg.det(cell))
     assert np.allclose(lmp.virial[1], -g["stress"][[0, 1, 2, 5, 4, 3]] * vol, rtol=1e-6, atol=1e-9)
+
+
+def test_calculator_prediction_mode_uncertainty():
+    """calculator/active.py:492-499: in prediction mode the covloss is evaluated every step, its maximum logged
+    (covlog) and uncertain structures handed on."""
+    import types
+
+    import autoforce_b200 as ab
+
+    g = load_golden("lipso108")
+    atoms = types.SimpleNamespace(positions=g["pos"], numbers=g["numbers"], cell=g["cell"], pbc=g["meta"]["pbc"])
+    seen = []
+    calc = ab.B200Calculator(model_from_golden(g), covloss=True, ediff=0.0, on_uncertain=lambda a, b: seen.append(b.copy()))
+    res = calc.calculate(atoms, properties=("energy", "forces", "stress"))
+    assert abs(float(res["energy"]) - float(g["energy"])) / len(g["numbers"]) < TOL_E_PER_ATOM
+    ref = g["covloss"]
+    assert np.abs(calc.beta ** 2 - ref ** 2).max() < 1e-9 and len(seen) == 1
+    assert abs(float(calc.covlog) - float(ref.max())) < 1e-6
+    # without the option nothing is evaluated until asked for
+    calc2 = ab.B200Calculator(model_from_golden(g))
+    calc2.calculate(atoms)
+    assert calc2.beta is None and calc2.covlog == ""
+    assert np.abs(calc2.get_covloss() ** 2 - ref ** 2).max() < 1e-9
+    with pytest.raises(ValueError):
+        import dataclasses
+
+        ab.B200Calculator(dataclasses.replace(model_from_golden(g), choli=None), covloss=True)

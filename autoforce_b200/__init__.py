@@ -9,6 +9,6 @@ CUDA device is missing.
 from .model import SgprModel  # noqa: F401
 from .engine import SgprEngine, library_path, load_library  # noqa: F401
 from .calculator import B200Calculator  # noqa: F401
-from .kernels import SeSoapKernel, SubSeSoapKernel, UniversalSoapKernel, DefaultRadii  # noqa: F401
+from .kernels import SeSoapKernel, SubSeSoapKernel, HeterogeneousSoapKernel, UniversalSoapKernel, DefaultRadii  # noqa: F401
 
 __version__ = "0.1.0"

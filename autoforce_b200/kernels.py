@@ -133,6 +133,37 @@ class SubSeSoapKernel(SeSoapKernel):
         return self._a
 
 
+class HeterogeneousSoapKernel(_SoapKernelBase):
+    """similarity/heterosoap.py:10-29 with the base kernel ``DotProd() ** exponent``: central species ``a``,
+    neighbour species list ``b``, descriptor [NormalizedSoap(] HeteroSoap [)] with ONE length unit for all species
+    (``atomic_unit`` or cutoff / 3, descriptor/soap.py:20-23)."""
+
+    kind = "universal"
+
+    def __init__(self, exponent, a, b, lmax, nmax, cutoff, atomic_unit=None, normalize=True):
+        self.lmax, self.nmax, self.exponent, self.cutoff = int(lmax), int(nmax), exponent, float(cutoff)
+        self.unit = float(atomic_unit) if atomic_unit else self.cutoff / 3
+        self.normalize = bool(normalize)
+        self.a_only = (int(a),)
+        self._a = int(a)
+        self.b = sorted(int(z) for z in (b if hasattr(b, "__iter__") else [b]))
+        self.dim = len(self.b) ** 2 * (self.nmax + 1) ** 2 * (self.lmax + 1)
+        self._args = "Pow(DotProd(), {}), {}, {}, {}, {}, PolyCut({}, n=2), atomic_unit={}, normalize={}".format(
+            exponent, a, b, lmax, nmax, self.cutoff, atomic_unit, normalize)
+        self.name = "kern_0"
+        self.params = []
+
+    def _radii_dict(self):
+        return {}
+
+    def _default_radius(self):
+        return self.unit
+
+    @property
+    def state_args(self):
+        return self._args
+
+
 class UniversalSoapKernel(_SoapKernelBase):
     kind = "universal"
 

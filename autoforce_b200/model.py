@@ -101,23 +101,24 @@ class SgprModel:
         Supports one SeSoapKernel / UniversalSoapKernel in ``model.gp.kern.kernels``."""
         kerns = list(model.gp.kern.kernels)
         a_only, b_only = (), ()
-        if len(kerns) > 1 or type(kerns[0]).__name__ == "SubSeSoapKernel":
+        names = {type(k).__name__ for k in kerns}
+        if len(kerns) > 1 or names & {"SubSeSoapKernel", "HeterogeneousSoapKernel"}:
             # default_kernel(species=...) (calculator/active.py:28-38): one SubSeSoapKernel per central species,
-            # all with the same hyper-parameters and neighbour list b -> one dense model, centres = the a's
-            if not all(type(k).__name__ == "SubSeSoapKernel" for k in kerns):
-                raise NotImplementedError("kernel lists are supported for SubSeSoapKernel only")
+            # all with the same hyper-parameters and neighbour list b -> one dense model, centres = the a's.
+            # Same for lists of its parent class HeterogeneousSoapKernel (similarity/heterosoap.py:10-29).
+            if len(names) != 1 or not names <= {"SubSeSoapKernel", "HeterogeneousSoapKernel"}:
+                raise NotImplementedError("kernel lists are supported for SubSeSoapKernel / HeterogeneousSoapKernel only")
             k0 = kerns[0]
-            sig = lambda k: (int(k.descriptor.ylm.lmax), int(k.descriptor.nmax), float(k.kern.eta) if hasattr(k.kern, "eta") else None,
-                             float(k.cutoff), tuple(k.b), repr(k.descriptor.radii), bool(k.descriptor.normalize))
-            if any(sig(k) != sig(k0) for k in kerns):
-                raise NotImplementedError("SubSeSoapKernels with different hyper-parameters need one engine each")
+            if any(_list_signature(k) != _list_signature(k0) for k in kerns):
+                raise NotImplementedError("kernels with different hyper-parameters need one engine each")
             a_only = tuple(int(k.a) for k in kerns)
             b_only = tuple(int(z) for z in k0.b)
         lone_weight = float(len(kerns))
         k = kerns[0]
         cname = type(k).__name__
         desc = k.descriptor
-        lmax, nmax = int(desc.ylm.lmax), int(desc.nmax)
+        inner = getattr(desc, "soap", desc)   # NormalizedSoap wraps the descriptor proper
+        lmax, nmax = int(inner.ylm.lmax), int(inner.nmax)
         species = set()
         envs = []
         for loc in model.X:
@@ -133,13 +134,28 @@ class SgprModel:
         elif cname == "UniversalSoapKernel":
             kind = "universal"
             radii, default = {}, float(desc.unit)
+        elif cname == "HeterogeneousSoapKernel":
+            # descriptor = [NormalizedSoap(] HeteroSoap [)]: one length unit for all species (descriptor/soap.py:13-26)
+            normalized = type(desc).__name__ == "NormalizedSoap"
+            soap = desc.soap if normalized else desc
+            if type(soap).__name__ != "HeteroSoap":
+                raise NotImplementedError(f"HeterogeneousSoapKernel over {type(soap).__name__} is not supported")
+            kind = "universal"
+            radii, default = {}, float(soap.unit)
+            lmax, nmax = int(soap.ylm.lmax), int(soap.nmax)
+            desc = type("D", (), {"normalize": normalized})()
         else:
             raise NotImplementedError(f"kernel class {cname} is not supported")
         a = getattr(k, "_a", None)
         a_not = tuple(getattr(a, "exceptions", ()) or ())
-        if cname != "SubSeSoapKernel" and a is not None and not hasattr(a, "exceptions"):
+        if cname not in ("SubSeSoapKernel", "HeterogeneousSoapKernel") and a is not None and not hasattr(a, "exceptions"):
             raise NotImplementedError("kernels restricted to a fixed central species (a=Z) are not supported")
-        exponent = k.exponent if cname != "SubSeSoapKernel" else _subse_exponent(k)
+        if cname == "SubSeSoapKernel":
+            exponent = _subse_exponent(k)
+        elif cname == "HeterogeneousSoapKernel":
+            exponent = _dotprod_exponent(k.kern)
+        else:
+            exponent = k.exponent
         mean = model.mean
         mean_w = {}
         for z, w in getattr(mean, "weights", {}).items():
@@ -177,6 +193,27 @@ class SgprModel:
                    ind_Z=z["ind_Z"], ind_first=z["ind_first"], ind_r=z["ind_r"],
                    ind_b=z["ind_b"], mu=z["mu"], mean_w=meta["mean_w"], choli=z["choli"] if "choli" in z.files else None,
                    vscale=meta["vscale"], lone_weight=float(meta.get("lone_weight", 1.0)))
+
+
+def _list_signature(k):
+    """Everything of a SubSeSoapKernel / HeterogeneousSoapKernel but its central species."""
+    desc = k.descriptor
+    inner = getattr(desc, "soap", desc)
+    if type(k).__name__ == "SubSeSoapKernel":
+        return (int(inner.ylm.lmax), int(inner.nmax), _subse_exponent(k), float(k.cutoff), tuple(k.b), repr(desc.radii),
+                bool(desc.normalize))
+    return (int(inner.ylm.lmax), int(inner.nmax), _dotprod_exponent(k.kern), float(k.cutoff), tuple(k.b), float(inner.unit),
+            type(desc).__name__)
+
+
+def _dotprod_exponent(kern):
+    """Base kernel of a HeterogeneousSoapKernel: only ``DotProd() ** eta`` (regression/kernel.py:187-199) maps onto
+    (q_hat . z_hat)^xi."""
+    if type(kern).__name__ == "Pow" and type(kern.kern).__name__ == "DotProd":
+        return float(kern.eta)
+    if type(kern).__name__ == "DotProd":
+        return 1.0
+    raise NotImplementedError(f"base kernel {getattr(kern, 'state', kern)} is not supported (DotProd() ** eta only)")
 
 
 def _subse_exponent(k):

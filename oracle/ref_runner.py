@@ -58,6 +58,15 @@ def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()
 
         species = list(radii["species"])
         return [SubSeSoapKernel(lmax, nmax, xi, float(rc), z, species, radii=DefaultRadii()) for z in species]
+    elif kind == "heterosoap":
+        # one HeterogeneousSoapKernel per central species over NormalizedSoap(HeteroSoap) (similarity/heterosoap.py:10-29)
+        from theforce.descriptor.cutoff import PolyCut
+        from theforce.regression.kernel import DotProd
+        from theforce.similarity.heterosoap import HeterogeneousSoapKernel
+
+        species = list(radii["species"])
+        return [HeterogeneousSoapKernel(DotProd() ** xi, z, species, lmax, nmax, PolyCut(float(rc)), atomic_unit=atomic_unit)
+                for z in species]
     elif kind == "universal":
         from theforce.similarity.universal import UniversalSoapKernel
 

@@ -148,6 +148,14 @@ def case_inputs(name):
         envs.append((3, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
         envs.append((8, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
         pbc = [True] * 3
+    elif name == "hetero_2sp":
+        # HeterogeneousSoapKernel(DotProd()**4, a, b, ...) per central species, descriptor NormalizedSoap(HeteroSoap):
+        # one length unit rc/3 for all species (descriptor/soap.py:13-26)
+        kern = dict(kind="heterosoap", lmax=3, nmax=2, xi=4, rc=4.5, species=[14, 8])
+        pos, cell, num = fcc((2, 2, 3), [14, 8], 0.1, 21, a0=3.4)
+        sp, sc, sn = fcc(3, [14, 8], 0.15, 121, a0=3.4)
+        envs = pick_inducing(sp, sc, True, sn, 4.5, 12, 22)
+        pbc = [True] * 3
     else:
         raise KeyError(name)
     M = len(envs)
@@ -162,7 +170,7 @@ def case_inputs(name):
 
 CASES = [
     "cu108_sesoap", "cu108_perfect", "lipso108", "tric_oh", "universal_2sp", "cluster_lone", "slab_ttf", "highres_l6n8", "anot_xi2",
-    "subse_3sp", "subse_lone",
+    "subse_3sp", "subse_lone", "hetero_2sp",
 ]
 
 
@@ -180,7 +188,7 @@ def run_case(name):
     c = case_inputs(name)
     k = c["kernel"]
     kern = rr.make_kernel(k["kind"], k["lmax"], k["nmax"], k["xi"], k["rc"], a_not=k.get("a_not", ()),
-                          radii={"species": k["species"]} if k["kind"] == "subsesoap" else None)
+                          radii={"species": k["species"]} if k["kind"] in ("subsesoap", "heterosoap") else None)
     model = rr.synth_model(kern, c["envs"], c["mu"], c["mean_w"], c["choli"], c["vscale"])
     t0 = time.time()
     want = [0, len(c["pos"]) // 2, len(c["pos"]) - 1]
@@ -197,7 +205,7 @@ def run_case(name):
     species = np.unique(np.concatenate([c["numbers"]] + [e[2] for e in envs] + [[e[0] for e in envs]]).astype(np.int64))
     descs = {}
     zdesc = []
-    if k["kind"] == "subsesoap":
+    if k["kind"] in ("subsesoap", "heterosoap"):
         zdesc = [np.zeros((1,))] * len(model.X)   # dense per-kernel caches: not stored (the oracle is pinned through K)
     else:
         for a, d in ref["descriptors"].items():
@@ -209,9 +217,11 @@ def run_case(name):
             zdesc.append(np.zeros((len(species), len(species), kern.dim)) if v is None else species_dense(v.detach().to_dense().numpy(), species, k["kind"]))
     meta = dict(kernel=k, pbc=[bool(x) for x in c["pbc"]], mean_w={str(z): w for z, w in c["mean_w"].items()},
                 vscale={str(z): v for z, v in c["vscale"].items()}, species=[int(z) for z in species],
-                unit=(float(kern.descriptor.unit) if k["kind"] == "universal" else None),
-                a_only=(k["species"] if k["kind"] == "subsesoap" else []), b_only=(k["species"] if k["kind"] == "subsesoap" else []),
-                lone_weight=(len(k["species"]) if k["kind"] == "subsesoap" else 1),
+                unit=(float(kern.descriptor.unit) if k["kind"] == "universal" else
+                      float(kern[0].descriptor.soap.unit) if k["kind"] == "heterosoap" else None),
+                a_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
+                b_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
+                lone_weight=(len(k["species"]) if k["kind"] in ("subsesoap", "heterosoap") else 1),
                 generator="tests/golden/make_golden.py", reference="theforce v2021.09", ref_seconds=round(dt, 2))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),

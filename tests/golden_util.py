@@ -37,7 +37,7 @@ def load_golden(name):
 def golden_radii(meta):
     """Z -> length unit, as the reference's kernel had it (DefaultRadii: H 0.5, else 1.0,
     descriptor/sesoap.py:84-99; UniversalSoap: one unit for all, soap.py:724-728)."""
-    if meta["kernel"]["kind"] == "universal":
+    if meta["kernel"]["kind"] in ("universal", "heterosoap"):   # HeteroSoap: one unit as well (descriptor/soap.py:20-23)
         return {int(z): float(meta["unit"]) for z in meta["species"]}, float(meta["unit"])
     return {1: 0.5}, 1.0
 
@@ -64,7 +64,7 @@ def b200_model(g, big=False):
     k = g["meta"]["kernel"]
     radii, default = golden_radii(g["meta"])
     return ab.SgprModel(
-        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind="universal" if k["kind"] == "universal" else "sesoap",
+        lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind="universal" if k["kind"] in ("universal", "heterosoap") else "sesoap",
         radii=radii, default_radius=default, a_not=tuple(k.get("a_not", ())), a_only=tuple(g["meta"].get("a_only", ())),
         b_only=tuple(g["meta"].get("b_only", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
         mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},

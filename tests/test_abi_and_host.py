@@ -174,3 +174,34 @@ def test_sgpr_tape_reader_roundtrip(tmp_path):
         ref_write(loc, buf_ref)
         sgprio.write_lce(buf_own, z, r, b)
         assert buf_own.getvalue() == "\nstart: local\n" + buf_ref.getvalue() + "end: local\n"
+
+
+def test_extract_heterogeneous_kernel_list_from_reference_model():
+    """HeterogeneousSoapKernel(DotProd()**xi, a, b, ...) per central species (similarity/heterosoap.py:10-29) maps onto
+    one dense model with a uniform length unit; other base kernels are refused."""
+    from oracle import ref_runner as rr
+
+    if not rr.reference_available():
+        pytest.skip("/root/reference not present")
+    import autoforce_b200 as ab
+    from golden_util import load_golden
+
+    g = load_golden("hetero_2sp")
+    k = g["meta"]["kernel"]
+    kern = rr.make_kernel("heterosoap", k["lmax"], k["nmax"], k["xi"], k["rc"], radii={"species": k["species"]})
+    envs = [(int(z), r, b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    ref_model = rr.synth_model(kern, envs, g["mu"], {int(z): w for z, w in g["meta"]["mean_w"].items()}, g["choli"],
+                               {int(z): v for z, v in g["meta"]["vscale"].items()})
+    m = ab.SgprModel.from_posterior_potential(ref_model)
+    assert (m.lmax, m.nmax, m.xi, m.rc, m.kind) == (k["lmax"], k["nmax"], float(k["xi"]), k["rc"], "universal")
+    assert sorted(m.a_only) == [8, 14] and sorted(m.b_only) == [8, 14] and m.lone_weight == 2.0
+    assert m.unit_of(14) == m.unit_of(8) == k["rc"] / 3 == g["meta"]["unit"] and m.normalize
+    mirror = ab.HeterogeneousSoapKernel(4, 14, [14, 8], 3, 2, 4.5)
+    assert mirror.state == kern[0].state
+    from theforce.regression.kernel import DotProd, Positive
+    from theforce.similarity.heterosoap import HeterogeneousSoapKernel
+    from theforce.descriptor.cutoff import PolyCut
+
+    ref_model.gp.kern.kernels[0] = HeterogeneousSoapKernel(Positive(1.0) * DotProd() ** 4, 14, [14, 8], 3, 2, PolyCut(4.5))
+    with pytest.raises(NotImplementedError):
+        ab.SgprModel.from_posterior_potential(ref_model)

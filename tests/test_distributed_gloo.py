@@ -24,13 +24,18 @@ class StubEngine:
         self.e_atom = rng.normal(size=N)
         self.w_atom = rng.normal(size=(N, 3, 3))
 
-    def predict(self, pos, numbers, cell, pbc, rank=0, world=1):
+        self.beta = np.abs(rng.normal(size=N))
+        self.beta[3] = np.nan        # centre excluded through a / a_not
+        self.beta[N - 2] = np.inf    # species without a vscale entry
+
+    def predict(self, pos, numbers, cell, pbc, rank=0, world=1, want_beta=False):
         N = len(numbers)
         c0, c1 = N * rank // world, N * (rank + 1) // world
         owned = np.zeros(N, dtype=bool)
         owned[c0:c1] = True
         F = np.where(owned[:, None], self.F, 0.0)
-        return float(self.e_atom[owned].sum()), F, self.w_atom[owned].sum(axis=0), owned
+        out = (float(self.e_atom[owned].sum()), F, self.w_atom[owned].sum(axis=0), owned)
+        return out + (np.where(owned, self.beta, 0.0),) if want_beta else out
 
     def close(self):
         pass
@@ -81,3 +86,36 @@ def test_two_rank_reduction(tmp_path, gather):
         assert np.abs(r[0]["forces"] + r[1]["forces"] - ref.F).max() < 1e-15
         assert np.all(r[0]["forces"][~r[0]["owned"]] == 0)
     assert np.all(r[0]["owned"] ^ r[1]["owned"])
+
+
+def _worker_beta(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import autoforce_b200 as ab
+
+    N = 37
+    model = ab.SgprModel.from_envs([], lmax=3, nmax=3, xi=4.0, rc=6.0, choli=np.zeros((0, 0)))
+    seen = []
+    calc = ab.B200Calculator(model, covloss=True, ediff=0.5, on_uncertain=lambda a, b: seen.append(rank))
+    calc._engine = StubEngine(N)
+    calc.calculate(Atoms(N))
+    torch.save({"beta": calc.beta, "covlog": calc.covlog, "seen": seen}, os.path.join(out, f"b{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_covloss_gather(tmp_path):
+    """Each rank fills the betas of the atoms it owns; the calculator merges them (NaN and inf survive) and every
+    rank logs the same maximum; only rank 0 reports the uncertain structure (calculator/active.py:492-499)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_beta, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(str(tmp_path), f"b{k}.pt"), weights_only=False) for k in range(2)]
+    ref = StubEngine(37).beta
+    for k in range(2):
+        assert np.array_equal(np.isnan(r[k]["beta"]), np.isnan(ref)) and np.array_equal(np.isinf(r[k]["beta"]), np.isinf(ref))
+        fin = np.isfinite(ref)
+        assert np.abs(r[k]["beta"][fin] - ref[fin]).max() < 1e-15
+    assert r[0]["covlog"] == r[1]["covlog"] == "nan"      # max() propagates NaN like torch.max
+    assert r[0]["seen"] == [] and r[1]["seen"] == []       # nan > ediff is False

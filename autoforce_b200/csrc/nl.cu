@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                                                                    PairRec* __restrict__ pairs, unsigned char* __restrict__ mark,
                                                                    unsigned* __restrict__ masks, int* __restrict__ nl_run) {
     __shared__ double xs[kBinCap], ys[kBinCap], zs[kBinCap];
+    __shared__ float cmag[kBinCap];          // |x| + |y| + |z| of the unshifted and shifted candidate (rounding bound)
     __shared__ int pj[kBinCap];
     __shared__ unsigned code[kBinCap];       // bin shift (3 x int8) | species << 24
     __shared__ int run_beg[kRunChunk], run_pre[kRunChunk + 1];
@@ -611,6 +612,7 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                 xs[q] = aj.x + s0;
                 ys[q] = aj.y + s1;
                 zs[q] = aj.z + s2;
+                cmag[q] = (float)(fabs(aj.x) + fabs(aj.y) + fabs(aj.z) + fabs(s0) + fabs(s1) + fabs(s2)) * 1.0001f;
                 pj[q] = p;
                 code[q] = sh | ((unsigned)meta_species(aj.meta) << 24);
             }
@@ -636,6 +638,10 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                 double w0, w1, w2;
                 shift_vec(g, meta_w(ai.meta, 0), meta_w(ai.meta, 1), meta_w(ai.meta, 2), w0, w1, w2);
                 const double xi = ai.x - w0, yi = ai.y - w1, zi = ai.z - w2;   // the atom's image inside the box
+                // |d2 - d2_reference| <= ~2 rc sqrt(3) * (rounding of the coordinates involved): the band in which the
+                // shared-memory test may disagree with the reference's rounding sequence grows with the coordinates'
+                // magnitude (unwrapped trajectories far from the origin)
+                const double imag = fabs(ai.x) + fabs(ai.y) + fabs(ai.z) + fabs(w0) + fabs(w1) + fabs(w2);
                 // distance test of candidate q (shared-memory tile); exact rounding sequence only near rc
                 auto test = [&](int q) -> bool {
                     const double dx = xs[q] - xi, dy = ys[q] - yi, dz = zs[q] - zi;
@@ -643,8 +649,9 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                     const unsigned cd = code[q];
                     const int p = pj[q];
                     if (p == c && (cd & 0xffffffu) == 0u) return false;   // the atom itself (zero image shift)
-                    if (d2 < fast_lo) return true;
-                    if (d2 > fast_hi) return false;
+                    const double band = 3.6e-15 * g.rc * ((double)cmag[q] + imag);   // 2^-48 rc (|x_j| + |x_i| + shifts)
+                    if (d2 < fast_lo - band) return true;
+                    if (d2 > fast_hi + band) return false;
                     const AtomRec aj = atoms[p];
                     const int sx = (int)(signed char)(cd & 0xff), sy = (int)(signed char)((cd >> 8) & 0xff),
                               sz = (int)(signed char)((cd >> 16) & 0xff);

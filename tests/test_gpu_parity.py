@@ -386,3 +386,31 @@ def test_calculator_prediction_mode_uncertainty():
         import dataclasses
 
         ab.B200Calculator(dataclasses.replace(model_from_golden(g), choli=None), covloss=True)
+
+
+@pytest.mark.parametrize("mode", ["bins", "warp"])
+def test_neighbor_list_far_from_the_origin(mode, monkeypatch):
+    """Unwrapped trajectories: atoms up to ~100 cells away from the unit cell (the library's limit is 120 and is
+    reported as an error).  The accept/reject decision must still be the reference's (distance from the given
+    positions in its rounding sequence), for both neighbour kernels."""
+    import autoforce_b200 as ab
+
+    monkeypatch.setenv("SGPR_NL", mode)
+    g = load_golden("cu108_perfect")    # perfect lattice: many pairs at exactly equal distances
+    rc = g["meta"]["kernel"]["rc"]
+    a0 = g["cell"][0, 0] / 3
+    # scale so that a shell of neighbours sits (numerically) at the cutoff, then move everything far away
+    scale = rc / (a0 * np.sqrt(2.5))
+    cell = g["cell"] * scale
+    pos = g["pos"] * scale + 100.0 * cell[0] - 97.0 * cell[1] + 64.0 * cell[2] + np.array([0.3, -0.2, 0.1])
+    pos[::7] -= 15.0 * cell[0]
+    pos[3::5] += 20.0 * cell[2]
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    first, J, S = eng.neighbors(pos, g["numbers"], cell, True)
+    f0, J0, S0 = o.neighbor_list(pos, cell, True, rc)
+    assert np.array_equal(first, f0)
+    a, b = sorted_rows(first, J, S), sorted_rows(f0, J0, S0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(RuntimeError, match="120 cells"):
+        eng.neighbors(pos + 400.0 * cell[1], g["numbers"], cell, True)
+    eng.close()

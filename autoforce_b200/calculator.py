@@ -25,6 +25,20 @@ except Exception:  # pragma: no cover
     _all_changes = ["positions", "numbers", "cell", "pbc"]
 
 
+def _as_models(covariance):
+    """-> list of SgprModel whose energies / forces / virials add up (one entry unless the reference model sums
+    similarity kernels with different hyper-parameters)."""
+    if isinstance(covariance, (list, tuple)) and all(isinstance(m, SgprModel) for m in covariance):
+        return list(covariance)
+    if hasattr(covariance, "gp") and hasattr(covariance, "X"):
+        return SgprModel.list_from_posterior_potential(covariance)
+    if isinstance(covariance, str) and not covariance.endswith(".npz"):
+        from theforce.regression.gppotential import PosteriorPotentialFromFolder
+
+        return SgprModel.list_from_posterior_potential(PosteriorPotentialFromFolder(covariance, load_data=False, update_data=False))
+    return [_as_model(covariance)]
+
+
 def _as_model(covariance):
     if isinstance(covariance, SgprModel):
         return covariance
@@ -51,13 +65,16 @@ class B200Calculator(_AseCalculator):
             raise NotImplementedError(
                 "on-the-fly training stays on the reference path: use theforce's ActiveCalculator with the "
                 "GPU kernel plugged in (INTEGRATION.md); B200Calculator is the prediction-mode drop-in")
-        self.model = _as_model(covariance)
+        self.models = _as_models(covariance)
+        self.model = self.models[0]
         # prediction-mode uncertainty (calculator/active.py:492-499): covloss=True evaluates beta = get_covloss() every
         # step on the device, records its maximum in ``covlog`` and hands structures with max(beta) > ediff to
         # ``on_uncertain(atoms, beta)`` (the reference appends them to active_uncertain.traj)
         self.covloss = bool(covloss)
         if self.covloss and self.model.choli is None:
             raise ValueError("covloss=True needs a model with choli")
+        if self.covloss and len(self.models) > 1:
+            raise NotImplementedError("covloss of a model that sums kernels with different hyper-parameters")
         self.ediff = float(ediff)
         self.on_uncertain = on_uncertain
         self.covlog = ""
@@ -67,6 +84,7 @@ class B200Calculator(_AseCalculator):
         self.results = {}
         self.step = 0
         self._engine = None
+        self._more_engines = []      # handles of the 2nd, 3rd ... model of a kernel sum
         self._device = device
         self.atoms = None
 
@@ -90,6 +108,9 @@ class B200Calculator(_AseCalculator):
                 self._engine.close()
             dev = self._device if self._device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
             self._engine = SgprEngine(self.model, species=sorted(need), device=dev)
+            for e in self._more_engines:
+                e.close()
+            self._more_engines = [SgprEngine(m, species=sorted(need), device=dev) for m in self.models[1:]]
         return self._engine
 
     def _reduce(self, dist, E, W, F, device_index):
@@ -149,10 +170,15 @@ class B200Calculator(_AseCalculator):
         pbc = np.broadcast_to(np.asarray(a.pbc), (3,))
         eng = self._get_engine(numbers)
         dist, rank, world = self._dist()
+        if world > 1 and self._more_engines and not self.gather_forces:
+            raise NotImplementedError("a kernel sum shards every handle by its own cell order: use gather_forces=True")
         if self.covloss:
             E, F, W, owned, beta = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world, want_beta=True)
         else:
             E, F, W, owned = eng.predict(pos, numbers, cell, pbc, rank=rank, world=world)
+            for e in self._more_engines:   # kernels with different hyper-parameters: the contributions add up
+                E2, F2, W2, _ = e.predict(pos, numbers, cell, pbc, rank=rank, world=world)
+                E, F, W = E + E2, F + F2, W + W2
             beta = None
         if world > 1:
             E, W, F = self._reduce(dist, E, W, F, getattr(eng, "device", 0))

@@ -557,7 +557,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         dp.nbr_enabled[s] = d->neighbor_enabled[s] ? 1 : 0;
     }
     h->xi = d->xi;
-    h->lone_w = d->lone_weight > 0 ? d->lone_weight : 1.0;
+    h->lone_w = d->lone_weight > 0 ? d->lone_weight : (d->lone_weight < 0 ? 0.0 : 1.0);
     h->xi_int = (d->xi == std::floor(d->xi) && d->xi >= 1 && d->xi <= 64) ? (int)d->xi : -1;
     SGPR_TRY(upload(h->ztab, h->z_to_species, sizeof(int) * 128));
     SGPR_TRY(h->errflag.ensure(sizeof(int) * 4));

@@ -414,8 +414,10 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         // chain rule through the normalisation (sesoap.py:229-235): dE/dq = (g - q_hat (q_hat.g)) / P with
         // q_hat.g = sum_m G_im k_im = xi e_i (the local energy from the kernel-matrix GEMM) -> no dot pass
         const int r = row_of[c];
-        const double pg = dp.normalize ? xi * erow[r] : 0.0;
-        const double rP = dp.normalize ? 1.0 / prow[r] : 1.0;
+        // ... times (|p| + eps) / |p| (q_hat = p / (|p| + eps), sesoap.py:249-251): matters only for tiny norms
+        const double Pn = dp.normalize ? prow[r] : 1.0;
+        const double pg = dp.normalize ? xi * erow[r] * (Pn > 2.0 * kEps ? Pn / (Pn - kEps) : 1.0) : 0.0;
+        const double rP = 1.0 / Pn;
 #pragma unroll 4
         for (int e = lane; e < dp.D; e += 32) T_s[e] = (tvec[row + e] - phat[row + e] * pg) * rP * ttab[e];
 #pragma unroll 4

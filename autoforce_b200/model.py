@@ -170,6 +170,33 @@ class SgprModel:
             lone_weight=lone_weight,
         )
 
+    @classmethod
+    def list_from_posterior_potential(cls, model):
+        """A reference model whose ``gp.kern.kernels`` cannot be merged into one dense model (similarity kernels with
+        different lmax / nmax / exponent / cutoff, summed by EnergyForceKernel, regression/gppotential.py:81-84) as one
+        SgprModel per kernel: energies, forces and virials of the handles add up.  The kernels of the reference share
+        the neighbour list of the largest cutoff, so "neighbour-less" refers to that cutoff: the lone-atoms term (once
+        per kernel, similarity.py:41-43,94-103) is carried by the model with the largest cutoff alone, and so is the mean.
+        Falls back to ``[from_posterior_potential(model)]`` when one model suffices."""
+        import types
+
+        try:
+            return [cls.from_posterior_potential(model)]
+        except NotImplementedError:
+            pass
+        kerns = list(model.gp.kern.kernels)
+        out = []
+        for k in kerns:
+            one = types.SimpleNamespace(gp=types.SimpleNamespace(kern=types.SimpleNamespace(kernels=[k])), X=model.X, mu=model.mu,
+                                        mean=model.mean, choli=getattr(model, "choli", None), _vscale=getattr(model, "_vscale", {}))
+            out.append(cls.from_posterior_potential(one))
+        lead = max(range(len(out)), key=lambda i: out[i].rc)
+        for i, m in enumerate(out):
+            m.lone_weight = float(len(kerns)) if i == lead else -1.0
+            if i != lead:
+                m.mean_w = {}
+        return out
+
     # ------------------------------------------------------------------ flat file format
     def save(self, path):
         meta = dict(format="autoforce_b200.sgpr_model", version=1, lmax=self.lmax, nmax=self.nmax, xi=self.xi, rc=self.rc,

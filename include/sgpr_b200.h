@@ -82,7 +82,9 @@ typedef struct {
     double  lone_weight;          /* number of similarity kernels in model.gp.kern.kernels: each adds the
                                      lone-atoms term (similarity/similarity.py:41-43,94-103), so two
                                      neighbour-less LCEs of one species have k = lone_weight (1 for a single
-                                     kernel, n for default_kernel(species=[...n...])); 0 is read as 1      */
+                                     kernel, n for default_kernel(species=[...n...])); 0 is read as 1, a negative
+                                     value switches the term off (secondary handles of a model that sums kernels
+                                     with different hyper-parameters)                      */
 } sgpr_model_desc;
 
 /* ---- life cycle ------------------------------------------------------------------ */

@@ -67,6 +67,9 @@ def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()
         species = list(radii["species"])
         return [HeterogeneousSoapKernel(DotProd() ** xi, z, species, lmax, nmax, PolyCut(float(rc)), atomic_unit=atomic_unit)
                 for z in species]
+    elif kind == "multi":
+        # a kernel list with DIFFERENT hyper-parameters: EnergyForceKernel sums them (regression/gppotential.py:81-84)
+        return [make_kernel(**k) for k in radii["kernels"]]
     elif kind == "universal":
         from theforce.similarity.universal import UniversalSoapKernel
 

@@ -446,8 +446,13 @@ def descriptor_backward(model, p_hat, aux, g):
     and also spells out in SeSoap.forward(grad=True), sesoap.py:204-246."""
     norm = aux["norm"][:, None, None, None, None, None]
     if model.normalize:
+        # p_hat = p / (|p| + eps):  dE/dp = [g - p_hat (p_hat.g) (|p| + eps) / |p|] / (|p| + eps)  -- what autograd gives
+        # (calculator/active.py:587-599); sesoap.py:229-235 drops the factor (|p| + eps) / |p| = 1 + O(eps / |p|)
         pg = (p_hat * g).sum(axis=(1, 2, 3, 4, 5), keepdims=True)
-        dp = (g - p_hat * pg) / norm
+        eps = np.finfo(float).eps
+        with np.errstate(divide="ignore", invalid="ignore"):
+            corr = np.where(norm > 2 * eps, norm / (norm - eps), 1.0)
+        dp = (g - p_hat * pg * corr) / norm
     else:
         dp = g
     q = dp * aux["nnl"]
@@ -514,6 +519,8 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
     reference's per-rank ``atoms.indices``, descriptor/atoms.py:321-341); forces
     and virial are then the partial sums over those environments.
     """
+    if isinstance(model, (list, tuple)):
+        return predict_kernel_list(model, pos, cell, pbc, numbers, want_K=want_K, want_beta=want_beta, chunk=chunk, atoms=atoms)
     pos = np.asarray(pos, dtype=float).reshape(-1, 3)
     numbers = np.asarray(numbers, dtype=np.int64)
     cell = np.asarray(cell, dtype=float).reshape(3, 3)
@@ -543,7 +550,12 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
         e_local[k0 : k0 + len(idx)] = K @ mu
         # self kernel k(x,x) (active.py:785-788): 1 for a normalised descriptor, 0 for an
         # excluded centre, 1 for a neighbour-less atom (similarity.py:94-103)
-        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, model.lone_weight, np.where(model.excluded_centres(numbers[idx]), 0.0, 1.0))
+        # self kernel (p_hat . p_hat)^xi: 1 up to O(eps / |p|) for a normalised descriptor, 0 for a zero descriptor (an
+        # environment whose neighbours all lie beyond this kernel's cutoff -- possible in kernel lists, which share the
+        # neighbour list of the largest cutoff)
+        selfk = _powxi((P.reshape(len(idx), -1) ** 2).sum(axis=1), model.xi) if model.normalize else np.ones(len(idx))
+        alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, model.lone_weight,
+                                                 np.where(model.excluded_centres(numbers[idx]), 0.0, selfk))
         if Kout is not None:
             Kout[k0 : k0 + len(idx)] = K
         xi = model.xi
@@ -570,12 +582,44 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
     except ValueError:
         vol = -2.0  # calculator/active.py:606-609
     stress = (W / vol).reshape(-1)[[0, 4, 8, 5, 2, 1]]
-    out = dict(energy=energy, forces=F, stress=stress, virial=W, first=first, j=J, S=S, e_local=e_local)
+    out = dict(energy=energy, forces=F, stress=stress, virial=W, first=first, j=J, S=S, e_local=e_local, alpha=alpha_all)
     if want_K:
         out["K"] = Kout
     if want_beta:
         out["beta"] = covloss(model, Kout, numbers[idx_all], alpha=alpha_all)
     return out
+
+
+def predict_kernel_list(models, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk=256, atoms=None):
+    """A model whose EnergyForceKernel sums several similarity kernels with DIFFERENT hyper-parameters
+    (regression/gppotential.py:81-84): the kernels share mu, choli, the inducing LCEs and ONE neighbour list, built with
+    the largest cutoff (model.cutoff, descriptor/atoms.py:348-355) -- so "neighbour-less" (similarity.py:94-103) means no
+    neighbour within the largest cutoff, and every kernel adds the lone-atoms term.  ``models``: one OracleModel per
+    kernel, each with lone_weight 1; the mean is taken from the first."""
+    pos = np.asarray(pos, dtype=float).reshape(-1, 3)
+    cell = np.asarray(cell, dtype=float).reshape(3, 3)
+    numbers = np.asarray(numbers, dtype=np.int64)
+    nl = neighbor_list(pos, cell, pbc, max(m.rc for m in models), centers=atoms)
+    tot = None
+    for k, m in enumerate(models):
+        if k > 0:
+            m = dataclass_replace(m, mean_w={})
+        out = predict(m, pos, cell, pbc, numbers, want_K=True, chunk=chunk, atoms=atoms, nl=nl)
+        if tot is None:
+            tot = dict(out)
+        else:
+            for key in ("energy", "forces", "virial", "stress", "e_local", "K", "alpha"):
+                tot[key] = tot[key] + out[key]
+    if want_beta:
+        idx = np.arange(len(numbers)) if atoms is None else np.asarray(atoms, dtype=np.int64)
+        tot["beta"] = covloss(models[0], tot["K"], numbers[idx], alpha=tot["alpha"])
+    return tot
+
+
+def dataclass_replace(obj, **kw):
+    import dataclasses
+
+    return dataclasses.replace(obj, **kw)
 
 
 def kernel_jacobian(model, pos, cell, pbc, numbers, chunk=256, scatter_quirk=False):

@@ -156,6 +156,20 @@ def case_inputs(name):
         sp, sc, sn = fcc(3, [14, 8], 0.15, 121, a0=3.4)
         envs = pick_inducing(sp, sc, True, sn, 4.5, 12, 22)
         pbc = [True] * 3
+    elif name == "two_kernels":
+        # two similarity kernels with different lmax / nmax / exponent / cutoff summed in one model; an isolated atom
+        # and an atom whose only neighbour lies between the two cutoffs
+        kern = dict(kind="multi", lmax=3, nmax=3, xi=4, rc=5.5,
+                    kernels=[dict(kind="sesoap", lmax=3, nmax=3, xi=4, rc=5.5), dict(kind="sesoap", lmax=2, nmax=2, xi=2, rc=3.8)])
+        pos, cell, num = fcc((2, 2, 2), [3, 8], 0.1, 23, a0=3.9)
+        cell = cell + np.diag([40.0, 0.0, 0.0])
+        pos = np.vstack([pos, [[25.0, 1.0, 1.0]], [[35.0, 4.0, 2.0]], [[39.5, 4.0, 2.0]]])
+        num = np.concatenate([num, [3, 8, 3]])
+        sp, sc, sn = fcc(2, [3, 8], 0.15, 123, a0=3.9)
+        envs = pick_inducing(sp, sc, True, sn, 5.5, 10, 24)
+        envs.append((3, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
+        envs.append((8, np.array([[4.5, 0.0, 0.0]]), np.array([3], dtype=np.int64)))
+        pbc = [True] * 3
     else:
         raise KeyError(name)
     M = len(envs)
@@ -170,7 +184,7 @@ def case_inputs(name):
 
 CASES = [
     "cu108_sesoap", "cu108_perfect", "lipso108", "tric_oh", "universal_2sp", "cluster_lone", "slab_ttf", "highres_l6n8", "anot_xi2",
-    "subse_3sp", "subse_lone", "hetero_2sp",
+    "subse_3sp", "subse_lone", "hetero_2sp", "two_kernels",
 ]
 
 
@@ -188,7 +202,8 @@ def run_case(name):
     c = case_inputs(name)
     k = c["kernel"]
     kern = rr.make_kernel(k["kind"], k["lmax"], k["nmax"], k["xi"], k["rc"], a_not=k.get("a_not", ()),
-                          radii={"species": k["species"]} if k["kind"] in ("subsesoap", "heterosoap") else None)
+                          radii={"species": k["species"]} if k["kind"] in ("subsesoap", "heterosoap") else
+                          {"kernels": k["kernels"]} if k["kind"] == "multi" else None)
     model = rr.synth_model(kern, c["envs"], c["mu"], c["mean_w"], c["choli"], c["vscale"])
     t0 = time.time()
     want = [0, len(c["pos"]) // 2, len(c["pos"]) - 1]
@@ -205,7 +220,7 @@ def run_case(name):
     species = np.unique(np.concatenate([c["numbers"]] + [e[2] for e in envs] + [[e[0] for e in envs]]).astype(np.int64))
     descs = {}
     zdesc = []
-    if k["kind"] in ("subsesoap", "heterosoap"):
+    if k["kind"] in ("subsesoap", "heterosoap", "multi"):
         zdesc = [np.zeros((1,))] * len(model.X)   # dense per-kernel caches: not stored (the oracle is pinned through K)
     else:
         for a, d in ref["descriptors"].items():
@@ -221,7 +236,8 @@ def run_case(name):
                       float(kern[0].descriptor.soap.unit) if k["kind"] == "heterosoap" else None),
                 a_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
                 b_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
-                lone_weight=(len(k["species"]) if k["kind"] in ("subsesoap", "heterosoap") else 1),
+                lone_weight=(len(k["species"]) if k["kind"] in ("subsesoap", "heterosoap") else
+                             len(k["kernels"]) if k["kind"] == "multi" else 1),
                 generator="tests/golden/make_golden.py", reference="theforce v2021.09", ref_seconds=round(dt, 2))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),

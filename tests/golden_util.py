@@ -42,10 +42,13 @@ def golden_radii(meta):
     return {1: 0.5}, 1.0
 
 
-def oracle_model(g, big=False):
+def oracle_model(g, big=False, kernel=None):
+    """OracleModel of a golden case; for a case with a list of different kernels (kind "multi") a list of them."""
     from oracle.sgpr_oracle import OracleModel
 
-    k = g["meta"]["kernel"]
+    k = g["meta"]["kernel"] if kernel is None else kernel
+    if k["kind"] == "multi":
+        return [oracle_model(g, big, dict(kk)) for kk in k["kernels"]]
     radii, default = golden_radii(g["meta"])
     return OracleModel(
         lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], radii=radii, default_radius=default,
@@ -53,15 +56,18 @@ def oracle_model(g, big=False):
         mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()}, choli=g["choli"],
         vscale={int(z): v for z, v in g["meta"]["vscale"].items()}, a_not=tuple(k.get("a_not", ())),
         a_only=tuple(g["meta"].get("a_only", ())), b_only=tuple(g["meta"].get("b_only", ())),
-        lone_weight=float(g["meta"].get("lone_weight", 1)),
+        lone_weight=float(g["meta"].get("lone_weight", 1)) if kernel is None else 1.0,
     )
 
 
-def b200_model(g, big=False):
-    """The same golden model as an autoforce_b200.SgprModel (product-side container)."""
+def b200_model(g, big=False, kernel=None):
+    """The same golden model as an autoforce_b200.SgprModel (product-side container); a list of them for a case with
+    a list of different kernels (kind "multi")."""
     import autoforce_b200 as ab
 
-    k = g["meta"]["kernel"]
+    k = g["meta"]["kernel"] if kernel is None else kernel
+    if k["kind"] == "multi":
+        return [b200_model(g, big, dict(kk)) for kk in k["kernels"]]
     radii, default = golden_radii(g["meta"])
     return ab.SgprModel(
         lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind="universal" if k["kind"] in ("universal", "heterosoap") else "sesoap",
@@ -69,4 +75,4 @@ def b200_model(g, big=False):
         b_only=tuple(g["meta"].get("b_only", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
         mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
         choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()},
-        lone_weight=float(g["meta"].get("lone_weight", 1)))
+        lone_weight=float(g["meta"].get("lone_weight", 1)) if kernel is None else 1.0)

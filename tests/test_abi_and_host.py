@@ -205,3 +205,27 @@ def test_extract_heterogeneous_kernel_list_from_reference_model():
     ref_model.gp.kern.kernels[0] = HeterogeneousSoapKernel(Positive(1.0) * DotProd() ** 4, 14, [14, 8], 3, 2, PolyCut(4.5))
     with pytest.raises(NotImplementedError):
         ab.SgprModel.from_posterior_potential(ref_model)
+
+
+def test_kernel_sum_is_split_into_one_model_per_kernel():
+    """SgprModel.list_from_posterior_potential: different hyper-parameters -> one model per kernel, the lone-atoms term
+    and the mean carried by the model with the largest cutoff."""
+    from oracle import ref_runner as rr
+
+    if not rr.reference_available():
+        pytest.skip("/root/reference not present")
+    import autoforce_b200 as ab
+    from golden_util import load_golden
+
+    g = load_golden("two_kernels")
+    k = g["meta"]["kernel"]
+    kern = rr.make_kernel("multi", 0, 0, 0, 0, radii={"kernels": k["kernels"]})
+    envs = [(int(z), r, b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    ref_model = rr.synth_model(kern, envs, g["mu"], {int(z): w for z, w in g["meta"]["mean_w"].items()}, g["choli"],
+                               {int(z): v for z, v in g["meta"]["vscale"].items()})
+    with pytest.raises(NotImplementedError):
+        ab.SgprModel.from_posterior_potential(ref_model)
+    ms = ab.SgprModel.list_from_posterior_potential(ref_model)
+    assert [(m.lmax, m.nmax, m.xi, m.rc) for m in ms] == [(kk["lmax"], kk["nmax"], float(kk["xi"]), kk["rc"]) for kk in k["kernels"]]
+    assert [m.lone_weight for m in ms] == [2.0, -1.0] and ms[1].mean_w == {} and len(ms[0].mean_w) == 2
+    assert all(np.array_equal(m.mu, g["mu"]) and np.array_equal(m.ind_r, g["ind_r"]) for m in ms)

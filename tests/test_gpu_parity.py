@@ -41,6 +41,8 @@ def case(request):
     import autoforce_b200 as ab
 
     g = load_golden(request.param)
+    if g["meta"]["kernel"]["kind"] == "multi":
+        pytest.skip("kernel sums run through one handle per kernel: test_kernel_sum_with_different_hyperparameters")
     eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
     yield g, eng
     eng.close()
@@ -57,7 +59,7 @@ def test_neighbor_list_bit_exact(case):
 
 def test_descriptors_match_reference_cache(case):
     g, eng = case
-    if g["meta"]["kernel"]["kind"] in ("subsesoap", "heterosoap"):
+    if g["meta"]["kernel"]["kind"] in ("subsesoap", "heterosoap", "multi"):
         pytest.skip("dense per-kernel caches are not stored for SubSeSoapKernel lists")
     species = np.array(g["meta"]["species"])
     Zh = eng.inducing_descriptors()
@@ -414,3 +416,40 @@ def test_neighbor_list_far_from_the_origin(mode, monkeypatch):
     with pytest.raises(RuntimeError, match="120 cells"):
         eng.neighbors(pos + 400.0 * cell[1], g["numbers"], cell, True)
     eng.close()
+
+
+def test_kernel_sum_with_different_hyperparameters():
+    """EnergyForceKernel sums similarity kernels (regression/gppotential.py:81-84); kernels with different lmax / nmax /
+    exponent / cutoff run as one handle each and add up.  The golden structure has an isolated atom and a pair whose
+    distance lies between the two cutoffs ("neighbour-less" refers to the largest cutoff in the reference)."""
+    import types
+
+    import autoforce_b200 as ab
+
+    g = load_golden("two_kernels")
+    models = model_from_golden(g)
+    assert len(models) == 2
+    lead = max(range(2), key=lambda i: models[i].rc)
+    for i, m in enumerate(models):      # what SgprModel.list_from_posterior_potential sets up
+        m.lone_weight = 2.0 if i == lead else -1.0
+        if i != lead:
+            m.mean_w = {}
+    atoms = types.SimpleNamespace(positions=g["pos"], numbers=g["numbers"], cell=g["cell"], pbc=g["meta"]["pbc"])
+    calc = ab.B200Calculator(models)
+    res = calc.calculate(atoms, properties=("energy", "forces", "stress"))
+    N = len(g["numbers"])
+    assert abs(float(res["energy"]) - float(g["energy"])) / N < TOL_E_PER_ATOM
+    assert np.abs(res["forces"] - g["forces"]).max() < TOL_F
+    assert np.abs(res["stress"] - g["stress"]).max() < TOL_S
+    # the kernel matrices add up as well
+    K = sum(e.kernel_matrix(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"]).cpu().numpy()
+            for e in [calc._engine] + calc._more_engines)
+    assert np.abs(K - g["K"]).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        ab.B200Calculator([dataclasses_replace(m, choli=g["choli"]) for m in models], covloss=True)
+
+
+def dataclasses_replace(obj, **kw):
+    import dataclasses
+
+    return dataclasses.replace(obj, **kw)

@@ -604,6 +604,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         const char* trs = getenv("SGPR_I8_TR");
         h->use_i8 = dp.normalize && !(eng && strcmp(eng, "dmma") == 0);
         h->i8_tr = (trs && atoi(trs) == 8) ? 8 : 7;
+        const char* tr2 = getenv("SGPR_I8_TR2");   // back projection (forces only): like the kernel matrix, or 6 / 7 / 8
+        h->i8_tr2 = tr2 ? (atoi(tr2) == 8 ? 8 : atoi(tr2) == 6 ? 6 : 7) : h->i8_tr;
         if (h->use_i8) {
             st = i8_prepare_model(h, false);
             if (st == SGPR_OK) st = i8_prepare_covloss(h);

@@ -227,11 +227,11 @@ struct Epi2 {   // back projection: g = mumax * C
     }
 };
 
-template <int TR, class Epi>
-int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
+template <int NS, int TR, class Epi>
+int launch_ns(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
     constexpr int STAGES = 3;
-    auto kern = i8gemm_kernel<kNS, TR, STAGES, Epi>;
-    const size_t smem = smem_bytes<kNS, STAGES>();
+    auto kern = i8gemm_kernel<NS, TR, STAGES, Epi>;
+    const size_t smem = smem_bytes<NS, STAGES>();
     static bool done = false;   // per instantiation
     if (!done) {
         SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -244,6 +244,11 @@ int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi&
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
+}
+
+template <int TR, class Epi>
+int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
+    return launch_ns<kNS, TR, Epi>(h, cm, probs_d, epi, st);
 }
 
 }  // namespace
@@ -372,8 +377,10 @@ static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Pr
             P.M = r1 - r0;
             P.N = dp.D;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
-            SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
-            SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, kNS, dp.D, h->i8_mp, (long long)dp.D, BN));
+            // t + u <= 6 uses the 5 most significant digit slices of both operands (same buffers, same slice stride)
+            const int ns2 = h->i8_tr2 == 6 ? 5 : kNS;
+            SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>() + (size_t)r0 * h->i8_mp, ns2, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, ns2, dp.D, h->i8_mp, (long long)dp.D, BN));
         } else {
             P.M = r1 - r0;
             P.N = h->M;
@@ -391,7 +398,8 @@ static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Pr
             // algorithmic flops of the dense product; the zero part of a triangular choli is skipped, not counted less
             h->stats.covloss_flops += 2.0 * P.M * (double)P.N * (m1 - m0);
         } else {
-            const int npairs = h->i8_tr == 8 ? 26 : 21;
+            const int tr = which == 2 ? h->i8_tr2 : h->i8_tr;
+            const int npairs = tr == 8 ? 26 : tr == 6 ? 15 : 21;
             h->stats.gemm_flops += 2.0 * P.M * (double)P.N * (which == 1 ? dp.D : (m1 - m0));
             h->stats.i8_ops += 2.0 * P.M * (double)P.N * P.Kpad * npairs;
         }
@@ -446,7 +454,8 @@ int i8_back_projection(sgpr_context* h, cudaStream_t st) {
     for (int p = 0; p < cm.n_prob; ++p) e.gvec[p] = h->gvec.as<double>() + (size_t)h->row_first[ps[p]] * h->dp.ldp;
     e.ldp = h->dp.ldp;
     e.mumax = h->i8_mumax;
-    return h->i8_tr == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+    if (h->i8_tr2 == 6) return launch_ns<5, 6>(h, cm, probs_d, e, st);
+    return h->i8_tr2 == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
 }
 
 // Covloss GEMM on tcgen05: b = K . choli^T per central species, reduced on the fly to per-row partial sums of

@@ -62,11 +62,13 @@ def test_model_roundtrip(tmp_path):
     rng = np.random.default_rng(0)
     envs = [(29, rng.normal(size=(5, 3)), np.full(5, 29)), (8, np.zeros((0, 3)), np.zeros(0, int)), (29, rng.normal(size=(2, 3)), np.array([8, 29]))]
     m = ab.SgprModel.from_envs(envs, lmax=3, nmax=2, xi=4.0, rc=5.5, radii={1: 0.5}, mu=rng.normal(size=3),
-                               mean_w={29: -3.0, 8: -1.0}, vscale={29: 1.0}, choli=np.eye(3), a_not=(8,))
+                               mean_w={29: -3.0, 8: -1.0}, vscale={29: 1.0}, choli=np.eye(3), a_not=(8,), a_only=(29,),
+                               b_only=(8, 29), lone_weight=2.0)
     p = str(tmp_path / "model.npz")
     m.save(p)
     m2 = ab.SgprModel.load(p)
-    for f in ("lmax", "nmax", "xi", "rc", "kind", "normalize", "radii", "default_radius", "a_not", "mean_w", "vscale"):
+    for f in ("lmax", "nmax", "xi", "rc", "kind", "normalize", "radii", "default_radius", "a_not", "a_only", "b_only", "lone_weight",
+              "mean_w", "vscale"):
         assert getattr(m, f) == getattr(m2, f), f
     for f in ("ind_Z", "ind_first", "ind_r", "ind_b", "mu", "choli"):
         assert np.array_equal(getattr(m, f), getattr(m2, f)), f

@@ -205,12 +205,43 @@ class B200Calculator(_AseCalculator):
         self.step += 1
         return self.results
 
-    # plain getters for non-ASE callers
-    def get_potential_energy(self, atoms=None):
-        return float(self.calculate(atoms)["energy"]) if atoms is not None or not self.results else float(self.results["energy"])
+    # ------------------------------------------------------------------ getters (callers without ASE)
+    def _same_state(self, atoms):
+        a = self.atoms
+        if a is None or not self.results:
+            return False
+        try:
+            return (np.array_equal(np.asarray(a.positions), np.asarray(atoms.positions))
+                    and np.array_equal(np.asarray(a.cell), np.asarray(atoms.cell))
+                    and np.array_equal(np.asarray(a.numbers), np.asarray(atoms.numbers))
+                    and np.array_equal(np.broadcast_to(np.asarray(a.pbc), (3,)), np.broadcast_to(np.asarray(atoms.pbc), (3,))))
+        except Exception:
+            return False
 
-    def get_forces(self, atoms=None):
-        return (self.calculate(atoms) if atoms is not None or not self.results else self.results)["forces"]
+    def _property(self, name, atoms):
+        """One evaluation per structure, like ase's Calculator.get_property: a second getter on an unchanged
+        structure returns the cached result (no second GPU pass, no second ``step`` / ``on_uncertain``)."""
+        if atoms is not None and not self._same_state(atoms):
+            self.calculate(atoms)
+        elif not self.results:
+            if self.atoms is None and atoms is None:
+                raise RuntimeError("no structure has been calculated yet")
+            self.calculate(atoms)
+        return self.results[name]
 
-    def get_stress(self, atoms=None):
-        return (self.calculate(atoms) if atoms is not None or not self.results else self.results)["stress"]
+
+if _AseCalculator is object:
+    # ase.calculators.calculator.Calculator provides these (with its own check_state caching) when ASE is there;
+    # otherwise the same signatures, incl. the ``force_consistent`` keyword ASE optimisers pass
+    def _get_potential_energy(self, atoms=None, force_consistent=False, **kw):
+        return float(self._property("free_energy" if force_consistent else "energy", atoms))
+
+    def _get_forces(self, atoms=None, **kw):
+        return self._property("forces", atoms)
+
+    def _get_stress(self, atoms=None, **kw):
+        return self._property("stress", atoms)
+
+    B200Calculator.get_potential_energy = _get_potential_energy
+    B200Calculator.get_forces = _get_forces
+    B200Calculator.get_stress = _get_stress

@@ -303,6 +303,8 @@ using namespace sgpr;
 extern "C" __attribute__((visibility("default"))) const char* sgpr_last_error(void) { return g_err; }
 extern "C" __attribute__((visibility("default"))) int sgpr_abi_version(void) { return SGPR_ABI_VERSION; }
 
+extern "C" void sgpr_destroy(sgpr_handle h);
+
 static int upload(DevBuf& b, const void* src, size_t bytes) {
     SGPR_TRY(b.ensure(bytes ? bytes : 8));
     if (bytes) SGPR_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
@@ -505,8 +507,19 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         set_error("invalid rc/xi/M");
         return SGPR_ERR_INVALID;
     }
+    if (d->M > 0 && (!d->mu_h || !d->ind_Z_h || !d->ind_first_h)) {
+        set_error("M = %d inducing LCEs but mu_h / ind_Z_h / ind_first_h is null", d->M);
+        return SGPR_ERR_INVALID;
+    }
     SGPR_CUDA(cudaSetDevice(d->device));
     sgpr_context* h = new sgpr_context();
+    // any error return below destroys the half-built context (stream, events, device buffers)
+    struct Guard {
+        sgpr_context* h;
+        ~Guard() {
+            if (h) sgpr_destroy(h);
+        }
+    } guard{h};
     h->device = d->device;
     cudaDeviceProp prop;
     SGPR_CUDA(cudaGetDeviceProperties(&prop, d->device));
@@ -533,7 +546,6 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     dp.rc = d->rc;
     if (dp.A > 255) {
         set_error("S*(nmax+1) = %d exceeds 255", dp.A);
-        delete h;
         return SGPR_ERR_INVALID;
     }
     for (int i = 0; i < 128; ++i) h->z_to_species[i] = -1;
@@ -547,8 +559,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         const int z = d->species_Z[s];
         if (z < 0 || z >= 128 || h->z_to_species[z] >= 0 || !(d->radii[s] > 0)) {
             set_error("bad species table entry %d (Z=%d, radius=%g)", s, z, d->radii[s]);
-            delete h;
-            return SGPR_ERR_INVALID;
+                return SGPR_ERR_INVALID;
         }
         h->species_Z[s] = z;
         h->z_to_species[z] = s;
@@ -586,15 +597,13 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     {
         const int st_ind = set_inducing(h, d->M, d->ind_Z_h, d->ind_first_h, d->ind_r_h, d->ind_b_h);
         if (st_ind != SGPR_OK) {
-            delete h;
-            return st_ind;
+                return st_ind;
         }
     }
     std::vector<double> zeros(SGPR_MAX_SPECIES, 0.0), infs(SGPR_MAX_SPECIES, INFINITY);
     int st = upload_weights(h, d->mu_h, d->mean_w_h ? d->mean_w_h : zeros.data(), d->choli_h,
                             d->vscale_h ? d->vscale_h : infs.data(), nullptr);
     if (st != SGPR_OK) {
-        delete h;
         return st;
     }
     {   // GEMM engine: tcgen05 int8-sliced (default, needs normalised descriptors) or FP64 DMMA
@@ -610,14 +619,14 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
             st = i8_prepare_model(h, false);
             if (st == SGPR_OK) st = i8_prepare_covloss(h);
             if (st != SGPR_OK) {
-                delete h;
-                return st;
+                        return st;
             }
         }
     }
     memset(&h->stats, 0, sizeof(h->stats));
     h->stats.d_packed = dp.D;
     h->stats.d_full = dp.A * dp.A * L;
+    guard.h = nullptr;
     *out = h;
     return SGPR_OK;
 }
@@ -905,8 +914,11 @@ extern "C" __attribute__((visibility("default"))) int sgpr_p2p_collect(sgpr_hand
 
 static int ensure_pinned(sgpr_context* h, size_t bytes) {
     if (bytes <= h->pinned_bytes) return SGPR_OK;
-    if (h->pinned) cudaFreeHost(h->pinned);
-    if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
+    // (i8_probs_pinned is an independent fixed-size allocation owned by i8gemm.cu: not touched here)
+    if (h->pinned) {
+        SGPR_CUDA(cudaStreamSynchronize(h->own_stream));   // no copy may still read the old staging area
+        cudaFreeHost(h->pinned);
+    }
     h->pinned = nullptr;
     h->pinned_bytes = 0;
     SGPR_CUDA(cudaMallocHost(&h->pinned, bytes + bytes / 4));

@@ -424,6 +424,16 @@ class SgprEngine:
         a3, p3 = arr(choli, M * M)
         a4, p4 = arr(vs, len(self.species))
         _check(self.lib, self.lib.sgpr_set_weights(self._h, p1, p2, p3, p4))
+        # keep the host-side model in step with the device (save(), `model.choli is None` checks)
+        m = self.model
+        if a1 is not None:
+            m.mu = a1.reshape(-1).copy()
+        if mean_w is not None:
+            m.mean_w = {int(z): float(w) for z, w in mean_w.items()}
+        if a3 is not None:
+            m.choli = a3.reshape(M, M).copy()
+        if vscale is not None:
+            m.vscale = {int(z): float(v) for z, v in vscale.items()}
 
     def append_inducing(self, envs, mu, choli=None):
         """Add inducing LCEs ``[(Z, r[nn,3], b[nn]), ...]`` after the existing ones and install the refitted

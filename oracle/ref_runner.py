@@ -1,9 +1,11 @@
 """Run the UNMODIFIED reference (`/root/reference/theforce`) in this container.
 
-TEST INFRASTRUCTURE, BUILD CONTAINER ONLY (see oracle/__init__.py): used by
-``tests/golden/make_golden.py`` to generate golden vectors and by the optional
-``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is absent,
-e.g. on the GPU box).  Follows SURVEY.md Appendix B.
+TEST / BENCH INFRASTRUCTURE (see oracle/__init__.py): used by
+``tests/golden/make_golden.py`` to generate golden vectors, by the tests that run the
+reference side by side with the product, and by ``bench.py --impl reference``.  The
+package is imported from /root/reference (build container) or from the unmodified copy
+staged under ``oracle/_ref`` by ``oracle/stage_ref.py`` (GPU box).  Follows SURVEY.md
+Appendix B.
 """
 from __future__ import annotations
 
@@ -12,12 +14,21 @@ import sys
 
 import numpy as np
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("AUTOFORCE_REFERENCE", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "theforce")):
+    # outside the build container (GPU box): the copy staged by oracle/stage_ref.py (git-ignored oracle/_ref/)
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
+_SHIMS = os.path.join(_HERE, "shims")
 
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "theforce"))
+
+
+def reference_kind():
+    """"source" = /root/reference itself, "staged" = the unmodified copy under oracle/_ref."""
+    return "staged" if REFERENCE_ROOT.endswith("_ref") else "source"
 
 
 def import_reference():

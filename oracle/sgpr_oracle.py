@@ -510,7 +510,8 @@ def kernel_from_descriptors(model, P, Zc, lone_c, Zh, lone_m):
 # --------------------------------------------------------------------------
 # a7-a9: energy / forces / stress / covloss  (calculator/active.py:548-611,781-804)
 # --------------------------------------------------------------------------
-def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk=256, atoms=None, nl=None, Zh=None):
+def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk=256, atoms=None, nl=None, Zh=None,
+            row_weights=None):
     """Full restatement of ``ActiveCalculator.calculate`` in prediction mode.
 
     returns dict(energy, forces[N,3], stress[6] (xx,yy,zz,yz,xz,xy), virial[3,3],
@@ -518,6 +519,9 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
     ``atoms``: optional index subset whose local energies are evaluated (the
     reference's per-rank ``atoms.indices``, descriptor/atoms.py:321-341); forces
     and virial are then the partial sums over those environments.
+    ``row_weights`` [N, M]: a cotangent dL/dK replacing mu row by row -- ``forces`` / ``virial`` are then the
+    vector-Jacobian product that torch.autograd.grad computes through ``cov`` in the reference
+    (calculator/active.py:587-599, regression/gppotential.py:905-911).
     """
     if isinstance(model, (list, tuple)):
         return predict_kernel_list(model, pos, cell, pbc, numbers, want_K=want_K, want_beta=want_beta, chunk=chunk, atoms=atoms)
@@ -559,7 +563,8 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
         if Kout is not None:
             Kout[k0 : k0 + len(idx)] = K
         xi = model.xi
-        Gm = np.where(valid, xi * _powxi(dot, xi - 1) * mu[None, :], 0.0)
+        wrow = mu[None, :] if row_weights is None else np.asarray(row_weights, dtype=float)[idx]
+        Gm = np.where(valid, xi * _powxi(dot, xi - 1) * wrow, 0.0)
         g = (Gm @ Zh.reshape(model.M, -1)).reshape(P.shape)
         dR = descriptor_backward(model, P, aux, g)
         for b, i in enumerate(idx):

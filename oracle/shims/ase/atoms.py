@@ -108,6 +108,24 @@ class Atoms:
             raise RuntimeError("Atoms object has no calculator.")
         return self._calc.get_property(name, self)
 
+    def write(self, path, format="extxyz", append=False):
+        """Minimal extended-xyz frame (io/sgprio.py:76-82 appends training data to the tape this way)."""
+        assert format == "extxyz"
+        sym = {1: "H", 3: "Li", 8: "O", 15: "P", 16: "S", 29: "Cu", 79: "Au"}
+        res = getattr(self._calc, "results", {}) if self._calc is not None else {}
+        head = 'Lattice="{}" Properties=species:S:1:pos:R:3{} pbc="{}"'.format(
+            " ".join(repr(float(v)) for v in self._cellobj.reshape(-1)), ":forces:R:3" if "forces" in res else "",
+            " ".join("T" if b else "F" for b in self._pbc))
+        if "energy" in res:
+            head += " energy={!r}".format(float(res["energy"]))
+        with open(path, "a" if append else "w") as f:
+            f.write(f"{len(self)}\n{head}\n")
+            for k, (z, x) in enumerate(zip(self.numbers, self.positions)):
+                line = "{:<2s} {:20.12f} {:20.12f} {:20.12f}".format(sym.get(int(z), f"X{int(z)}"), *x)
+                if "forces" in res:
+                    line += " {:20.12f} {:20.12f} {:20.12f}".format(*np.asarray(res["forces"])[k])
+                f.write(line + "\n")
+
     def get_potential_energy(self):
         return self._get("energy")
 

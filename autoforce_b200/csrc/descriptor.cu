@@ -69,13 +69,19 @@ struct Nbr {
             const AtomRec aj = src.atoms[pr.j];
             j = pr.j;
             sp = pr.sp;
-            const double S0 = (double)(pr.sb[0] - meta_w(aj.meta, 0) + meta_w(ai.meta, 0));
-            const double S1 = (double)(pr.sb[1] - meta_w(aj.meta, 1) + meta_w(ai.meta, 1));
-            const double S2 = (double)(pr.sb[2] - meta_w(aj.meta, 2) + meta_w(ai.meta, 2));
+            const int i0 = pr.sb[0] - meta_w(aj.meta, 0) + meta_w(ai.meta, 0);
+            const int i1 = pr.sb[1] - meta_w(aj.meta, 1) + meta_w(ai.meta, 1);
+            const int i2 = pr.sb[2] - meta_w(aj.meta, 2) + meta_w(ai.meta, 2);
             // r = xyz[n] - xyz[a] + (off[...,None]*lll).sum(dim=1)   (descriptor/atoms.py:366-368)
-            rx = __dadd_rn(__dadd_rn(aj.x, -ai.x), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[0]), __dmul_rn(S1, g.cell[3])), __dmul_rn(S2, g.cell[6])));
-            ry = __dadd_rn(__dadd_rn(aj.y, -ai.y), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[1]), __dmul_rn(S1, g.cell[4])), __dmul_rn(S2, g.cell[7])));
-            rz = __dadd_rn(__dadd_rn(aj.z, -ai.z), __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[2]), __dmul_rn(S1, g.cell[5])), __dmul_rn(S2, g.cell[8])));
+            rx = __dadd_rn(aj.x, -ai.x);
+            ry = __dadd_rn(aj.y, -ai.y);
+            rz = __dadd_rn(aj.z, -ai.z);
+            if ((i0 | i1 | i2) != 0) {   // image shift 0 (the bulk of a large cell): the cell term is an exact + 0.0
+                const double S0 = (double)i0, S1 = (double)i1, S2 = (double)i2;
+                rx = __dadd_rn(rx, __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[0]), __dmul_rn(S1, g.cell[3])), __dmul_rn(S2, g.cell[6])));
+                ry = __dadd_rn(ry, __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[1]), __dmul_rn(S1, g.cell[4])), __dmul_rn(S2, g.cell[7])));
+                rz = __dadd_rn(rz, __dadd_rn(__dadd_rn(__dmul_rn(S0, g.cell[2]), __dmul_rn(S1, g.cell[5])), __dmul_rn(S2, g.cell[8])));
+            }
         }
     }
 };
@@ -130,6 +136,15 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
     const int L = dp.lmax + 1;
     const int npairs = dp.A * (dp.A + 1) / 2;
     const bool cache_q = dp.D <= 32 * stride;            // packed row fits the (then idle) chunk buffer
+    // column (s, n) of this lane's B fragments in the all-species product (loop invariant: no integer division inside)
+    constexpr int NT_ = (kMaxNB + 7) / 8;
+    int col_s[NT_], col_n[NT_];
+#pragma unroll
+    for (int nt = 0; nt < NT_; ++nt) {
+        const int col = nt * 8 + (lane >> 2);
+        col_s[nt] = col / dp.nb;
+        col_n[nt] = col - col_s[nt] * dp.nb;
+    }
     for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
         long long beg, end;
         AtomRec ai;
@@ -152,8 +167,7 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
             double rx, ry, rz;
             int sp, j;
             Nbr<ENV>::load(src, g, ai, k, rx, ry, rz, sp, j);
-            const double u = dp.radii[sp];
-            hit |= near_z_axis(rx / u, ry / u, rz / u);
+            hit |= near_z_axis(rx, ry, rz);   // |x| < a |z| and |y| < a |z| does not depend on the length unit
         }
         const bool flag = __any_sync(0xffffffffu, hit);
         __syncwarp();
@@ -183,12 +197,12 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                 double rx, ry, rz;
                 int sp, j;
                 Nbr<ENV>::load(src, g, ai, k, rx, ry, rz, sp, j);
-                const double u = dp.radii[sp];
-                const double x = rx / u, y = ry / u, z = rz / u;
+                const double u = dp.radii[sp], ru = dp.rinv[sp];
+                const double x = rx * ru, y = ry * ru, z = rz * ru;
                 const double d2 = x * x + y * y + z * z;
                 const double d = sqrt(d2);
                 double R, Rpd;
-                radial(d, u, dp.rc, R, Rpd);
+                radial_fast(d2, d, 1.0, u, dp.rc, dp.rc_inv, R, Rpd);   // R'(d)/d is not needed here
                 if (!dp.nbr_enabled[sp]) R = 0.0;   // species outside the descriptor's `b` list
                 double* my = buf + lane * stride;
                 double fn = R;
@@ -218,8 +232,7 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     double bv[NT];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        const int col = nt * 8 + g8, cs = col / dp.nb;
-                        bv[nt] = (cs == sj) ? row[col - cs * dp.nb] : 0.0;
+                        bv[nt] = (col_s[nt] == sj) ? row[col_n[nt]] : 0.0;
                     }
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -345,7 +358,9 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
         if (cbuf) {
             for (int t = lane; t < dp.csize; t += 32) cbuf[(size_t)env * dp.csize + t] = c_s[t];
             if (lane == 0) {
-                prow[row_of[c]] = P;   // consumed by the back-projection epilogue (row order)
+                // norm of the row: the backward pass divides by it; for an un-normalised model (P = 1) the covloss
+                // needs the self kernel (p.p)^xi instead (calculator/active.py:784-791)
+                prow[row_of[c]] = dp.normalize ? P : sqrt(ss);
                 sflag[env] = flag ? 1 : 0;
             }
         }
@@ -461,12 +476,13 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
             double rx, ry, rz;
             int sp, j;
             Nbr<false>::load(src, g, ai, k, rx, ry, rz, sp, j);
-            const double u = dp.radii[sp];
-            const double x = rx / u, y = ry / u, z = rz / u;
+            const double u = dp.radii[sp], ru = dp.rinv[sp];
+            const double x = rx * ru, y = ry * ru, z = rz * ru;
             const double d2 = x * x + y * y + z * z;
-            const double d = sqrt(d2);
+            const double rd = rsqrt(d2);
+            const double d = d2 * rd;
             double R, Rpd;
-            radial(d, u, dp.rc, R, Rpd);
+            radial_fast(d2, d, rd, u, dp.rc, dp.rc_inv, R, Rpd);
             if (!dp.nbr_enabled[sp]) {
                 R = 0.0;
                 Rpd = 0.0;
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
 #pragma unroll
             for (int n = 0; n < NB; ++n)
                 if (n < dp.nb) rad += Tn[n] * hh[n];
-            const double Gx = (rad * x + gx) / u, Gy = (rad * y + gy) / u, Gz = (rad * z + gz) / u;
+            const double Gx = (rad * x + gx) * ru, Gy = (rad * y + gy) * ru, Gz = (rad * z + gz) * ru;
             if (own_i) {
                 Fx += Gx;
                 Fy += Gy;

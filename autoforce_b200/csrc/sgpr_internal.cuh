@@ -79,7 +79,9 @@ struct DescParams {
     int ldp;                // leading dimension of packed descriptor rows (doubles)
     int normalize;
     double rc;
+    double rc_inv;                  // 1 / rc
     double radii[kMaxSpecies];
+    double rinv[kMaxSpecies];       // 1 / radii (exact for the reference's radii 1.0 and 0.5)
     int central_enabled[kMaxSpecies];
     int nbr_enabled[kMaxSpecies];   // 0: neighbours of this species are left out of the expansion
 };

@@ -132,6 +132,19 @@ SGPR_HD void radial(double d, double u, double rc, double& R, double& Rp_over_d)
     Rp_over_d = ((u * dcut) * ex) / d - cut * ex;
 }
 
+// Same functions for the hot kernels, division-free: d2 = d^2 and rd = 1/d are passed in, rc_inv = 1/rc.
+// (1 - rt/rc is formed as 1 - rt * rc_inv: at most one ulp of rt/rc away.)
+SGPR_HD void radial_fast(double d2, double d, double rd, double u, double rc, double rc_inv, double& R, double& Rp_over_d) {
+    const double rt = u * d;
+    const double step = (rt < rc) ? 1.0 : 0.0;
+    const double w = 1.0 - rt * rc_inv;
+    const double ex = exp(-0.5 * d2);
+    const double cut = step * w * w;
+    const double dcut = step * (-2.0 * w * rc_inv);
+    R = cut * ex;
+    Rp_over_d = ((u * dcut) * ex) * rd - cut * ex;
+}
+
 // a_{n,l} = 1 / ((2l+1) 2^(2n+l) n! (n+l)!)   (sesoap.py:119-128)
 inline double anl(int n, int l) {
     double f1 = 1.0, f2 = 1.0;

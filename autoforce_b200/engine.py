@@ -60,6 +60,7 @@ EXPORTS = {
                                  c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "sgpr_descriptors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_inducing_descriptors": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "sgpr_kernel_envs": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_get_stats": (c_int32, [c_void_p, POINTER(sgpr_stats)]),
     "sgpr_enable_timing": (c_int32, [c_void_p, c_int32]),
 }
@@ -131,19 +132,13 @@ class PeerForceExchange:
         over the ranks."""
         import torch.distributed as dist
 
-        eng, lib = self.engine, self.engine.lib
+        eng = self.engine
         p = self.parity
         # the other buffer was collected at the end of the previous step: clear it for the next one
         self.buf[(1 - p) * self.stride:(2 - p) * self.stride].zero_()
-        peers = np.array([ptr + 8 * p * self.stride for ptr in self.ptrs], dtype=np.uint64)
-        cell_h, pbc_h = eng._geom(cell, pbc)
-        _check(lib, lib.sgpr_predict_p2p(eng._h, self.N, c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()), _ptr(cell_h),
-                                         _ptr(pbc_h), self.rank, self.world, eng._stream(), _ptr(peers),
-                                         c_void_p(self.ew.data_ptr()), c_void_p(self.ew.data_ptr() + 8)))
+        eng.predict_p2p(pos_t, z_t, cell, pbc, self.rank, self.world, [ptr + 8 * p * self.stride for ptr in self.ptrs], self.ew)
         dist.all_reduce(self.ew, group=self.group)   # E + virial; also: every rank's force kernel has finished
-        own = self.buf[p * self.stride:(p + 1) * self.stride]
-        _check(lib, lib.sgpr_p2p_collect(eng._h, eng._stream(), c_void_p(own.data_ptr()), c_void_p(self.F.data_ptr()),
-                                         c_void_p(self.owned.data_ptr())))
+        eng.p2p_collect(self.buf[p * self.stride:(p + 1) * self.stride], self.F, self.owned)
         self.parity = 1 - p
         return self.ew[0], self.F, self.ew[1:].view(3, 3), self.owned
 
@@ -309,6 +304,22 @@ class SgprEngine:
                                                c_void_p(F.data_ptr()), c_void_p(W.data_ptr()), None, None))
         return E, F, W
 
+    def predict_p2p(self, pos_t, z_t, cell, pbc, rank, world, peer_ptrs, ew):
+        """``sgpr_predict_p2p``: this rank's environments only; forces on every atom are ADDED into the accumulation
+        buffer of the atom's owner, ``peer_ptrs[r]`` (device addresses valid on this GPU: peer-mapped over NVLink, or plain
+        local buffers when several ranks are emulated on one GPU).  ``ew`` [10] receives this rank's E and 3x3 virial."""
+        cell_h, pbc_h = self._geom(cell, pbc)
+        peers = np.array([int(p) for p in peer_ptrs], dtype=np.uint64)
+        _check(self.lib, self.lib.sgpr_predict_p2p(self._h, z_t.numel(), c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()),
+                                                   _ptr(cell_h), _ptr(pbc_h), int(rank), int(world), self._stream(), _ptr(peers),
+                                                   c_void_p(ew.data_ptr()), c_void_p(ew.data_ptr() + 8)))
+
+    def p2p_collect(self, own_buf, F, owned):
+        """``sgpr_p2p_collect``: after every rank's ``predict_p2p`` has finished, copy this rank's accumulated forces
+        (cell order) into ``F`` [N,3] (caller's order, rows of owned atoms) and fill the ``owned`` mask."""
+        _check(self.lib, self.lib.sgpr_p2p_collect(self._h, self._stream(), c_void_p(own_buf.data_ptr()), c_void_p(F.data_ptr()),
+                                                   c_void_p(owned.data_ptr())))
+
     def peer_exchange(self, N, group=None):
         """Set up the peer-memory (NVLink) force exchange for structures of N atoms (torch symmetric memory)."""
         return PeerForceExchange(self, N, group)
@@ -406,6 +417,31 @@ class SgprEngine:
         _check(self.lib, self.lib.sgpr_inducing_descriptors(self._h, self._stream(), c_void_p(Zh.data_ptr())))
         S, n, L = len(self.species), self.model.nmax + 1, self.model.lmax + 1
         return Zh.cpu().numpy().reshape(self.model.M, S, S, n, n, L)
+
+    def kernel_envs(self, envs, want_K=True, want_descriptors=False):
+        """Explicit environments ``[(Z, r[nn,3], b[nn]), ...]`` (reference ``Local``s) against the inducing set:
+        ``K [n, M]`` = ``kern(locs, X)`` (device tensor) and / or their descriptors ``[n, S, S, nmax+1, nmax+1, lmax+1]``
+        (numpy) = ``kern.call_descriptor(loc, grad=False)`` (similarity/universal.py:97-122)."""
+        import torch
+
+        n = len(envs)
+        Z = np.ascontiguousarray([int(e[0]) for e in envs], dtype=np.int32)
+        rs = [np.asarray(e[1], dtype=np.float64).reshape(-1, 3) for e in envs]
+        bs = [np.asarray(e[2], dtype=np.int32).reshape(-1) for e in envs]
+        first = np.zeros(n + 1, dtype=np.int64)
+        first[1:] = np.cumsum([len(b) for b in bs])
+        r = np.ascontiguousarray(np.concatenate(rs) if n else np.zeros((0, 3)))
+        b = np.ascontiguousarray(np.concatenate(bs) if n else np.zeros(0, dtype=np.int32))
+        dev = torch.device("cuda", self.device)
+        K = torch.zeros((n, self.model.M), dtype=torch.float64, device=dev) if want_K else None
+        P = torch.zeros((n, self.d_full), dtype=torch.float64, device=dev) if want_descriptors else None
+        if n:
+            _check(self.lib, self.lib.sgpr_kernel_envs(self._h, n, _ptr(Z), _ptr(first), _ptr(r), _ptr(b), self._stream(),
+                                                       c_void_p(K.data_ptr()) if want_K else None,
+                                                       c_void_p(P.data_ptr()) if want_descriptors else None))
+        S, nb, L = len(self.species), self.model.nmax + 1, self.model.lmax + 1
+        Pn = P.cpu().numpy().reshape(n, S, S, nb, nb, L) if want_descriptors else None
+        return (K, Pn) if (want_K and want_descriptors) else (K if want_K else Pn)
 
     # ------------------------------------------------------------------ misc
     def set_weights(self, mu=None, mean_w=None, choli=None, vscale=None):

@@ -149,7 +149,7 @@ class SgprModel:
         a = getattr(k, "_a", None)
         a_not = tuple(getattr(a, "exceptions", ()) or ())
         if cname not in ("SubSeSoapKernel", "HeterogeneousSoapKernel") and a is not None and not hasattr(a, "exceptions"):
-            raise NotImplementedError("kernels restricted to a fixed central species (a=Z) are not supported")
+            a_only = (int(a),)   # a kernel restricted to one central species: loc.number == self.a (universal.py:101)
         if cname == "SubSeSoapKernel":
             exponent = _subse_exponent(k)
         elif cname == "HeterogeneousSoapKernel":

@@ -203,6 +203,18 @@ int sgpr_descriptors(sgpr_handle h, int64_t N, const double* pos_d, const int32_
 /* Same layout for the inducing LCEs (loc.kern_0_value): Zhat_d [M, S*S*(nmax+1)^2*(lmax+1)]. */
 int sgpr_inducing_descriptors(sgpr_handle h, void* stream, double* Zhat_d);
 
+/* Explicit local chemical environments (reference `Local` objects: number, _r, _b; descriptor/atoms.py:36-52) against
+ * the inducing set -- the similarity interface on LCEs rather than structures:
+ *   K_d [n_env, M]   = kern(locs, X)            (similarity/similarity.py:17-43, universal.py:109-122 incl. the
+ *                                                 lone-atoms term), columns in the caller's inducing order; with the
+ *                                                 handle's own LCEs as input this is the M x M matrix of
+ *                                                 regression/gppotential.py:511 / 781.
+ *   P_d [n_env, S*S*(nmax+1)^2*(lmax+1)] = kern.call_descriptor(loc, grad=False) / precalculate (universal.py:97-107)
+ *                                                 in the dense block layout of sgpr_descriptors.
+ * Environments are host CSR arrays like sgpr_model_desc.ind_*; either output may be NULL.  Synchronises the stream. */
+int sgpr_kernel_envs(sgpr_handle h, int32_t n_env, const int32_t* env_Z_h, const int64_t* env_first_h,
+                     const double* env_r_h, const int32_t* env_b_h, void* stream, double* K_d, double* P_d);
+
 /* ---- introspection ------------------------------------------------------------------ */
 
 typedef struct {

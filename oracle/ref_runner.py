@@ -49,7 +49,7 @@ def import_reference():
     return theforce
 
 
-def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()):
+def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=(), normalize=True, a=None):
     import_reference()
     if kind == "sesoap":
         from theforce.descriptor.sesoap import DefaultRadii, SpecialRadii
@@ -60,8 +60,9 @@ def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()
             rad = DefaultRadii()
         else:
             rad = SpecialRadii({int(k): float(v) for k, v in radii.items() if k != "others"}, float(radii.get("others", 1.0)))
-        a = EqAll(list(a_not)) if len(a_not) else None
-        return SeSoapKernel(lmax, nmax, xi, float(rc), a=a, radii=rad)
+        if a is None:
+            a = EqAll(list(a_not)) if len(a_not) else None   # else: a fixed central species (similarity/universal.py:101)
+        return SeSoapKernel(lmax, nmax, xi, float(rc), a=a, radii=rad, normalize=normalize)
     elif kind == "subsesoap":
         # default_kernel(species=...) of calculator/active.py:28-38
         from theforce.descriptor.sesoap import DefaultRadii
@@ -84,7 +85,7 @@ def make_kernel(kind, lmax, nmax, xi, rc, radii=None, atomic_unit=None, a_not=()
     elif kind == "universal":
         from theforce.similarity.universal import UniversalSoapKernel
 
-        return UniversalSoapKernel(lmax, nmax, xi, float(rc), atomic_unit=atomic_unit, a_not=list(a_not))
+        return UniversalSoapKernel(lmax, nmax, xi, float(rc), atomic_unit=atomic_unit, a_not=list(a_not), normalize=normalize, a=a)
     raise ValueError(kind)
 
 

@@ -557,7 +557,7 @@ def predict(model, pos, cell, pbc, numbers, want_K=False, want_beta=False, chunk
         # self kernel (p_hat . p_hat)^xi: 1 up to O(eps / |p|) for a normalised descriptor, 0 for a zero descriptor (an
         # environment whose neighbours all lie beyond this kernel's cutoff -- possible in kernel lists, which share the
         # neighbour list of the largest cutoff)
-        selfk = _powxi((P.reshape(len(idx), -1) ** 2).sum(axis=1), model.xi) if model.normalize else np.ones(len(idx))
+        selfk = _powxi((P.reshape(len(idx), -1) ** 2).sum(axis=1), model.xi)
         alpha_all[k0 : k0 + len(idx)] = np.where(lone_c, model.lone_weight,
                                                  np.where(model.excluded_centres(numbers[idx]), 0.0, selfk))
         if Kout is not None:

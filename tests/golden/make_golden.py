@@ -170,11 +170,27 @@ def case_inputs(name):
         envs.append((3, np.zeros((0, 3)), np.zeros(0, dtype=np.int64)))
         envs.append((8, np.array([[4.5, 0.0, 0.0]]), np.array([3], dtype=np.int64)))
         pbc = [True] * 3
+    elif name == "unnorm_2sp":
+        # un-normalised descriptor (normalize=False): the power spectrum itself enters the kernel (sesoap.py:249-251 off)
+        kern = dict(kind="sesoap", lmax=2, nmax=2, xi=2, rc=4.5, normalize=False)
+        pos, cell, num = fcc((2, 2, 2), [3, 8], 0.1, 25, a0=3.9)
+        sp, sc, sn = fcc(2, [3, 8], 0.15, 125, a0=3.9)
+        envs = pick_inducing(sp, sc, True, sn, 4.5, 10, 26)
+        pbc = [True] * 3
+    elif name == "afixed_2sp":
+        # a kernel restricted to ONE central species (a=8): other centres give zero rows (universal.py:100-107)
+        kern = dict(kind="sesoap", lmax=3, nmax=2, xi=4, rc=5.0, a=8)
+        pos, cell, num = fcc((2, 2, 2), [3, 8], 0.1, 27, a0=3.9)
+        sp, sc, sn = fcc(2, [3, 8], 0.15, 127, a0=3.9)
+        envs = pick_inducing(sp, sc, True, sn, 5.0, 10, 28)
+        pbc = [True] * 3
     else:
         raise KeyError(name)
     M = len(envs)
     Zs = np.unique(np.concatenate([num] + [e[2] for e in envs] + [[e[0] for e in envs]]).astype(np.int64))
     mu = rng.normal(0, 1, M) * 0.1
+    if not kern.get("normalize", True):
+        mu = mu * 1e9   # the un-normalised power spectrum is tiny (nnl ~ 1e-3 ... 1e-6 per entry): K ~ 1e-9
     A = rng.normal(0, 1, (M, M)) * 0.05
     choli = 0.5 * np.eye(M) + np.tril(A)
     mean_w = {int(z): -3.0 + 0.1 * k for k, z in enumerate(Zs)}
@@ -184,7 +200,7 @@ def case_inputs(name):
 
 CASES = [
     "cu108_sesoap", "cu108_perfect", "lipso108", "tric_oh", "universal_2sp", "cluster_lone", "slab_ttf", "highres_l6n8", "anot_xi2",
-    "subse_3sp", "subse_lone", "hetero_2sp", "two_kernels",
+    "subse_3sp", "subse_lone", "hetero_2sp", "two_kernels", "unnorm_2sp", "afixed_2sp",
 ]
 
 
@@ -202,6 +218,7 @@ def run_case(name):
     c = case_inputs(name)
     k = c["kernel"]
     kern = rr.make_kernel(k["kind"], k["lmax"], k["nmax"], k["xi"], k["rc"], a_not=k.get("a_not", ()),
+                          normalize=k.get("normalize", True), a=k.get("a"),
                           radii={"species": k["species"]} if k["kind"] in ("subsesoap", "heterosoap") else
                           {"kernels": k["kernels"]} if k["kind"] == "multi" else None)
     model = rr.synth_model(kern, c["envs"], c["mu"], c["mean_w"], c["choli"], c["vscale"])
@@ -234,7 +251,7 @@ def run_case(name):
                 vscale={str(z): v for z, v in c["vscale"].items()}, species=[int(z) for z in species],
                 unit=(float(kern.descriptor.unit) if k["kind"] == "universal" else
                       float(kern[0].descriptor.soap.unit) if k["kind"] == "heterosoap" else None),
-                a_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
+                a_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else [k["a"]] if k.get("a") is not None else []),
                 b_only=(k["species"] if k["kind"] in ("subsesoap", "heterosoap") else []),
                 lone_weight=(len(k["species"]) if k["kind"] in ("subsesoap", "heterosoap") else
                              len(k["kernels"]) if k["kind"] == "multi" else 1),

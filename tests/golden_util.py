@@ -55,6 +55,7 @@ def oracle_model(g, big=False, kernel=None):
         ind_Z=g["ind_Z"], ind_r=g["envs_r"], ind_b=g["envs_b"], mu=g["mu_big"] if big else g["mu"],
         mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()}, choli=g["choli"],
         vscale={int(z): v for z, v in g["meta"]["vscale"].items()}, a_not=tuple(k.get("a_not", ())),
+        normalize=bool(k.get("normalize", True)),
         a_only=tuple(g["meta"].get("a_only", ())), b_only=tuple(g["meta"].get("b_only", ())),
         lone_weight=float(g["meta"].get("lone_weight", 1)) if kernel is None else 1.0,
     )
@@ -72,6 +73,7 @@ def b200_model(g, big=False, kernel=None):
     return ab.SgprModel(
         lmax=k["lmax"], nmax=k["nmax"], xi=k["xi"], rc=k["rc"], kind="universal" if k["kind"] in ("universal", "heterosoap") else "sesoap",
         radii=radii, default_radius=default, a_not=tuple(k.get("a_not", ())), a_only=tuple(g["meta"].get("a_only", ())),
+        normalize=bool(k.get("normalize", True)),
         b_only=tuple(g["meta"].get("b_only", ())), ind_Z=g["ind_Z"], ind_first=g["ind_first"], ind_r=g["ind_r"], ind_b=g["ind_b"],
         mu=g["mu_big"] if big else g["mu"], mean_w={int(z): w for z, w in g["meta"]["mean_w"].items()},
         choli=g["choli"], vscale={int(z): v for z, v in g["meta"]["vscale"].items()},

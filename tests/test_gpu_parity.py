@@ -63,16 +63,16 @@ def test_descriptors_match_reference_cache(case):
         pytest.skip("dense per-kernel caches are not stored for SubSeSoapKernel lists")
     species = np.array(g["meta"]["species"])
     Zh = eng.inducing_descriptors()
-    keep = ~np.isin(g["ind_Z"], np.array(g["meta"]["kernel"].get("a_not", []), dtype=np.int64))
+    keep = ~oracle_model(g).excluded_centres(g["ind_Z"])
     ref = g["ind_desc"].reshape(Zh.shape)
     assert np.abs(Zh[keep] - ref[keep]).max() < 1e-13
     Zo, _ = o.inducing_descriptors(oracle_model(g), species)
     assert np.abs(Zh - Zo).max() < 1e-13
     P = eng.descriptors(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
-    excluded = set(g["meta"]["kernel"].get("a_not", []))
+    om = oracle_model(g)
     for key in [k for k in g if k.startswith("desc_")]:
         a = int(key.split("_")[1])
-        if int(g["numbers"][a]) in excluded:
+        if om.excluded_centres(g["numbers"][a:a + 1])[0]:
             continue
         assert np.abs(P[a] - g[key].reshape(P[a].shape)).max() < 1e-13
 
@@ -477,3 +477,121 @@ def test_one_handle_survives_growing_structures():
         assert np.abs(F.reshape(n, len(Z), 3) - g["forces"][None]).max() < TOL_F
         assert np.abs(stress_of(W, C) - g["stress"]).max() < TOL_S
     eng.close()
+
+
+def test_similarity_interface_on_environments_and_cached_engine():
+    """the kernel mirrors take environments (reference ``Local``-like objects or tuples) on either
+    side, keep ONE engine per inducing set, and expose precalculate / call_descriptor (similarity/universal.py:97-107)."""
+    import types
+
+    import autoforce_b200 as ab
+    from autoforce_b200 import engine as eng_mod
+
+    g = load_golden("lipso108")
+    k = g["meta"]["kernel"]
+    kern = ab.SeSoapKernel(k["lmax"], k["nmax"], k["xi"], k["rc"], radii=ab.DefaultRadii())
+    atoms = types.SimpleNamespace(positions=g["pos"], numbers=g["numbers"], cell=g["cell"], pbc=g["meta"]["pbc"])
+    X = [types.SimpleNamespace(number=int(z), _r=r, _b=b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    created = []
+    orig = eng_mod.SgprEngine.__init__
+
+    def counting(self, *a, **kw):
+        created.append(1)
+        orig(self, *a, **kw)
+
+    eng_mod.SgprEngine.__init__ = counting
+    try:
+        K1 = kern(atoms, X)
+        K2 = kern(atoms, X)
+        assert len(created) == 1, "the engine of an inducing set must be cached"
+        assert np.abs(K1 - g["K"]).max() < 1e-12 and np.array_equal(K1, K2)
+        # a grown inducing set extends the cached engine in place
+        extra = types.SimpleNamespace(number=int(g["ind_Z"][0]), _r=g["envs_r"][0] * 1.01, _b=g["envs_b"][0])
+        K3 = kern(atoms, X + [extra])
+        assert len(created) == 1 and K3.shape[1] == len(X) + 1 and np.abs(K3[:, :-1] - g["K"]).max() < 1e-12
+    finally:
+        eng_mod.SgprEngine.__init__ = orig
+    # environments on the left: kern(X, X) is the M x M matrix; it equals the oracle's and has a unit diagonal
+    KXX = kern(X, X)
+    om = oracle_model(g)
+    species = np.array(g["meta"]["species"])
+    Zh, lone = o.inducing_descriptors(om, species)
+    Ko, _, _ = o.kernel_from_descriptors(om, Zh, np.asarray(g["ind_Z"], dtype=np.int64), lone, Zh, lone)
+    assert KXX.shape == (len(X), len(X)) and np.abs(KXX - Ko).max() < 1e-12
+    assert np.abs(np.diag(KXX) - 1.0).max() < 1e-12
+    # one environment against the set: a row of the same matrix
+    assert np.abs(kern(X[3], X) - KXX[3:4]).max() < 1e-13
+    # a structure on the right stands for all of its environments: kern(atoms, atoms) (calculator/active.py:655)
+    Kaa = kern(atoms, atoms)
+    assert Kaa.shape == (len(g["numbers"]), len(g["numbers"])) and np.abs(np.diag(Kaa) - 1.0).max() < 1e-12
+    assert np.abs(Kaa - Kaa.T).max() < 1e-12
+    # call_descriptor / precalculate: the reference's sparse [120, 120, dim] cache (loc.kern_0_value)
+    d = kern.call_descriptor(X[0]).to_dense().numpy()
+    ref = g["ind_desc"][0].reshape(len(species), len(species), -1)
+    for a, z1 in enumerate(species):
+        for b, z2 in enumerate(species):
+            assert np.abs(d[z2, z1] - ref[a, b]).max() < 1e-13
+    assert kern.precalculate(X[0]) is not None and X[0].kern_0_value is not None
+    lone_loc = types.SimpleNamespace(number=3, _r=np.zeros((0, 3)), _b=np.zeros(0, dtype=np.int64))
+    assert kern.precalculate(lone_loc) is None and lone_loc.kern_0_value is None
+    kern.close()
+
+
+def test_fixed_central_species_kernel():
+    """a kernel with a fixed central species (a=Z) must only produce rows for that species."""
+    import types
+
+    import autoforce_b200 as ab
+
+    g = load_golden("afixed_2sp")
+    k = g["meta"]["kernel"]
+    kern = ab.SeSoapKernel(k["lmax"], k["nmax"], k["xi"], k["rc"], a=k["a"], radii=ab.DefaultRadii())
+    atoms = types.SimpleNamespace(positions=g["pos"], numbers=g["numbers"], cell=g["cell"], pbc=g["meta"]["pbc"])
+    X = [(int(z), r, b) for z, r, b in zip(g["ind_Z"], g["envs_r"], g["envs_b"])]
+    K = kern(atoms, X)
+    assert np.abs(K - g["K"]).max() < 1e-12
+    assert np.abs(K[np.asarray(g["numbers"]) != k["a"]]).max() == 0.0
+    kern.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_memory_exchange_emulated_on_one_gpu(case, world):
+    """The force exchange bench.py --gpus N uses (sgpr_predict_p2p + sgpr_p2p_collect): every emulated rank evaluates
+    only the environments it owns and adds neighbour forces into the OWNER's accumulation buffer.  Here the peer table
+    points at ``world`` local buffers of one GPU (one handle per emulated rank); the assembled result must equal the
+    unsharded one.  (tools/p2p_check.py runs the same comparison over real NVLink peers under torchrun.)"""
+    import torch
+
+    import autoforce_b200 as ab
+
+    g, eng0 = case
+    N = len(g["numbers"])
+    E0, F0, W0, _ = eng0.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    dev = torch.device("cuda", 0)
+    pos_t = torch.as_tensor(np.asarray(g["pos"], dtype=np.float64), device=dev)
+    z_t = torch.as_tensor(np.asarray(g["numbers"], dtype=np.int32), device=dev)
+    bufs = torch.zeros((world, 3 * N + 8), dtype=torch.float64, device=dev)
+    ews = torch.zeros((world, 10), dtype=torch.float64, device=dev)
+    engines = [ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"]) for _ in range(world)]
+    try:
+        ptrs = [bufs[r].data_ptr() for r in range(world)]
+        for r, e in enumerate(engines):
+            e.predict_p2p(pos_t, z_t, g["cell"], g["meta"]["pbc"], r, world, ptrs, ews[r])
+        torch.cuda.synchronize()
+        F = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+        covered = torch.zeros(N, dtype=torch.int32, device=dev)
+        for r, e in enumerate(engines):
+            Fr = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+            own = torch.zeros(N, dtype=torch.uint8, device=dev)
+            e.p2p_collect(bufs[r], Fr, own)
+            torch.cuda.synchronize()
+            F += Fr * own.to(torch.float64)[:, None]
+            covered += own.to(torch.int32)
+        assert bool((covered == 1).all()), "every atom is owned by exactly one rank"
+        ew = ews.sum(dim=0).cpu().numpy()
+        assert abs(ew[0] - E0) / N < 1e-12
+        assert np.abs(F.cpu().numpy() - F0).max() < 1e-10
+        assert np.abs(ew[1:].reshape(3, 3) - W0).max() < 1e-9
+    finally:
+        for e in engines:
+            e.close()

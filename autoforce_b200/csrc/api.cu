@@ -5,9 +5,18 @@
 #include <algorithm>
 #include <cmath>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sgpr_internal.cuh"
 
 namespace sgpr {
+
+// NVTX ranges on the reference's timing nodes (calculator/active.py:427-535: nl+desc | kernel | results | active):
+// here nl / desc / gemm / force / covloss, visible in Nsight Systems / Compute next to the kernels they enclose.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local char g_err[1024] = "";
 
@@ -777,6 +786,13 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     SGPR_TRY(build_geometry(h, N, pos_d, cell_h, pbc_h, st, g));
     h->last_geom = *g;
     if (h->timing) cudaEventRecord(h->ev[0], st);
+    nvtxRangePushA("sgpr:nl");
+    struct PopOnExit {
+        bool armed = true;
+        ~PopOnExit() {
+            if (armed) nvtxRangePop();
+        }
+    } nl_range;
     SGPR_TRY(cell_sort(h, N, pos_d, Z_d, *g, st));
     // neighbour list (+ halo when sharded); species row ranges come back with the pair count
     int64_t n_pairs = 0;
@@ -786,6 +802,9 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
         SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs, with_halo));
     h->stats.n_active = h->n_active;
     h->stats.n_pairs = n_pairs;
+    nl_range.armed = false;
+    nvtxRangePop();
+    NvtxRange desc_range("sgpr:desc");
     if (h->timing) cudaEventRecord(h->ev[1], st);
     SGPR_TRY(h->phat.ensure(sizeof(double) * ((size_t)h->n_active + 1) * h->dp.ldp));
     if (h->use_i8_now) SGPR_TRY(i8_ensure_step_buffers(h, (size_t)h->n_active, with_k8));
@@ -854,6 +873,13 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
     if (!peer_f_h) SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
     if (beta_d && !h->use_i8_now) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
+    nvtxRangePushA("sgpr:gemm");
+    struct PopGemm {
+        bool armed = true;
+        ~PopGemm() {
+            if (armed) nvtxRangePop();
+        }
+    } gemm_range;
     if (h->use_i8_now)
         SGPR_TRY(i8_kernel_matrix(h, st, beta_d != nullptr));
     else
@@ -867,6 +893,9 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     else
         SGPR_TRY(gemm_back_projection(h, st));
     if (h->timing) cudaEventRecord(h->ev[3], st);
+    gemm_range.armed = false;
+    nvtxRangePop();
+    NvtxRange force_range("sgpr:force");
     SGPR_TRY(descriptor_backward_atoms(h, g, owned, st, peer_f_h ? &peers : nullptr));
     if (N > 0) {
         atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, active, h->atoms.as<AtomRec>(),
@@ -885,6 +914,7 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     if (h->timing) cudaEventRecord(h->ev[4], st);
     h->stats.covloss_flops = 0.0;
     if (beta_d) {
+        NvtxRange covloss_range("sgpr:covloss");
         const int n_part = h->use_i8_now ? i8_covloss_parts(h) : gemm_covloss_parts(h);
         SGPR_TRY(h->cpart.ensure(sizeof(double) * (size_t)n_part * nrows));
         SGPR_CUDA(cudaMemsetAsync(beta_d, 0, sizeof(double) * (size_t)N, st));

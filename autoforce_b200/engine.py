@@ -193,7 +193,7 @@ class SgprEngine:
         self.lib = load_library()
         self.model = model
         self.device = int(device)
-        self.species = sorted(set(model.species()) | set(int(z) for z in (species or [])))
+        self.species = sorted(set(model.species()) | set(int(z) for z in (species if species is not None else [])))
         if len(self.species) > MAX_SPECIES:
             raise ValueError(f"at most {MAX_SPECIES} species are supported, got {self.species}")
         self._h = c_void_p()

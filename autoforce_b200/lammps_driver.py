@@ -10,6 +10,8 @@ types to atomic numbers, and the fix must be called ``autoforce``: ``fix autofor
 """
 from __future__ import annotations
 
+import ast
+import re
 import types
 
 import numpy as np
@@ -37,30 +39,61 @@ def convert(value, quantity, fromunits, tounits):
     return value
 
 
+_DIRECTIVE = re.compile(r"^#\s*autoforce\b(.*)$", re.IGNORECASE)
+_ASSIGN = re.compile(r"^\s*([A-Za-z_]\w*)\s*=\s*(.+?)\s*$")
+
+
+class LammpsInput:
+    """A LAMMPS input script as the AutoForce driver sees it (conventions of cl/lmp.py:8-33).
+
+    * ``#autoforce name = <python literal>`` comment lines are directives; ``atomic_numbers = {type: Z, ...}`` is
+      mandatory.  The value is parsed with ``ast.literal_eval`` (the reference ``exec``s the line; a literal is all
+      the convention needs, and an input deck should not be able to run code).
+    * everything after ``#`` is a comment; blank lines are dropped; whitespace is normalised.
+    * ``units <style>`` selects the unit style; ``fix autoforce <group> external pf/callback 1 1`` is the fix the
+      callback is attached to -- the commands up to and including it run first, then the callback is set.
+    """
+
+    def __init__(self, text):
+        self.directives, self.commands = {}, []
+        self.units, self.fix_id, self.fix_index = None, None, None
+        for raw in text.splitlines():
+            m = _DIRECTIVE.match(raw.strip())
+            if m:
+                self._directive(m.group(1))
+                continue
+            words = raw.split("#", 1)[0].split()
+            if not words:
+                continue
+            if words[0] == "units" and len(words) > 1:
+                self.units = words[1]
+            if len(words) > 1 and words[0].lower() == "fix" and words[1].lower() == "autoforce":
+                self.fix_id, self.fix_index = words[1], len(self.commands)
+            self.commands.append(" ".join(words))
+        if "atomic_numbers" not in self.directives:
+            raise RuntimeError("no '#autoforce atomic_numbers = {...}' line!")
+        if self.fix_id is None:
+            raise RuntimeError("no fix autoforce!")
+
+    def _directive(self, body):
+        m = _ASSIGN.match(body)
+        if not m:
+            raise RuntimeError(f"cannot parse '#autoforce{body}': expected 'name = literal'")
+        try:
+            self.directives[m.group(1)] = ast.literal_eval(m.group(2))
+        except (ValueError, SyntaxError) as ex:
+            raise RuntimeError(f"'#autoforce {m.group(1)} = ...' is not a Python literal: {ex}") from None
+
+    @property
+    def map_numbers(self):
+        return {int(t): int(z) for t, z in dict(self.directives["atomic_numbers"]).items()}
+
+
 def read_lammps_file(file):
-    """cl/lmp.py:8-33: returns (units, map_numbers, fixID, fixIndex, commands)."""
-    commands, units, fix_id, fix_index = [], None, None, None
-    scope = {}
-    for line in open(file):
-        if line.lower().startswith("#autoforce"):
-            exec(line[10:].strip(), scope)
-            continue
-        if "#" in line:
-            line = line[: line.index("#")]
-        line = " ".join(line.split())
-        if line == "":
-            continue
-        if line.startswith("units"):
-            units = line.split()[1]
-        if line.lower().startswith("fix autoforce"):
-            fix_id = line.split()[1]
-            fix_index = len(commands)
-        commands.append(line)
-    if "atomic_numbers" not in scope:
-        raise RuntimeError("no '#autoforce atomic_numbers = {...}' line!")
-    if fix_id is None:
-        raise RuntimeError("no fix autoforce!")
-    return units, scope["atomic_numbers"], fix_id, fix_index, commands
+    """-> (units, map_numbers, fixID, fixIndex, commands), the tuple cl/lmp.py:8-33 returns."""
+    with open(file) as f:
+        inp = LammpsInput(f.read())
+    return inp.units, inp.map_numbers, inp.fix_id, inp.fix_index, inp.commands
 
 
 class FixExternalCallback:

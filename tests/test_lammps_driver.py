@@ -57,6 +57,11 @@ def test_read_lammps_file(tmp_path):
     g.write_text("#autoforce atomic_numbers = {1: 29}\nunits metal\nrun 1\n")
     with pytest.raises(RuntimeError):
         ld.read_lammps_file(str(g))
+    # directives are literals, never code (the reference exec()s this line, cl/lmp.py:14-16)
+    h = tmp_path / "evil.lammps"
+    h.write_text("#autoforce atomic_numbers = __import__('os').system('true')\nunits metal\nfix autoforce all external pf/callback 1 1\n")
+    with pytest.raises(RuntimeError, match="not a Python literal"):
+        ld.read_lammps_file(str(h))
     lmp = FakeLammps(np.eye(3) * 5, np.zeros((2, 3)), [1, 2])
     cb = ld.run(str(f), FakeCalc(), lmp=lmp)
     assert lmp.commands == [cmds[:3], cmds[3:]] and lmp.cb == ("autoforce", cb)

@@ -123,20 +123,23 @@ __global__ void beta_finish_kernel(int n_active, const int* __restrict__ active,
 // local energies e_r = sum of the per-(column tile, warp) partials written by the kernel-matrix
 // GEMM (fixed order -> reproducible); also block partial sums of the owned rows for the total.
 struct RowSpecies {
-    int row_first[SGPR_MAX_SPECIES + 1];
     int n_part[SGPR_MAX_SPECIES];   // 0 where the species has no usable inducing points
     int S;
 };
-__global__ void row_energy_kernel(int n_rows, RowSpecies rs, const double* __restrict__ part, int part_ld,
+__global__ void row_energy_kernel(int n_rows, RowSpecies rs, const int* __restrict__ row_first,
+                                  const double* __restrict__ part, int part_ld,
                                   const unsigned char* __restrict__ row_owned, double* __restrict__ erow,
                                   double* __restrict__ epart) {
     __shared__ double red[256];
+    __shared__ int rf[SGPR_MAX_SPECIES + 1];
+    if (threadIdx.x <= rs.S) rf[threadIdx.x] = row_first[threadIdx.x];   // species row ranges live on the device
+    __syncthreads();
     double tot = 0.0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         int np = 0;
 #pragma unroll
         for (int s = 0; s < SGPR_MAX_SPECIES; ++s)
-            if (s < rs.S && r >= rs.row_first[s] && r < rs.row_first[s + 1]) np = rs.n_part[s];
+            if (s < rs.S && r >= rf[s] && r < rf[s + 1]) np = rs.n_part[s];
         double e = 0.0;
         for (int p = 0; p < np; ++p) e += part[(size_t)p * part_ld + r];
         erow[r] = e;
@@ -350,6 +353,7 @@ extern "C" __attribute__((visibility("default"))) const char* sgpr_last_error(vo
 extern "C" __attribute__((visibility("default"))) int sgpr_abi_version(void) { return SGPR_ABI_VERSION; }
 
 extern "C" void sgpr_destroy(sgpr_handle h);
+static void drop_graphs(sgpr_context* h);
 
 static int upload(DevBuf& b, const void* src, size_t bytes) {
     SGPR_TRY(b.ensure(bytes ? bytes : 8));
@@ -621,6 +625,12 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     h->xi_int = (d->xi == std::floor(d->xi) && d->xi >= 1 && d->xi <= 64) ? (int)d->xi : -1;
     SGPR_TRY(upload(h->ztab, h->z_to_species, sizeof(int) * 128));
     SGPR_TRY(h->errflag.ensure(sizeof(int) * 4));
+    SGPR_TRY(h->status_d.ensure(sizeof(long long) * 8));
+    SGPR_CUDA(cudaMemset(h->status_d.p, 0, sizeof(long long) * 8));
+    SGPR_CUDA(cudaMallocHost((void**)&h->status_pinned, sizeof(long long) * 8));
+    memset(h->status_pinned, 0, sizeof(long long) * 8);
+    SGPR_TRY(h->row_first_d.ensure(sizeof(int) * (SGPR_MAX_SPECIES + 2)));
+    SGPR_CUDA(cudaMemset(h->row_first_d.p, 0, sizeof(int) * (SGPR_MAX_SPECIES + 2)));
 
     // packed-entry tables
     {
@@ -658,6 +668,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     {   // GEMM engine: tcgen05 int8-sliced (default, needs normalised descriptors) or FP64 DMMA
         const char* nlm = getenv("SGPR_NL");
         h->nl_mode = !nlm ? 0 : strcmp(nlm, "warp") == 0 ? 1 : strcmp(nlm, "bins") == 0 ? 2 : 0;
+        const char* gr = getenv("SGPR_GRAPH");
+        h->use_graph = !(gr && atoi(gr) == 0);
         const char* eng = getenv("SGPR_GEMM");
         const char* trs = getenv("SGPR_I8_TR");
         h->use_i8 = dp.normalize && !(eng && strcmp(eng, "dmma") == 0);
@@ -684,16 +696,18 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    drop_graphs(h);
     DevBuf* bufs[] = {&h->zhat, &h->zhat_t, &h->mu, &h->lone_mu, &h->ptab, &h->nnlk, &h->ztab, &h->errflag,
                       &h->ind_perm_d, &h->sp_on, &h->ind_sp_d, &h->ind_lone_d, &h->mean_w_d, &h->cnt, &h->cstart,
                       &h->rstart, &h->keyrank, &h->atoms, &h->order, &h->rowof, &h->active_list, &h->nl_cnt,
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk, &h->row_first_d, &h->status_d};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
+    if (h->status_pinned) cudaFreeHost(h->status_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (int i = 0; i < 6; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -708,6 +722,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_set_weights(sgpr_hand
     }
     SGPR_CUDA(cudaSetDevice(h->device));
     SGPR_CUDA(cudaDeviceSynchronize());
+    drop_graphs(h);   // weight buffers may be reallocated
+    h->warm_ok = false;
     SGPR_TRY(upload_weights(h, mu_h, mean_w_h, choli_h, vscale_h, nullptr));
     if (mu_h && h->use_i8) SGPR_TRY(i8_prepare_model(h, true));
     if (choli_h && h->use_i8) SGPR_TRY(i8_prepare_covloss(h));
@@ -756,6 +772,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_append_inducing(sgpr_
     }
     h->has_choli = false;
     h->fwd_valid = false;
+    h->warm_ok = false;
+    drop_graphs(h);
     h->i8_cap_rows = 0;   // the K padding of the per-step digit buffers follows max M_s
     SGPR_TRY(upload_weights(h, mu_h, nullptr, choli_h, nullptr, nullptr));
     if (h->use_i8) {
@@ -770,7 +788,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_append_inducing(sgpr_
 // =====================================================================================
 static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                        const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false,
-                       bool with_halo = true, bool with_k8 = false) {
+                       bool with_halo = true, bool with_k8 = false, bool warm = false) {
     h->use_i8_now = i8 && h->use_i8;
     h->stats.i8_ops = 0.0;
     h->fwd_valid = false;
@@ -797,11 +815,11 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     // neighbour list (+ halo when sharded); species row ranges come back with the pair count
     int64_t n_pairs = 0;
     if (world == 1)
-        SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs));  // synchronises the stream
+        SGPR_TRY(neighbor_build(h, N, *g, st, &n_pairs, warm));  // sizing step: synchronises the stream
     else
-        SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs, with_halo));
+        SGPR_TRY(neighbor_build_sharded(h, N, *g, rank, world, st, &n_pairs, with_halo, warm));
     h->stats.n_active = h->n_active;
-    h->stats.n_pairs = n_pairs;
+    if (!warm) h->stats.n_pairs = n_pairs;
     nl_range.armed = false;
     nvtxRangePop();
     NvtxRange desc_range("sgpr:desc");
@@ -813,9 +831,15 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     return SGPR_OK;
 }
 
-static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+static bool warm_possible(sgpr_handle h, int64_t N, const int32_t* pbc_h, int32_t rank, int32_t world, bool p2p, bool beta) {
+    const bool halo_mode = world > 1 && !p2p;
+    return h->use_i8 && pbc_h[0] && pbc_h[1] && pbc_h[2] && !halo_mode && h->warm_ok && N == h->warm_N &&
+           rank == h->warm_rank && world == h->warm_world && beta == h->warm_beta && !h->timing;
+}
+
+static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                         const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
-                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h) {
+                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm) {
     if (!h || !cell_h || !pbc_h || !E_d || (!F_d && !peer_f_h) || !W_d || (N > 0 && (!pos_d || !Z_d))) {
         set_error("null argument");
         return SGPR_ERR_INVALID;
@@ -835,8 +859,15 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
+    // Sync-free ("warm") step: every size the host needs was fixed by an earlier sizing step of the same shape; the
+    // pair count, the species row ranges and the error flags stay on the device (nl.cu: nl_status_kernel).
+    const bool halo_mode = world > 1 && peer_f_h == nullptr;
+    const bool shape_ok = h->use_i8 && pbc_h[0] && pbc_h[1] && pbc_h[2] && !halo_mode;
+    const bool warm = allow_warm && warm_possible(h, N, pbc_h, rank, world, peer_f_h != nullptr, beta_d != nullptr);
+    h->step_was_warm = warm;
     SGPR_TRY(stage_front(h, N, pos_d, Z_d, cell_h, pbc_h, st, &g, rank, world, /*i8=*/true,
-                         /*with_halo=*/peer_f_h == nullptr, /*with_k8=*/beta_d != nullptr));
+                         /*with_halo=*/peer_f_h == nullptr, /*with_k8=*/beta_d != nullptr, warm));
+    if (h->use_i8_now) SGPR_TRY(i8_setup_step(h, st));
     PeerForces peers{};
     if (peer_f_h) {
         peers.world = world;
@@ -856,7 +887,6 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     RowSpecies rs{};
     rs.S = h->S;
     int max_part = 1;
-    for (int s = 0; s <= h->S; ++s) rs.row_first[s] = h->row_first[s];
     for (int s = 0; s < h->S; ++s) {
         const int Ms = h->m_first[s + 1] - h->m_first[s];
         rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? (h->use_i8_now ? i8_energy_parts(Ms) : gemm_energy_parts(Ms)) : 0;
@@ -884,8 +914,8 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
         SGPR_TRY(i8_kernel_matrix(h, st, beta_d != nullptr));
     else
         SGPR_TRY(gemm_kernel_matrix(h, nullptr, 0, nullptr, beta_d != nullptr, st));
-    row_energy_kernel<<<grid_g, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows,
-                                              h->active_all ? nullptr : h->row_owned.as<unsigned char>(),
+    row_energy_kernel<<<grid_g, 256, 0, st>>>((int)h->n_active, rs, h->row_first_d.as<int>(), h->erow_part.as<double>(),
+                                              (int)nrows, h->active_all ? nullptr : h->row_owned.as<unsigned char>(),
                                               h->erow.as<double>(), h->epart.as<double>());
     h->stats.kernel_launches += 1;
     if (h->use_i8_now)
@@ -934,6 +964,18 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
         }
         SGPR_CUDA(cudaGetLastError());
     }
+    if (warm) {
+        // the step's status (pair count, validity) follows the results to the host; nobody waits for it here
+        SGPR_CUDA(cudaMemcpyAsync(h->status_pinned, h->status_d.p, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st));
+    } else if (shape_ok) {
+        h->warm_ok = true;
+        h->warm_N = N;
+        h->warm_rank = rank;
+        h->warm_world = world;
+        h->warm_beta = beta_d != nullptr;
+    } else {
+        h->warm_ok = false;
+    }
     if (h->timing) {
         cudaEventRecord(h->ev[5], st);
         SGPR_CUDA(cudaEventSynchronize(h->ev[5]));
@@ -947,10 +989,126 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     return SGPR_OK;
 }
 
+// A warm step is the same launch sequence with the same arguments every time (same shape, same buffers, same cell):
+// it is captured ONCE into a CUDA graph and replayed with a single cudaGraphLaunch afterwards -- ~30 kernel launches,
+// memsets and the status copy collapse into one submission, which is what bounds small systems and multi-GPU shards.
+// Graphs are keyed by everything that is baked into the nodes.
+static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
+                        const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
+                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm) {
+    if (!h || !pbc_h || !cell_h || !h->use_graph || !allow_warm || world > SGPR_MAX_RANKS ||
+        !warm_possible(h, N, pbc_h, rank, world, peer_f_h != nullptr, beta_d != nullptr))
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+    cudaStream_t st = (cudaStream_t)stream;
+    SGPR_CUDA(cudaSetDevice(h->device));
+    sgpr_context::GraphKey key{};
+    key.N = N;
+    key.rank = rank;
+    key.world = world;
+    key.stream = stream;
+    key.ptr[0] = pos_d; key.ptr[1] = Z_d; key.ptr[2] = E_d; key.ptr[3] = F_d; key.ptr[4] = W_d; key.ptr[5] = beta_d; key.ptr[6] = owned_d;
+    for (int r = 0; r < SGPR_MAX_RANKS; ++r) key.peer[r] = (peer_f_h && r < world) ? peer_f_h[r] : 0;
+    for (int i = 0; i < 9; ++i) key.cell[i] = cell_h[i];
+    for (auto& e : h->graphs) {
+        if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+            e.stamp = ++h->graph_clock;
+            h->step_was_warm = true;
+            h->stats.kernel_launches = e.launches;
+            SGPR_CUDA(cudaGraphLaunch(e.exec, st));
+            return SGPR_OK;
+        }
+    }
+    // first warm step of this key: record it
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();   // e.g. the legacy default stream cannot be captured: run the step directly
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+    }
+    const int rc = predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != SGPR_OK || ce != cudaSuccess || !graph || !h->step_was_warm) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->use_graph = false;   // something in the sequence is not capturable here: plain launches from now on
+        h->warm_ok = false;     // (whatever was enqueued during the failed capture never ran)
+        if (rc != SGPR_OK) return rc;
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false);
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->use_graph = false;
+        h->warm_ok = false;
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false);
+    }
+    cudaGraphDestroy(graph);
+    if (h->graphs.size() >= 16) {   // evict the least recently used entry
+        size_t lru = 0;
+        for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+        cudaGraphExecDestroy(h->graphs[lru].exec);
+        h->graphs.erase(h->graphs.begin() + lru);
+    }
+    sgpr_context::GraphEntry e;
+    e.key = key;
+    e.exec = exec;
+    e.stamp = ++h->graph_clock;
+    e.launches = h->stats.kernel_launches;
+    h->graphs.push_back(e);
+    SGPR_CUDA(cudaGraphLaunch(exec, st));
+    return SGPR_OK;
+}
+
+static void drop_graphs(sgpr_context* h) {
+    for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
+    h->graphs.clear();
+}
+
 extern "C" __attribute__((visibility("default"))) int sgpr_predict(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                             const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
                             double* W_d, double* beta_d, uint8_t* owned_d) {
-    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, nullptr);
+    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, nullptr,
+                        h && h->async_mode);
+}
+
+// Asynchronous mode of the device-pointer entry points (sgpr_predict, sgpr_predict_p2p): once a sizing step of the same
+// shape has run, later steps enqueue their whole kernel sequence without any device-to-host copy or synchronisation.
+// The price: a step whose pair list outgrew the capacity (or that met an unknown species) cannot report it from the
+// call that enqueued it -- sgpr_check() does, after the caller synchronised the stream.
+extern "C" __attribute__((visibility("default"))) int sgpr_set_async(sgpr_handle h, int32_t on) {
+    if (!h) {
+        set_error("null handle");
+        return SGPR_ERR_INVALID;
+    }
+    h->async_mode = on != 0;
+    return SGPR_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sgpr_check(sgpr_handle h, int64_t* n_pairs_out) {
+    if (!h) {
+        set_error("null handle");
+        return SGPR_ERR_INVALID;
+    }
+    SGPR_CUDA(cudaSetDevice(h->device));
+    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (h->status_d.p) SGPR_CUDA(cudaMemcpy(st, h->status_d.p, sizeof(st), cudaMemcpyDeviceToHost));
+    if (n_pairs_out) *n_pairs_out = h->step_was_warm ? st[0] : h->stats.n_pairs;
+    if (h->step_was_warm) h->stats.n_pairs = st[0];
+    if (st[1] != h->bad_steps_seen) {
+        const long long n_bad = st[1] - h->bad_steps_seen;
+        h->bad_steps_seen = st[1];
+        h->warm_ok = false;   // the next step sizes its buffers again
+        if (st[2] == 1)
+            set_error("%lld asynchronous step(s) invalid: atomic number %lld is not in the handle's species table", n_bad, st[3]);
+        else if (st[2] == 2)
+            set_error("%lld asynchronous step(s) invalid: an atom lies more than 120 cells outside the unit cell", n_bad);
+        else
+            set_error("%lld asynchronous step(s) invalid: %lld neighbour pairs exceed the capacity %lld sized by an earlier step; "
+                      "repeat the step (it will size its buffers again)", n_bad, st[4], st[5]);
+        return st[2] == 1 ? SGPR_ERR_SPECIES : st[2] == 2 ? SGPR_ERR_GEOMETRY : SGPR_ERR_RETRY;
+    }
+    return SGPR_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int sgpr_predict_p2p(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
@@ -964,7 +1122,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_p2p(sgpr_hand
         set_error("sgpr_predict_p2p needs world > 1 (use sgpr_predict)");
         return SGPR_ERR_INVALID;
     }
-    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f_h);
+    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f_h,
+                        h && h->async_mode);
 }
 
 extern "C" __attribute__((visibility("default"))) int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double* F_d, uint8_t* owned_d) {
@@ -1027,18 +1186,28 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_host(sgpr_han
     double* out_d = h->stage_out.as<double>();  // [E(1) pad(6) W(9) F(3N) beta(N)]
     double* beta_d = beta_h ? out_d + 16 + 3 * (size_t)N : nullptr;
     uint8_t* own_d = owned_h ? (uint8_t*)(out_d + 16 + (beta_h ? 4 : 3) * (size_t)N) : nullptr;
-    SGPR_TRY(sgpr_predict(h, N, h->stage_pos.as<double>(), h->stage_z.as<int32_t>(), cell_h, pbc_h, rank, world, st,
-                          out_d, out_d + 16, out_d + 7, beta_d, own_d));
-    if (f_pinned) {
-        SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
-        SGPR_CUDA(cudaMemcpyAsync(F_h, out_d + 16, nb_pos, cudaMemcpyDeviceToHost, st));
-        if (beta_h)
-            SGPR_CUDA(cudaMemcpyAsync(pin_out + 16 + 3 * (size_t)N, beta_d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
-    } else {
-        SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
+    // The step runs without any host synchronisation when an earlier step of the same shape sized the buffers; its
+    // status block arrives with the results.  An invalid step (pair list outgrew the capacity) is simply repeated
+    // as a sizing step: the caller always gets exact results or an error from THIS call.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SGPR_TRY(predict_impl(h, N, h->stage_pos.as<double>(), h->stage_z.as<int32_t>(), cell_h, pbc_h, rank, world, st, out_d,
+                              out_d + 16, out_d + 7, beta_d, own_d, nullptr, /*allow_warm=*/attempt == 0));
+        if (f_pinned) {
+            SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
+            SGPR_CUDA(cudaMemcpyAsync(F_h, out_d + 16, nb_pos, cudaMemcpyDeviceToHost, st));
+            if (beta_h)
+                SGPR_CUDA(cudaMemcpyAsync(pin_out + 16 + 3 * (size_t)N, beta_d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+        } else {
+            SGPR_CUDA(cudaMemcpyAsync(pin_out, out_d, nb_out, cudaMemcpyDeviceToHost, st));
+        }
+        if (owned_h) SGPR_CUDA(cudaMemcpyAsync(pin_own, own_d, (size_t)N, cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaStreamSynchronize(st));
+        if (!h->step_was_warm) break;
+        h->stats.n_pairs = h->status_pinned[0];
+        if (h->status_pinned[6] == 0) break;
+        h->bad_steps_seen = h->status_pinned[1];
+        h->warm_ok = false;
     }
-    if (owned_h) SGPR_CUDA(cudaMemcpyAsync(pin_own, own_d, (size_t)N, cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaStreamSynchronize(st));
     E_h[0] = pin_out[0];
     memcpy(W_h, pin_out + 7, sizeof(double) * 9);
     if (!f_pinned) memcpy(F_h, pin_out + 16, nb_pos);
@@ -1106,7 +1275,6 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_
     RowSpecies rs{};
     rs.S = h->S;
     int max_part = 1;
-    for (int s = 0; s <= h->S; ++s) rs.row_first[s] = h->row_first[s];
     for (int s = 0; s < h->S; ++s) {
         const int Ms = h->m_first[s + 1] - h->m_first[s];
         rs.n_part[s] = (Ms > 0 && h->dp.central_enabled[s]) ? gemm_energy_parts(Ms) : 0;
@@ -1125,8 +1293,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_
     h->use_i8_now = false;
     if (N > 0 && h->M > 0) {
         SGPR_TRY(gemm_kernel_matrix(h, nullptr, h->M, h->rowmap.as<int>(), false, st, gK_d));
-        row_energy_kernel<<<grid_e, 256, 0, st>>>((int)h->n_active, rs, h->erow_part.as<double>(), (int)nrows, nullptr,
-                                                  h->erow.as<double>(), h->epart.as<double>());
+        row_energy_kernel<<<grid_e, 256, 0, st>>>((int)h->n_active, rs, h->row_first_d.as<int>(), h->erow_part.as<double>(),
+                                                  (int)nrows, nullptr, h->erow.as<double>(), h->epart.as<double>());
         SGPR_TRY(gemm_back_projection(h, st));
         SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
     }

@@ -115,16 +115,17 @@ constexpr int kNS = 6;
 
 struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
     const double* mu[kMaxSpecies];       // per problem: mu of the species' inducing block
-    double* erow_part[kMaxSpecies];      // + r0
-    signed char* g8[kMaxSpecies];        // + r0 * Mp   (slice 0)
-    signed char* k8[kMaxSpecies];        // + r0 * Mp; digits of k^xi for the covloss GEMM (nullptr: not wanted)
+    double* erow_part;                   // [parts][erow_ld]
+    signed char* g8;                     // slice 0, row 0
+    signed char* k8;                     // digits of k^xi for the covloss GEMM (nullptr: not wanted)
     int erow_ld;
     int Mp;
     long long g8_slice;                  // bytes between slices
     double xi;
     int xi_int;
-    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
         if (row >= M) return;
+        row += row0;
         const double* mup = mu[p];
         double pw[16];
         // k^(xi-1): the usual exponents unrolled (independent multiplies), anything else by pow()
@@ -170,12 +171,12 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
                 w.y = (int)gather_byte(u + 4, b);
                 w.z = (int)gather_byte(u + 8, b);
                 w.w = (int)gather_byte(u + 12, b);
-                *reinterpret_cast<int4*>(g8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+                *reinterpret_cast<int4*>(g8 + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
             }
         }
         // energy partial of this 16-column chunk
-        erow_part[p][(long long)(col0 >> 4) * erow_ld + row] = e;
-        if (k8[p] != nullptr && col0 < Mp) {   // K = k^xi, the A operand of the covloss GEMM
+        erow_part[(long long)(col0 >> 4) * erow_ld + row] = e;
+        if (k8 != nullptr && col0 < Mp) {   // K = k^xi, the A operand of the covloss GEMM
 #pragma unroll
             for (int j = 0; j < 16; ++j) u[j] = digit_bytes<kNS>(col0 + j < N ? pw[j] * v[j] : 0.0);
 #pragma unroll
@@ -186,7 +187,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
                 w.y = (int)gather_byte(u + 4, b);
                 w.z = (int)gather_byte(u + 8, b);
                 w.w = (int)gather_byte(u + 12, b);
-                *reinterpret_cast<int4*>(k8[p] + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+                *reinterpret_cast<int4*>(k8 + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
             }
         }
     }
@@ -194,10 +195,11 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
 
 struct Epi3 {   // covloss: per-row partial sums of squares of b = K . choli^T  (calculator/active.py:781-783)
     const double* rs[kMaxSpecies];       // power-of-two scales of the choli rows (= output columns)
-    double* part[kMaxSpecies];           // + r0
+    double* part;                        // [parts][part_ld]
     int part_ld;
-    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
         if (row >= M) return;
+        row += row0;
         const double* r = rs[p];
         double s = 0.0;
 #pragma unroll
@@ -205,17 +207,17 @@ struct Epi3 {   // covloss: per-row partial sums of squares of b = K . choli^T  
             const double t = col0 + j < N ? v[j] * r[col0 + j] : 0.0;
             s = fma(t, t, s);
         }
-        part[p][(long long)(col0 >> 4) * part_ld + row] = s;
+        part[(long long)(col0 >> 4) * part_ld + row] = s;
     }
 };
 
 struct Epi2 {   // back projection: g = mumax * C
-    double* gvec[kMaxSpecies];           // + r0 * ldp
+    double* gvec;                        // [rows][ldp]
     int ldp;
     double mumax;
-    __device__ void operator()(int p, int row, int col0, const double* v, int M, int N) const {
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
         if (row >= M) return;
-        double* dst = gvec[p] + (long long)row * ldp + col0;
+        double* dst = gvec + (long long)(row0 + row) * ldp + col0;
         if (col0 + 16 <= N) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(v[j] * mumax, v[j + 1] * mumax);
@@ -228,7 +230,7 @@ struct Epi2 {   // back projection: g = mumax * C
 };
 
 template <int NS, int TR, class Epi>
-int launch_ns(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
+int launch_ns(sgpr_context* h, const Common* cm_d, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
     constexpr int STAGES = 3;
     auto kern = i8gemm_kernel<NS, TR, STAGES, Epi>;
     const size_t smem = smem_bytes<NS, STAGES>();
@@ -237,18 +239,42 @@ int launch_ns(sgpr_context* h, const Common& cm, const Problem* probs_d, const E
         SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
-    int grid = h->sm_count;
-    if (cm.tile_start[cm.n_prob] < grid) grid = cm.tile_start[cm.n_prob];
-    if (grid < 1) return SGPR_OK;
-    kern<<<grid, NTHREADS, smem, st>>>(cm, probs_d, epi);
+    // persistent: one CTA per SM; the tile count lives on the device (CTAs beyond it exit at once)
+    kern<<<h->sm_count, NTHREADS, smem, st>>>(cm_d, probs_d, epi);
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
 }
 
 template <int TR, class Epi>
-int launch(sgpr_context* h, const Common& cm, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
-    return launch_ns<kNS, TR, Epi>(h, cm, probs_d, epi, st);
+int launch(sgpr_context* h, const Common* cm_d, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
+    return launch_ns<kNS, TR, Epi>(h, cm_d, probs_d, epi, st);
+}
+
+// Work lists of the three grouped GEMMs from the species row ranges on the device (one warp).
+typedef I8Setup SetupDesc;
+__global__ void i8_setup_kernel(SetupDesc sd, const int* __restrict__ row_first, Common* __restrict__ out) {
+    if (threadIdx.x >= 3) return;
+    const int w = threadIdx.x;
+    Common cm;
+    cm.n_prob = sd.n_prob;
+    int t = 0;
+    for (int p = 0; p < 8; ++p) {
+        cm.tile_start[p] = t;
+        cm.row0[p] = 0;
+        cm.M[p] = 0;
+        if (p < sd.n_prob) {
+            const int s = sd.species[p];
+            const int r0 = row_first[s], r1 = row_first[s + 1];
+            cm.row0[p] = r0;
+            cm.M[p] = r1 - r0;
+            t += ((r1 - r0 + BM - 1) / BM) * ((sd.ncol[w][p] + BN - 1) / BN);
+        }
+    }
+    cm.tile_start[8] = t;
+    // tile_start[n_prob] is the total the kernel reads
+    for (int p = sd.n_prob; p < 9; ++p) cm.tile_start[p] = t;
+    out[w] = cm;
 }
 
 }  // namespace
@@ -263,6 +289,7 @@ int i8_prepare_model(sgpr_context* h, bool weights_only) {
     int maxMs = 0;
     for (int s = 0; s < S; ++s) maxMs = std::max(maxMs, h->m_first[s + 1] - h->m_first[s]);
     h->i8_mp = std::max(64, (maxMs + 63) / 64 * 64);
+    h->i8_model_version++;
     if (M == 0) return SGPR_OK;
     if (!weights_only) {
         SGPR_TRY(h->z8.ensure((size_t)kNS * M * h->i8_kp1 + 64));
@@ -357,105 +384,154 @@ int i8_ensure_step_buffers(sgpr_context* h, size_t n_rows, bool with_k8) {
     return SGPR_OK;
 }
 
-static int build_problems(sgpr_context* h, int which, Common& cm, std::vector<Problem>& probs, int* prob_species) {
+// Problem descriptors (tensor maps over the WHOLE operand buffers + static shapes) of GEMM `which`; they depend only on
+// the model and on the buffer addresses, not on the step: rebuilt and uploaded when those change.
+static int build_problems(sgpr_context* h, int which, std::vector<Problem>& probs, SetupDesc& sd) {
     const DescParams& dp = h->dp;
-    cm = Common{};
     probs.clear();
+    sd.n_prob = 0;
+    const long long cap = (long long)h->i8_cap_rows;
     for (int s = 0; s < h->S; ++s) {
-        const int r0 = h->row_first[s], r1 = h->row_first[s + 1];
         const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
-        if (r1 == r0 || m1 == m0 || !dp.central_enabled[s]) continue;
+        if (m1 == m0 || !dp.central_enabled[s]) continue;
         Problem P;
         P.nk_tn = nullptr;
+        P.M = 0;
         if (which == 1) {
-            P.M = r1 - r0;
             P.N = m1 - m0;
             P.Kpad = h->i8_kp1;
-            SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>() + (size_t)r0 * h->i8_kp1, kNS, P.M, P.Kpad, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>(), kNS, cap, P.Kpad, cap, BM));
             SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * h->i8_kp1, kNS, P.N, P.Kpad, (long long)h->M, BN));
         } else if (which == 2) {
-            P.M = r1 - r0;
             P.N = dp.D;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
             // t + u <= 6 uses the 5 most significant digit slices of both operands (same buffers, same slice stride)
             const int ns2 = h->i8_tr2 == 6 ? 5 : kNS;
-            SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>() + (size_t)r0 * h->i8_mp, ns2, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>(), ns2, cap, h->i8_mp, cap, BM));
             SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, ns2, dp.D, h->i8_mp, (long long)dp.D, BN));
         } else {
-            P.M = r1 - r0;
             P.N = h->M;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
-            SGPR_TRY(make_map(&P.mapA, h->k8.as<signed char>() + (size_t)r0 * h->i8_mp, kNS, P.M, h->i8_mp, (long long)h->i8_cap_rows, BM));
+            SGPR_TRY(make_map(&P.mapA, h->k8.as<signed char>(), kNS, cap, h->i8_mp, cap, BM));
             SGPR_TRY(make_map(&P.mapB, h->c8.as<signed char>() + (size_t)s * kNS * h->M * h->i8_mp, kNS, h->M, h->i8_mp, (long long)h->M, BN));
             const int ntn = (h->M + BN - 1) / BN;
             if (h->cov_nk.p) P.nk_tn = h->cov_nk.as<int>() + (size_t)s * ntn;
         }
-        prob_species[cm.n_prob] = s;
-        cm.tile_start[cm.n_prob + 1] = cm.tile_start[cm.n_prob] + ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN);
-        cm.n_prob++;
+        sd.species[sd.n_prob] = s;
+        sd.ncol[0][sd.n_prob] = m1 - m0;
+        sd.ncol[1][sd.n_prob] = dp.D;
+        sd.ncol[2][sd.n_prob] = h->M;
+        sd.n_prob++;
         probs.push_back(P);
-        if (which == 3) {
-            // algorithmic flops of the dense product; the zero part of a triangular choli is skipped, not counted less
-            h->stats.covloss_flops += 2.0 * P.M * (double)P.N * (m1 - m0);
-        } else {
-            const int tr = which == 2 ? h->i8_tr2 : h->i8_tr;
-            const int npairs = tr == 8 ? 26 : tr == 6 ? 15 : 21;
-            h->stats.gemm_flops += 2.0 * P.M * (double)P.N * (which == 1 ? dp.D : (m1 - m0));
-            h->stats.i8_ops += 2.0 * P.M * (double)P.N * P.Kpad * npairs;
-        }
     }
     return SGPR_OK;
 }
 
-static int upload_problems(sgpr_context* h, int slot, const std::vector<Problem>& probs, cudaStream_t st, const Problem** out) {
-    SGPR_TRY(h->i8_probs.ensure(sizeof(Problem) * 3 * kMaxSpecies));
+// algorithmic work of the step's GEMMs (needs the species row ranges on the host: sizing steps only)
+static void count_work(sgpr_context* h, int which) {
+    const DescParams& dp = h->dp;
+    if (!h->row_first_host_valid) return;
+    for (int s = 0; s < h->S; ++s) {
+        const int r0 = h->row_first[s], r1 = h->row_first[s + 1];
+        const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
+        if (r1 == r0 || m1 == m0 || !dp.central_enabled[s]) continue;
+        const double M = r1 - r0;
+        if (which == 3) {
+            // algorithmic flops of the dense product; the zero part of a triangular choli is skipped, not counted less
+            h->stats.covloss_flops += 2.0 * M * (double)h->M * (m1 - m0);
+        } else {
+            const int tr = which == 2 ? h->i8_tr2 : h->i8_tr;
+            const int npairs = tr == 8 ? 26 : tr == 6 ? 15 : 21;
+            const double N = which == 1 ? (m1 - m0) : dp.D;
+            const double Kpad = which == 1 ? h->i8_kp1 : ((m1 - m0) + 63) / 64 * 64;
+            h->stats.gemm_flops += 2.0 * M * N * (which == 1 ? dp.D : (m1 - m0));
+            h->stats.i8_ops += 2.0 * M * N * Kpad * npairs;
+        }
+    }
+}
+
+// Problems of GEMM `which` on the device (slot which-1), re-uploaded only when the model or a buffer moved.
+static int device_problems(sgpr_context* h, int which, cudaStream_t st, const Problem** out, SetupDesc* sd_out) {
+    SGPR_TRY(h->i8_probs.ensure(sizeof(Problem) * 3 * kMaxSpecies + sizeof(Common) * 4));
     if (!h->i8_probs_pinned) SGPR_CUDA(cudaMallocHost(&h->i8_probs_pinned, sizeof(Problem) * 3 * kMaxSpecies));
-    Problem* pin = (Problem*)h->i8_probs_pinned + slot * kMaxSpecies;
+    const int slot = which - 1;
+    // signature of everything the descriptors encode
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)(uintptr_t)h->p8.p); mix((unsigned long long)(uintptr_t)h->g8.p); mix((unsigned long long)(uintptr_t)h->k8.p);
+    mix((unsigned long long)(uintptr_t)h->z8.p); mix((unsigned long long)(uintptr_t)h->zt8.p); mix((unsigned long long)(uintptr_t)h->c8.p);
+    mix((unsigned long long)(uintptr_t)h->cov_nk.p); mix((unsigned long long)(uintptr_t)h->i8_probs.p);
+    mix(h->i8_cap_rows); mix(h->M); mix(h->i8_kp1); mix(h->i8_mp); mix(h->i8_tr2); mix(h->i8_model_version);
+    for (int s = 0; s <= h->S; ++s) mix(h->m_first[s]);
     Problem* dev = h->i8_probs.as<Problem>() + slot * kMaxSpecies;
-    for (size_t i = 0; i < probs.size(); ++i) pin[i] = probs[i];
-    if (!probs.empty()) SGPR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(Problem) * probs.size(), cudaMemcpyHostToDevice, st));
+    if (h->i8_prob_sig[slot] != sig) {
+        std::vector<Problem> probs;
+        SetupDesc sd{};
+        SGPR_TRY(build_problems(h, which, probs, sd));
+        Problem* pin = (Problem*)h->i8_probs_pinned + slot * kMaxSpecies;
+        // the staging slot may still be read by an earlier asynchronous upload
+        SGPR_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < probs.size(); ++i) pin[i] = probs[i];
+        if (!probs.empty()) SGPR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(Problem) * probs.size(), cudaMemcpyHostToDevice, st));
+        h->i8_prob_sig[slot] = sig;
+        h->i8_setup[slot] = sd;
+    }
     *out = dev;
+    *sd_out = h->i8_setup[slot];
+    return SGPR_OK;
+}
+
+static Common* common_d(sgpr_context* h, int which) {
+    return reinterpret_cast<Common*>(h->i8_probs.as<Problem>() + 3 * kMaxSpecies) + (which - 1);
+}
+
+// one-warp set-up kernel: the three work lists of this step from the device-side species row ranges
+int i8_setup_step(sgpr_context* h, cudaStream_t st) {
+    const Problem* dummy = nullptr;
+    SetupDesc sd{};
+    SGPR_TRY(device_problems(h, 1, st, &dummy, &sd));
+    if (sd.n_prob == 0) {
+        h->i8_nprob = 0;
+        return SGPR_OK;
+    }
+    h->i8_nprob = sd.n_prob;
+    i8_setup_kernel<<<1, 32, 0, st>>>(sd, h->row_first_d.as<int>(), common_d(h, 1));
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
     return SGPR_OK;
 }
 
 int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
-    Common cm;
-    std::vector<Problem> probs;
-    int ps[kMaxSpecies];
-    SGPR_TRY(build_problems(h, 1, cm, probs, ps));
-    if (cm.n_prob == 0) return SGPR_OK;
     const Problem* probs_d = nullptr;
-    SGPR_TRY(upload_problems(h, 0, probs, st, &probs_d));
+    SetupDesc sd{};
+    SGPR_TRY(device_problems(h, 1, st, &probs_d, &sd));
+    if (sd.n_prob == 0) return SGPR_OK;
+    count_work(h, 1);
     Epi1 e{};
-    for (int p = 0; p < cm.n_prob; ++p) {
-        const int s = ps[p], r0 = h->row_first[s], m0 = h->m_first[s];
-        e.mu[p] = h->mu.as<double>() + m0;
-        e.erow_part[p] = h->erow_part.as<double>() + r0;
-        e.g8[p] = h->g8.as<signed char>() + (size_t)r0 * h->i8_mp;
-        e.k8[p] = store_k8 ? h->k8.as<signed char>() + (size_t)r0 * h->i8_mp : nullptr;
-    }
+    for (int p = 0; p < sd.n_prob; ++p) e.mu[p] = h->mu.as<double>() + h->m_first[sd.species[p]];
+    e.erow_part = h->erow_part.as<double>();
+    e.g8 = h->g8.as<signed char>();
+    e.k8 = store_k8 ? h->k8.as<signed char>() : nullptr;
     e.erow_ld = (int)h->n_active + 1;
     e.Mp = h->i8_mp;
     e.g8_slice = (long long)h->i8_cap_rows * h->i8_mp;
     e.xi = h->xi;
     e.xi_int = h->xi_int;
-    return h->i8_tr == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+    return h->i8_tr == 8 ? launch<8>(h, common_d(h, 1), probs_d, e, st) : launch<7>(h, common_d(h, 1), probs_d, e, st);
 }
 
 int i8_back_projection(sgpr_context* h, cudaStream_t st) {
-    Common cm;
-    std::vector<Problem> probs;
-    int ps[kMaxSpecies];
-    SGPR_TRY(build_problems(h, 2, cm, probs, ps));
-    if (cm.n_prob == 0) return SGPR_OK;
     const Problem* probs_d = nullptr;
-    SGPR_TRY(upload_problems(h, 1, probs, st, &probs_d));
+    SetupDesc sd{};
+    SGPR_TRY(device_problems(h, 2, st, &probs_d, &sd));
+    if (sd.n_prob == 0) return SGPR_OK;
+    count_work(h, 2);
     Epi2 e{};
-    for (int p = 0; p < cm.n_prob; ++p) e.gvec[p] = h->gvec.as<double>() + (size_t)h->row_first[ps[p]] * h->dp.ldp;
+    e.gvec = h->gvec.as<double>();
     e.ldp = h->dp.ldp;
     e.mumax = h->i8_mumax;
-    if (h->i8_tr2 == 6) return launch_ns<5, 6>(h, cm, probs_d, e, st);
-    return h->i8_tr2 == 8 ? launch<8>(h, cm, probs_d, e, st) : launch<7>(h, cm, probs_d, e, st);
+    if (h->i8_tr2 == 6) return launch_ns<5, 6>(h, common_d(h, 2), probs_d, e, st);
+    return h->i8_tr2 == 8 ? launch<8>(h, common_d(h, 2), probs_d, e, st) : launch<7>(h, common_d(h, 2), probs_d, e, st);
 }
 
 // Covloss GEMM on tcgen05: b = K . choli^T per central species, reduced on the fly to per-row partial sums of
@@ -463,20 +539,16 @@ int i8_back_projection(sgpr_context* h, cudaStream_t st) {
 int i8_covloss_parts(sgpr_context* h) { return ((h->M + BN - 1) / BN) * (BN / 16); }
 
 int i8_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st) {
-    Common cm;
-    std::vector<Problem> probs;
-    int ps[kMaxSpecies];
-    SGPR_TRY(build_problems(h, 3, cm, probs, ps));
-    if (cm.n_prob == 0) return SGPR_OK;
     const Problem* probs_d = nullptr;
-    SGPR_TRY(upload_problems(h, 2, probs, st, &probs_d));
+    SetupDesc sd{};
+    SGPR_TRY(device_problems(h, 3, st, &probs_d, &sd));
+    if (sd.n_prob == 0) return SGPR_OK;
+    count_work(h, 3);
     Epi3 e{};
-    for (int p = 0; p < cm.n_prob; ++p) {
-        e.rs[p] = h->crs.as<double>() + (size_t)ps[p] * h->M;
-        e.part[p] = h->cpart.as<double>() + h->row_first[ps[p]];
-    }
+    for (int p = 0; p < sd.n_prob; ++p) e.rs[p] = h->crs.as<double>() + (size_t)sd.species[p] * h->M;
+    e.part = h->cpart.as<double>();
     e.part_ld = (int)n_rows;
-    return launch<8>(h, cm, probs_d, e, st);
+    return launch<8>(h, common_d(h, 3), probs_d, e, st);
 }
 
 }  // namespace sgpr

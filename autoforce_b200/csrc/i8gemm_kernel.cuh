@@ -131,17 +131,24 @@ __device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
 }
 
 struct Problem {
-    CUtensorMap mapA;    // int8 [NS][rowsA][Kpad], box {64, 128, NS}
+    CUtensorMap mapA;    // int8 [NS][rowsA][Kpad], box {64, 128, NS}; covers the WHOLE operand buffer (all species' rows):
+                         // the problem's first row comes from Common::row0
     CUtensorMap mapB;    // int8 [NS][rowsB][Kpad], box {64,  64, NS}
-    int M, N, Kpad;      // Kpad multiple of 64 (zero padded)
+    int M, N, Kpad;      // N columns; Kpad multiple of 64 (zero padded); M unused (Common::M)
     const int* nk_tn;    // optional [ceil(N/64)]: K chunks (of 64) that can be non-zero for column tile tn; nullptr =
                          // Kpad / 64 for every tile.  Lets a triangular B (choli) skip its zero part; 0 = the tile
                          // is identically zero: no loads, no MMAs, the epilogue runs on zeros.
 };
 
+// Work list of one grouped launch.  It lives in DEVICE memory and is written by a one-warp set-up kernel from the
+// species row ranges the neighbour stage left on the device (i8gemm.cu: i8_setup_kernel), so the host never needs to
+// know how many rows each central species has this step: no device-to-host copy, no synchronisation, and the launch
+// sequence is identical from step to step (CUDA-graph capturable).
 struct Common {
     int n_prob;
     int tile_start[9];   // first tile of each problem (problem-major)
+    int row0[8];         // first row of problem p in the row-major operand / output buffers (species block)
+    int M[8];            // rows of problem p
 };
 
 template <int NS, int TR>
@@ -207,11 +214,16 @@ __device__ __forceinline__ void combine16(uint32_t taddr_lane_col, double* v) {
     }
 }
 
-// Epilogue functor:  epi(prob, row, col0, v[16], M, N)  called by each of the 128 epilogue threads (one
-// output row each) for every 16-column chunk of its row.
+// Epilogue functor:  epi(prob, row0, row, col0, v[16], M, N)  called by each of the 128 epilogue threads (one
+// output row each: row0 + row in the buffers, row < M valid) for every 16-column chunk of its row.
 template <int NS, int TR, int STAGES, class Epi, int DEBUG_SKIP = 0>
-__global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_constant__ Common cm,
+__global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __restrict__ cmp,
                                                              const Problem* __restrict__ probs, Epi epi) {
+    // the work list is read once per CTA into shared memory: every role indexes it with run-time indices, which
+    // would otherwise put a per-thread copy into local memory on the tile-scheduling path
+    __shared__ Common cm;
+    static_assert(sizeof(Common) % 4 == 0, "Common is copied word-wise");
+    if (threadIdx.x < sizeof(Common) / 4) reinterpret_cast<int*>(&cm)[threadIdx.x] = reinterpret_cast<const int*>(cmp)[threadIdx.x];
     using SC = Scheme<NS, TR>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
                 if (elect_one()) {
                     uint8_t* sa = smem + (size_t)stage * SC::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], SC::STAGE_BYTES);
-                    tma_load_3d(sa, &P.mapA, &full_bar[stage], kt * BKB, tm * BM, 0);
+                    tma_load_3d(sa, &P.mapA, &full_bar[stage], kt * BKB, cm.row0[pi] + tm * BM, 0);
                     tma_load_3d(sa + SC::A_BYTES, &P.mapB, &full_bar[stage], kt * BKB, tn * BN, 0);
                 }
                 __syncwarp();
@@ -339,7 +351,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < HC; ++j) v[j] = 0.0;
 #pragma unroll
-                for (int cc = 0; cc < HC; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, P.M, P.N);
+                for (int cc = 0; cc < HC; cc += 16)
+                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N);
                 continue;
             }
             mbar_wait(tmem_full, tphase);
@@ -357,11 +370,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const __grid_consta
             tphase ^= 1;
             if (DEBUG_SKIP == 0) {
 #pragma unroll
-                for (int cc = 0; cc < HC; cc += 16) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, P.M, P.N);
+                for (int cc = 0; cc < HC; cc += 16)
+                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N);
             } else if (DEBUG_SKIP == 1) {
                 double s = 0;
                 for (int j = 0; j < HC; ++j) s += v[j];
-                if (s == 123.456) epi(pi, tm * BM + row_in_tile, tn * BN + half * HC, v, P.M, P.N);
+                if (s == 123.456) epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC, v, cm.M[pi], P.N);
             }
         }
     }

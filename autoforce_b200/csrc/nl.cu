@@ -842,28 +842,70 @@ static int check_err_flags(const int* err) {
     return SGPR_OK;
 }
 
-// row totals -> exclusive scan -> (sync: pair count, error flags, species row ranges) -> fill
+// Sync-free steps: the pair count and the error flags stay on the device.  One thread records them in the status
+// block and decides whether the step is valid (the pair list fits the capacity sized by an earlier step, no error
+// flag); an invalid step gets EMPTY neighbour rows, so that every later kernel stays inside its buffers -- the step's
+// results are then meaningless and the sticky counter status[1] says so (sgpr_check / the host entry point re-run it).
+__global__ void nl_status_kernel(int na, const long long* __restrict__ first, long long cap, const int* __restrict__ err,
+                                 long long* __restrict__ status) {
+    const long long total = first[na];
+    const bool bad = total > cap || err[0] != 0;
+    status[0] = total;
+    status[6] = bad ? 1 : 0;
+    if (bad) {
+        status[1] += 1;
+        status[2] = err[0];
+        status[3] = err[1];
+        status[4] = total;
+        status[5] = cap;
+    }
+}
+__global__ void nl_clamp_kernel(int na, long long* __restrict__ first, const long long* __restrict__ status) {
+    if (status[6] == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= na) first[i] = 0;
+}
+
+// row totals -> exclusive scan -> (sizing step: sync for pair count, error flags, species row ranges) -> fill
 static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int* row_first_src, int row_first_pitch,
-                     int64_t* n_pairs, int contig_c0, int n_contig) {
+                     int64_t* n_pairs, int contig_c0, int n_contig, bool warm) {
     const int S = h->S;
     const int na = (int)h->n_active;
     SGPR_TRY(h->nl_first.ensure(sizeof(long long) * 2 * ((size_t)na + 1)));
+    SGPR_TRY(h->row_first_d.ensure(sizeof(int) * (SGPR_MAX_SPECIES + 2)));
+    SGPR_TRY(h->status_d.ensure(sizeof(long long) * 8));
     long long* first = h->nl_first.as<long long>();
     long long* tot = first + (na + 1);
     const int T = 256;
     row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
     SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
+    // species row ranges in their canonical device location (read by the GEMM set-up kernel and row_energy_kernel)
+    SGPR_CUDA(cudaMemcpy2DAsync(h->row_first_d.p, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
+                                cudaMemcpyDeviceToDevice, st));
     long long total = 0;
-    int err[4] = {0, 0, 0, 0};
-    int rf[SGPR_MAX_SPECIES + 1];
-    SGPR_CUDA(cudaMemcpyAsync(&total, first + na, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaMemcpyAsync(err, h->errflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaMemcpy2DAsync(rf, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
-                                cudaMemcpyDeviceToHost, st));
-    SGPR_CUDA(cudaStreamSynchronize(st));
-    SGPR_TRY(check_err_flags(err));
-    for (int s = 0; s <= S; ++s) h->row_first[s] = rf[s];
-    SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)(total + 1)));
+    if (warm) {
+        h->row_first_host_valid = false;
+        nl_status_kernel<<<1, 1, 0, st>>>(na, first, h->pairs_cap, h->errflag.as<int>(), h->status_d.as<long long>());
+        nl_clamp_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, first, h->status_d.as<long long>());
+        h->stats.kernel_launches += 2;
+    } else {
+        int err[4] = {0, 0, 0, 0};
+        int rf[SGPR_MAX_SPECIES + 1];
+        SGPR_CUDA(cudaMemcpyAsync(&total, first + na, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaMemcpyAsync(err, h->errflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaMemcpy2DAsync(rf, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
+                                    cudaMemcpyDeviceToHost, st));
+        SGPR_CUDA(cudaStreamSynchronize(st));
+        SGPR_TRY(check_err_flags(err));
+        for (int s = 0; s <= S; ++s) h->row_first[s] = rf[s];
+        h->row_first_host_valid = true;
+        // capacity with head room: the following steps of a trajectory reuse it without asking the device
+        if (total + 1 > h->pairs_cap) {
+            const long long want = total + total / 4 + 4096;
+            SGPR_TRY(h->nl_pairs.ensure(sizeof(PairRec) * (size_t)want));
+            h->pairs_cap = (long long)(h->nl_pairs.bytes / sizeof(PairRec)) - 1;
+        }
+    }
     int done = 0;   // environments 0 .. n_contig-1 are a contiguous range of the cell order: block-per-bin fill
     if (n_contig > 0 && use_bin_kernels(h, g)) {
         SGPR_TRY(h->nl_run.ensure(sizeof(int) * ((size_t)n_contig * S + 1)));
@@ -887,7 +929,7 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
 // Neighbour list of ALL atoms (single-GPU path): rows in cell order, descriptor rows from the
 // species-major scan of cell_sort.  Output: nl_cnt [N,S], nl_first [N+1] (int64), nl_pairs,
 // rows ordered by neighbour species, then bin traversal order, then cell order; h->row_first.
-int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs) {
+int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs, bool warm) {
     h->active_all = true;
     h->n_active = N;
     SGPR_TRY(h->nl_cnt.ensure(sizeof(int) * ((size_t)N * h->S + 1)));
@@ -895,7 +937,7 @@ int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, i
     SGPR_TRY(launch_count(h, 0, (int)N, g, nullptr, st, 0));
     const int nkeys = g.ncell * h->S;
     const int* rstartT = h->rstart.as<int>() + (nkeys + 1);
-    return nl_finish(h, g, st, rstartT, (int)sizeof(int) * g.ncell, n_pairs, 0, (int)N);
+    return nl_finish(h, g, st, rstartT, (int)sizeof(int) * g.ncell, n_pairs, 0, (int)N, warm);
 }
 
 // ---------------------------------------------------------------------------------
@@ -993,7 +1035,11 @@ __global__ void contig_rows_kernel(int c0, int n_own, int S, int ncell, const At
 // Owned range of the cell order + exact one-cutoff halo (atoms that have an owned atom as a
 // neighbour).  Active list = owned ++ halo; rows are species-major over the active list.
 int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
-                           int64_t* n_pairs, bool with_halo) {
+                           int64_t* n_pairs, bool with_halo, bool warm) {
+    if (warm && with_halo) {
+        set_error("internal: the halo mode sizes its active list on the host");
+        return SGPR_ERR_INVALID;
+    }
     const int S = h->S;
     const int c0 = (int)((N * rank) / world), c1 = (int)((N * (rank + 1)) / world);
     const int n_own = c1 - c0;
@@ -1048,7 +1094,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
                                                                  h->row_owned.as<unsigned char>());
         h->stats.kernel_launches += 3;
         SGPR_CUDA(cudaGetLastError());
-        return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own);
+        return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own, warm);
     }
     for (int s = 0; s < S; ++s) {
         species_flag_kernel<<<nblkA, T, 0, st>>>(na, active, h->atoms.as<AtomRec>(), s, flag);
@@ -1061,7 +1107,7 @@ int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, 
     }
     h->stats.kernel_launches += 5 + 4 * S;
     SGPR_CUDA(cudaGetLastError());
-    return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own);
+    return nl_finish(h, g, st, row_first_d, (int)sizeof(int), n_pairs, c0, n_own, false);
 }
 
 }  // namespace sgpr

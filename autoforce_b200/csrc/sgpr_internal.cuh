@@ -86,6 +86,14 @@ struct DescParams {
     int nbr_enabled[kMaxSpecies];   // 0: neighbours of this species are left out of the expansion
 };
 
+// static part of the grouped tcgen05 GEMM work lists (i8gemm.cu): which central species form a problem and how many
+// output columns each has in GEMM 1 (kernel matrix), 2 (back projection), 3 (covloss)
+struct I8Setup {
+    int n_prob;
+    int species[kMaxSpecies];
+    int ncol[3][kMaxSpecies];
+};
+
 // host-side mirror of a grow-only device buffer
 struct DevBuf {
     void* p = nullptr;
@@ -150,8 +158,44 @@ struct sgpr_context {
     sgpr::DevBuf p8, g8;        // per-step digit slices: q_hat [6][cap][kp1], k^(xi-1) [6][cap][mp]
     sgpr::DevBuf cov_nk;        // [S][ceil(M/64)] non-zero K chunks of choli per column tile (triangular skip)
     sgpr::DevBuf k8, c8, crs;   // covloss: k^xi digits [6][cap][mp], choli digits [S][6][M][mp], choli row scales [S][M]
-    sgpr::DevBuf i8_probs;      // device copies of the tensor-map problem descriptors
+    sgpr::DevBuf i8_probs;      // device copies of the tensor-map problem descriptors + the three per-step work lists
     void* i8_probs_pinned = nullptr;
+    unsigned long long i8_prob_sig[3] = {0, 0, 0};   // what the uploaded descriptors were built from (addresses, shapes)
+    sgpr::I8Setup i8_setup[3];
+    int i8_nprob = 0;
+    unsigned long long i8_model_version = 0;
+    // ---- species row ranges / pair count stay on the device (sync-free steps)
+    sgpr::DevBuf row_first_d;   // [S+1] first descriptor row of each central species (device copy of row_first)
+    bool row_first_host_valid = false;   // h->row_first[] describes the current step (sizing steps only)
+    sgpr::DevBuf status_d;      // [8] long long: 0 pairs of the step, 1 sticky count of invalid steps, 2-5 error flags
+    long long* status_pinned = nullptr;  // host mirror, copied at the end of a step
+    long long pairs_cap = 0;    // capacity of nl_pairs (records)
+    bool warm_ok = false;       // sizes of a previous step are valid: the next one may run without host synchronisation
+    int64_t warm_N = -1;
+    int warm_rank = -1, warm_world = -1;
+    bool warm_halo = false;
+    bool async_mode = false;    // sgpr_set_async: device-pointer entry points skip the sizing synchronisation when warm
+    bool step_was_warm = false;
+    long long bad_steps_seen = 0;   // value of the sticky invalid-step counter already reported
+    bool warm_beta = false;
+    // ---- CUDA graphs of warm steps (api.cu: predict_impl), keyed by everything baked into the nodes
+    struct GraphKey {
+        int64_t N;
+        int rank, world;
+        void* stream;
+        const void* ptr[7];                 // pos, Z, E, F, W, beta, owned
+        uint64_t peer[SGPR_MAX_RANKS];      // peer force buffers (p2p exchange)
+        double cell[9];
+    };
+    struct GraphEntry {
+        GraphKey key;
+        cudaGraphExec_t exec;
+        unsigned long long stamp;
+        long long launches;
+    };
+    std::vector<GraphEntry> graphs;
+    unsigned long long graph_clock = 0;
+    bool use_graph = true;          // SGPR_GRAPH=0 switches the replay off
     sgpr::DevBuf ptab, nnlk;  // packed-entry tables [D]
     sgpr::DevBuf ztab;        // [128] atomic number -> species
     sgpr::DevBuf ind_perm_d;  // [M]
@@ -187,9 +231,11 @@ namespace sgpr {
 int build_geometry(sgpr_context* h, int64_t N, const double* pos_d, const double* cell_h, const int32_t* pbc_h,
                    cudaStream_t st, Geom* g);
 int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_d, const Geom& g, cudaStream_t st);
-int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs);
+// warm = true: no device-to-host copy, no synchronisation -- pair count, error flags and species row ranges stay on
+// the device (status_d, row_first_d); needs h->pairs_cap from an earlier sizing step; *n_pairs is then not set
+int neighbor_build(sgpr_context* h, int64_t N, const Geom& g, cudaStream_t st, int64_t* n_pairs, bool warm = false);
 int neighbor_build_sharded(sgpr_context* h, int64_t N, const Geom& g, int rank, int world, cudaStream_t st,
-                           int64_t* n_pairs, bool with_halo = true);
+                           int64_t* n_pairs, bool with_halo = true, bool warm = false);
 int scan_exclusive_ll(sgpr_context* h, const long long* in, long long* out, int n, cudaStream_t st);
 
 // ---- descriptor.cu ----------------------------------------------------------------
@@ -225,6 +271,7 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8 = false);
 int i8_covloss_parts(sgpr_context* h);
 int i8_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st);
 int i8_back_projection(sgpr_context* h, cudaStream_t st);
+int i8_setup_step(sgpr_context* h, cudaStream_t st);   // work lists of this step's GEMMs from row_first_d (one warp)
 int gemm_back_projection(sgpr_context* h, cudaStream_t st);
 
 }  // namespace sgpr

@@ -61,6 +61,8 @@ EXPORTS = {
     "sgpr_descriptors": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_inducing_descriptors": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_envs": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_set_async": (c_int32, [c_void_p, c_int32]),
+    "sgpr_check": (c_int32, [c_void_p, POINTER(c_int64)]),
     "sgpr_get_stats": (c_int32, [c_void_p, POINTER(sgpr_stats)]),
     "sgpr_enable_timing": (c_int32, [c_void_p, c_int32]),
 }
@@ -505,6 +507,18 @@ class SgprEngine:
         m.ind_b = np.concatenate([m.ind_b, b])
         m.mu = mu
         m.choli = ch
+
+    def set_async(self, on=True):
+        """Device-pointer entry points (predict_device, peer exchange) enqueue warm steps without synchronising; call
+        ``check()`` after synchronising the stream (include/sgpr_b200.h, "Asynchronous steps")."""
+        _check(self.lib, self.lib.sgpr_set_async(self._h, 1 if on else 0))
+
+    def check(self):
+        """Validate the asynchronous steps since the last check; returns the pair count of the last step.  Raises
+        ``RuntimeError`` (SGPR_ERR_RETRY ...) if one of them was invalid: repeat it."""
+        n = c_int64(0)
+        _check(self.lib, self.lib.sgpr_check(self._h, ctypes.byref(n)))
+        return int(n.value)
 
     def enable_timing(self, on=True):
         _check(self.lib, self.lib.sgpr_enable_timing(self._h, 1 if on else 0))

@@ -301,6 +301,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # all device work of the bench runs on ONE explicit (non-default) stream: the library captures its warm steps into
+    # CUDA graphs, which the legacy default stream does not allow; the CUDA events below are recorded on the same stream
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     w, pos_variants, cell, numbers = workload_inputs(args.workload, args.variants)
     N = len(numbers)
@@ -388,11 +391,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0].item()), float(t[1].item())
 
-    # ---- device-resident leg (value): no in-library events, no stats calls inside the timed region
+    # ---- device-resident leg (value): no in-library events, no stats calls inside the timed region; after the first
+    # (sizing) step the library enqueues every step without host synchronisation -- validated after the timed region
+    eng.set_async(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, wall_dev = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop()
+    eng.check()          # raises if any asynchronous step was invalid (pair list outgrew its capacity ...)
     launches_per_step = eng.stats()["kernel_launches"] + (1 if px is not None else 0)
     # ---- stage split: a separate, untimed pass with CUDA events between the stages inside the library
     eng.enable_timing(True)
@@ -409,6 +415,7 @@ def main():
     eng.enable_timing(False)
     # ---- end-to-end leg: host buffers through the public host API (H2D + D2H inside)
     ms_e2e, wall_e2e = timed(step_host, args.steps, args.warmup)
+    eng.check()
 
     # ---- parity, outside the timed regions, every N
     parity = {}

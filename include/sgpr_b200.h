@@ -38,7 +38,9 @@ typedef enum {
     SGPR_ERR_SPECIES = -3,      /* atomic number not in the handle's species table   */
     SGPR_ERR_GEOMETRY = -4,     /* singular cell / atom too far outside the cell     */
     SGPR_ERR_NOMEM = -5,
-    SGPR_ERR_NO_DEVICE = -6     /* no CUDA device: there is NO CPU fallback          */
+    SGPR_ERR_NO_DEVICE = -6,    /* no CUDA device: there is NO CPU fallback          */
+    SGPR_ERR_RETRY = -7         /* an asynchronous step outgrew the buffers sized by an earlier
+                                   step (sgpr_check): repeat it                       */
 } sgpr_status;
 
 /* Frozen model = kernel hyper-parameters + inducing set + weights.
@@ -202,6 +204,21 @@ int sgpr_descriptors(sgpr_handle h, int64_t N, const double* pos_d, const int32_
 
 /* Same layout for the inducing LCEs (loc.kern_0_value): Zhat_d [M, S*S*(nmax+1)^2*(lmax+1)]. */
 int sgpr_inducing_descriptors(sgpr_handle h, void* stream, double* Zhat_d);
+
+/* Asynchronous steps.  The first sgpr_predict / sgpr_predict_p2p / sgpr_predict_host of a given shape (atom count,
+ * rank, world) is a SIZING step: it synchronises the stream once to learn the pair count and the per-species row
+ * ranges.  Later steps of the same shape need neither: both stay on the device (capacity + overflow flag, work lists of
+ * the GEMMs written by a one-warp kernel), so the host enqueues the whole step without waiting -- the same launch
+ * sequence every step.
+ *   - sgpr_predict_host always does this and validates the step itself (an overflowing step is repeated as a sizing
+ *     step inside the same call);
+ *   - the device-pointer entry points do it only after sgpr_set_async(h, 1), because they return before the step has
+ *     run: call sgpr_check(h, &n_pairs) after synchronising the stream -- SGPR_OK, or SGPR_ERR_RETRY / _SPECIES /
+ *     _GEOMETRY if any step since the last check was invalid (its outputs are then meaningless; an invalid step never
+ *     writes outside its buffers).
+ * Non-periodic cells, halo-recompute sharding (sgpr_predict with world > 1) and the FP64 DMMA path always size. */
+int sgpr_set_async(sgpr_handle h, int32_t on);
+int sgpr_check(sgpr_handle h, int64_t* n_pairs_out);
 
 /* Explicit local chemical environments (reference `Local` objects: number, _r, _b; descriptor/atoms.py:36-52) against
  * the inducing set -- the similarity interface on LCEs rather than structures:

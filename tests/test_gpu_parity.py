@@ -595,3 +595,76 @@ def test_peer_memory_exchange_emulated_on_one_gpu(case, world):
     finally:
         for e in engines:
             e.close()
+
+
+def test_sync_free_steps_and_overflow_recovery():
+    """Steps after the first one of a shape run without host synchronisation (pair count, species row ranges and error
+    flags stay on the device).  (1) warm steps reproduce the sizing step bit for bit; (2) a warm step whose pair list
+    outgrows the capacity sized earlier is repeated transparently by the host entry point; (3) the asynchronous
+    device-pointer entry point reports it through check() and never corrupts memory; (4) species per atom may change
+    between warm steps (row ranges are re-derived on the device)."""
+    import torch
+
+    import autoforce_b200 as ab
+    from autoforce_b200 import synth
+
+    Zs = [3, 8]
+    model = synth.synth_model(Zs, 40, 5, lmax=3, nmax=3, rc=6.0)
+    pos, cell, numbers = synth.fcc(6, Zs, 0.1, 1)
+    N = len(numbers)
+    ref_eng = ab.SgprEngine(model, species=Zs)
+    E_ref, F_ref, W_ref, _ = ref_eng.predict(pos, numbers, cell, True)
+    n_pairs_dense = ref_eng.stats()["n_pairs"]
+    eng = ab.SgprEngine(model, species=Zs)
+    # (1) sizing step then warm steps: identical results
+    E0, F0, W0, _ = eng.predict(pos, numbers, cell, True)
+    for _ in range(3):
+        E1, F1, W1, _ = eng.predict(pos, numbers, cell, True)
+        assert E1 == E0 and np.array_equal(W1, W0) and np.abs(F1 - F0).max() < 1e-11
+    assert E0 == E_ref
+    # (4) another species assignment of the same atoms, still warm
+    numbers2 = numbers.copy()
+    numbers2[::3] = np.where(numbers2[::3] == 3, 8, 3)
+    E2, F2, W2, _ = eng.predict(pos, numbers2, cell, True)
+    E2r, F2r, W2r, _ = ref_eng.predict(pos, numbers2, cell, True)
+    assert abs(E2 - E2r) / N < 1e-13 and np.abs(F2 - F2r).max() < 1e-11
+    eng.close()
+    # (2) capacity sized on an expanded (sparse) structure, then the dense one: transparent repeat
+    eng = ab.SgprEngine(model, species=Zs)
+    Es, Fs, Ws, _ = eng.predict(pos * 1.5, numbers, cell * 1.5, True)
+    assert eng.stats()["n_pairs"] * 2 < n_pairs_dense
+    Ed, Fd, Wd, _ = eng.predict(pos, numbers, cell, True)
+    assert Ed == E_ref and np.abs(Fd - F_ref).max() < 1e-11 and np.array_equal(Wd, W_ref)
+    assert eng.stats()["n_pairs"] == n_pairs_dense
+    Ed2, Fd2, _, _ = eng.predict(pos, numbers, cell, True)     # warm again, now with enough room
+    assert Ed2 == E_ref
+    eng.close()
+    # (3) asynchronous device-pointer API
+    eng = ab.SgprEngine(model, species=Zs)
+    eng.set_async(True)
+    dev = torch.device("cuda", 0)
+    z_t = torch.as_tensor(numbers.astype(np.int32), device=dev)
+    p_sparse, p_dense = torch.as_tensor(pos * 1.5, device=dev), torch.as_tensor(pos, device=dev)
+    eng.predict_device(p_sparse, z_t, cell * 1.5, True)      # sizing step
+    torch.cuda.synchronize()
+    eng.check()
+    E, F, W = eng.predict_device(p_dense, z_t, cell, True)   # warm: overflows
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="exceed the capacity"):
+        eng.check()
+    E, F, W = eng.predict_device(p_dense, z_t, cell, True)   # sizes again
+    torch.cuda.synchronize()
+    assert eng.check() == n_pairs_dense
+    assert float(E.item()) == E_ref and np.abs(F.cpu().numpy() - F_ref).max() < 1e-11
+    E, F, W = eng.predict_device(p_dense, z_t, cell, True)   # warm and valid
+    torch.cuda.synchronize()
+    assert eng.check() == n_pairs_dense and float(E.item()) == E_ref
+    # an unknown species in a warm step is reported, not silently evaluated
+    z_bad = z_t.clone()
+    z_bad[5] = 47
+    eng.predict_device(p_dense, z_bad, cell, True)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="species table"):
+        eng.check()
+    eng.close()
+    ref_eng.close()

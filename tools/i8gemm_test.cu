@@ -54,6 +54,10 @@ struct StoreEpi {
         for (int j = 0; j < 16; ++j)
             if (col0 + j < N) C[(size_t)row * ldc + col0 + j] = v[j];
     }
+    // production kernel: rows are offsets from the problem's first row (Common::row0)
+    __device__ void operator()(int prob, int row0, int row, int col0, const double* v, int M, int N) const {
+        if (row < M) (*this)(prob, row0 + row, col0, v, row0 + M, N);
+    }
 };
 
 int main(int argc, char** argv) {
@@ -110,8 +114,13 @@ int main(int argc, char** argv) {
     cm.n_prob = 1;
     cm.tile_start[0] = 0;
     cm.tile_start[1] = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    cm.row0[0] = 0;
+    cm.M[0] = M;
+    Common* dcm;   // the production kernel reads its work list from device memory (written by i8_setup_kernel there)
+    cudaMalloc(&dcm, sizeof(Common));
+    cudaMemcpy(dcm, &cm, sizeof(Common), cudaMemcpyHostToDevice);
     StoreEpi epi{dC, N};
-    void (*kern)(const Common, const Problem*, StoreEpi) = nullptr;
+    void (*kern)(const Common*, const Problem*, StoreEpi) = nullptr;
     void (*kern_ta)(const Common, const ProblemTA*, StoreEpi) = nullptr;
     size_t smem = 0;
     int nthreads = NTHREADS;
@@ -132,7 +141,7 @@ int main(int argc, char** argv) {
     int grid = std::min(prop.multiProcessorCount, cm.tile_start[1]);
     if (getenv("GRID")) grid = std::min(grid, atoi(getenv("GRID")));
     if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
-    else kern<<<grid, nthreads, smem>>>(cm, dP, epi);
+    else kern<<<grid, nthreads, smem>>>(dcm, dP, epi);
     e = cudaDeviceSynchronize();
     printf("kernel: %s\n", cudaGetErrorString(e));
     if (e != cudaSuccess) return 1;
@@ -156,7 +165,7 @@ int main(int argc, char** argv) {
     const int reps = 5;
     for (int r = 0; r < reps; ++r) {
         if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
-        else kern<<<grid, nthreads, smem>>>(cm, dP, epi);
+        else kern<<<grid, nthreads, smem>>>(dcm, dP, epi);
     }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);

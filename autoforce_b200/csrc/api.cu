@@ -313,6 +313,67 @@ __global__ void env_kernel_rows_kernel(int n_env, int M, int D, int ldp, const d
     }
 }
 
+// ---------------------------------------------------------------------------------
+// exchange step of the atom-sharded path without NCCL: E + 3x3 virial travel through peer-mapped mailboxes, a stamped
+// flag per (rank, step parity) doubles as the barrier after which a rank may read the forces its peers added to it
+// ---------------------------------------------------------------------------------
+// mailbox block of one rank: [2 parities][world slots][16 doubles]; slot r = {E, W[9], -, ..., stamp (int64 at [15])}
+__global__ void p2p_publish_kernel(int rank, int world, int parity, P2PPeers peers, const double* __restrict__ ew_local,
+                                   long long* __restrict__ step_counter) {
+    // every earlier kernel of this stream (the force kernel with its remote red.add) has completed
+    const long long stamp = *step_counter + 1;
+    const int r = threadIdx.x;
+    if (r < world) {
+        double* slot = peers.mail[r] + ((size_t)parity * world + rank) * 16;
+        for (int q = 0; q < 10; ++q) slot[q] = ew_local[q];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(slot + 15)),
+                     "l"((unsigned long long)stamp)
+                     : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_counter = stamp;
+}
+__global__ void p2p_wait_reduce_kernel(int world, int parity, const double* __restrict__ my_mail,
+                                       const long long* __restrict__ step_counter, double* __restrict__ E,
+                                       double* __restrict__ W, long long* __restrict__ status) {
+    __shared__ double acc[SGPR_MAX_RANKS][10];
+    __shared__ int timed_out;
+    const long long stamp = *step_counter;   // set by this step's publish kernel
+    const int r = threadIdx.x;
+    if (r == 0) timed_out = 0;
+    __syncthreads();
+    if (r < world) {
+        const double* slot = my_mail + ((size_t)parity * world + r) * 16;
+        unsigned long long t0, t1, seen = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(reinterpret_cast<const unsigned long long*>(slot + 15)) : "memory");
+            if ((long long)seen >= stamp) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) {   // 10 s: a peer died; never hang the GPU
+                timed_out = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        for (int q = 0; q < 10; ++q) acc[r][q] = slot[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double v = 0.0;
+        for (int k = 0; k < world; ++k) v += acc[k][threadIdx.x];   // fixed order: every rank gets the same bits
+        if (threadIdx.x == 0)
+            E[0] = v;
+        else
+            W[threadIdx.x - 1] = v;
+    }
+    if (threadIdx.x == 0 && timed_out) {
+        status[1] += 1;
+        status[2] = 3;
+    }
+}
+
 // CSR neighbour list in the caller's atom order (parity hook)
 __global__ void nl_count_orig_kernel(int64_t N, const AtomRec* __restrict__ atoms, const long long* __restrict__ nl_first,
                                      long long* __restrict__ cnt) {
@@ -703,7 +764,7 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk, &h->row_first_d, &h->status_d};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk, &h->row_first_d, &h->status_d, &h->p2p_local};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
@@ -839,7 +900,8 @@ static bool warm_possible(sgpr_handle h, int64_t N, const int32_t* pbc_h, int32_
 
 static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                         const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
-                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm) {
+                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm,
+                        const P2PStep* px = nullptr) {
     if (!h || !cell_h || !pbc_h || !E_d || (!F_d && !peer_f_h) || !W_d || (N > 0 && (!pos_d || !Z_d))) {
         set_error("null argument");
         return SGPR_ERR_INVALID;
@@ -859,6 +921,20 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     Geom g;
+    double* E_out = E_d;
+    double* W_out = W_d;
+    if (px) {
+        // fused exchange step: the accumulation buffer of the NEXT step is cleared now (its last readers finished in
+        // the previous step of this stream; remote ranks touch it only after they have seen this step's flag)
+        SGPR_TRY(h->p2p_local.ensure(sizeof(double) * 16 + sizeof(long long) * 2));
+        if (!h->p2p_counter_init) {
+            SGPR_CUDA(cudaMemsetAsync(h->p2p_local.p, 0, sizeof(double) * 16 + sizeof(long long) * 2, st));
+            h->p2p_counter_init = true;
+        }
+        SGPR_CUDA(cudaMemsetAsync((void*)(uintptr_t)px->own_next, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+        E_d = h->p2p_local.as<double>();        // this rank's partial sums
+        W_d = h->p2p_local.as<double>() + 1;
+    }
     // Sync-free ("warm") step: every size the host needs was fixed by an earlier sizing step of the same shape; the
     // pair count, the species row ranges and the error flags stay on the device (nl.cu: nl_status_kernel).
     const bool halo_mode = world > 1 && peer_f_h == nullptr;
@@ -964,6 +1040,17 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
         }
         SGPR_CUDA(cudaGetLastError());
     }
+    if (px) {
+        long long* counter = reinterpret_cast<long long*>(h->p2p_local.as<double>() + 16);
+        p2p_publish_kernel<<<1, 32, 0, st>>>(rank, world, px->parity, px->peers, h->p2p_local.as<double>(), counter);
+        p2p_wait_reduce_kernel<<<1, 32, 0, st>>>(world, px->parity, px->peers.mail[rank], counter, E_out, W_out,
+                                                 h->status_d.as<long long>());
+        if (N > 0)
+            scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), px->own_now,
+                                                                          h->owned.as<unsigned char>(), px->F_d, px->owned_d);
+        h->stats.kernel_launches += 3;
+        SGPR_CUDA(cudaGetLastError());
+    }
     if (warm) {
         // the step's status (pair count, validity) follows the results to the host; nobody waits for it here
         SGPR_CUDA(cudaMemcpyAsync(h->status_pinned, h->status_d.p, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st));
@@ -995,10 +1082,11 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
 // Graphs are keyed by everything that is baked into the nodes.
 static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                         const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
-                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm) {
+                        double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm,
+                        const P2PStep* px = nullptr) {
     if (!h || !pbc_h || !cell_h || !h->use_graph || !allow_warm || world > SGPR_MAX_RANKS ||
         !warm_possible(h, N, pbc_h, rank, world, peer_f_h != nullptr, beta_d != nullptr))
-        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm, px);
     cudaStream_t st = (cudaStream_t)stream;
     SGPR_CUDA(cudaSetDevice(h->device));
     sgpr_context::GraphKey key{};
@@ -1009,6 +1097,13 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     key.ptr[0] = pos_d; key.ptr[1] = Z_d; key.ptr[2] = E_d; key.ptr[3] = F_d; key.ptr[4] = W_d; key.ptr[5] = beta_d; key.ptr[6] = owned_d;
     for (int r = 0; r < SGPR_MAX_RANKS; ++r) key.peer[r] = (peer_f_h && r < world) ? peer_f_h[r] : 0;
     for (int i = 0; i < 9; ++i) key.cell[i] = cell_h[i];
+    if (px) {
+        key.px_parity = 1 + px->parity;
+        key.px_ptr[0] = px->F_d;
+        key.px_ptr[1] = px->owned_d;
+        key.px_ptr[2] = px->own_now;
+        for (int r = 0; r < SGPR_MAX_RANKS; ++r) key.px_mail[r] = (uint64_t)(uintptr_t)px->peers.mail[r];
+    }
     for (auto& e : h->graphs) {
         if (memcmp(&e.key, &key, sizeof(key)) == 0) {
             e.stamp = ++h->graph_clock;
@@ -1022,9 +1117,9 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
         cudaGetLastError();   // e.g. the legacy default stream cannot be captured: run the step directly
-        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm, px);
     }
-    const int rc = predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm);
+    const int rc = predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm, px);
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != SGPR_OK || ce != cudaSuccess || !graph || !h->step_was_warm) {
         if (graph) cudaGraphDestroy(graph);
@@ -1032,7 +1127,7 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
         h->use_graph = false;   // something in the sequence is not capturable here: plain launches from now on
         h->warm_ok = false;     // (whatever was enqueued during the failed capture never ran)
         if (rc != SGPR_OK) return rc;
-        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false);
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false, px);
     }
     cudaGraphExec_t exec = nullptr;
     if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
@@ -1040,7 +1135,7 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
         cudaGetLastError();
         h->use_graph = false;
         h->warm_ok = false;
-        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false);
+        return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, false, px);
     }
     cudaGraphDestroy(graph);
     if (h->graphs.size() >= 16) {   // evict the least recently used entry
@@ -1124,6 +1219,35 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_p2p(sgpr_hand
     }
     return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f_h,
                         h && h->async_mode);
+}
+
+// One call per step and rank: clear the next accumulation buffer, evaluate the owned environments (forces on atoms of
+// other ranks go straight into their buffers over NVLink), publish E + virial to every peer's mailbox with a stamped
+// flag, wait for all peers' flags (= every force kernel has finished), reduce in rank order, collect the own forces.
+extern "C" __attribute__((visibility("default"))) int sgpr_p2p_step(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
+                                                                    const double* cell_h, const int32_t* pbc_h, int32_t rank,
+                                                                    int32_t world, void* stream, const uint64_t* peer_base_h,
+                                                                    int32_t parity, double* E_d, double* F_d, double* W_d,
+                                                                    uint8_t* owned_d) {
+    if (!h || !peer_base_h || !F_d || !E_d || !W_d || world < 2 || world > SGPR_MAX_RANKS || rank < 0 || rank >= world ||
+        (parity != 0 && parity != 1)) {
+        set_error("sgpr_p2p_step: bad argument (2 <= world <= %d)", SGPR_MAX_RANKS);
+        return SGPR_ERR_INVALID;
+    }
+    const size_t stride = 3 * (size_t)N + 8;                 // doubles per accumulation buffer
+    uint64_t peer_f[SGPR_MAX_RANKS];
+    P2PStep px{};
+    px.parity = parity;
+    for (int r = 0; r < world; ++r) {
+        peer_f[r] = peer_base_h[r] + sizeof(double) * stride * (size_t)parity;
+        px.peers.mail[r] = reinterpret_cast<double*>((uintptr_t)(peer_base_h[r] + sizeof(double) * 2 * stride));
+    }
+    px.own_now = reinterpret_cast<const double*>((uintptr_t)peer_f[rank]);
+    px.own_next = peer_base_h[rank] + sizeof(double) * stride * (size_t)(1 - parity);
+    px.F_d = F_d;
+    px.owned_d = owned_d;
+    return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f,
+                        h->async_mode, &px);
 }
 
 extern "C" __attribute__((visibility("default"))) int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double* F_d, uint8_t* owned_d) {

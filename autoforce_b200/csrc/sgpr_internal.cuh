@@ -186,6 +186,9 @@ struct sgpr_context {
         const void* ptr[7];                 // pos, Z, E, F, W, beta, owned
         uint64_t peer[SGPR_MAX_RANKS];      // peer force buffers (p2p exchange)
         double cell[9];
+        long long px_parity;                // fused exchange step: 1 + parity, else 0
+        const void* px_ptr[3];
+        uint64_t px_mail[SGPR_MAX_RANKS];
     };
     struct GraphEntry {
         GraphKey key;
@@ -208,6 +211,8 @@ struct sgpr_context {
     sgpr::DevBuf owned, shard_tmp, row_owned;    // atom sharding: owned/mark masks, scans, per-row ownership
     sgpr::DevBuf phat, cbuf, pnorm, sflag, gmat, gvec, epart, wpart, fcell, misc;
     sgpr::DevBuf stage_pos, stage_z, stage_out;  // device staging for the host API
+    sgpr::DevBuf p2p_local;                      // fused exchange step: [16] partial E/W + step counter
+    bool p2p_counter_init = false;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;
@@ -251,6 +256,18 @@ struct PeerForces {
 };
 int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st,
                               const PeerForces* peers = nullptr);
+// fused exchange step (api.cu: sgpr_p2p_step)
+struct P2PPeers {
+    double* mail[SGPR_MAX_RANKS];     // mailbox block of every rank, mapped on this device
+};
+struct P2PStep {
+    P2PPeers peers;
+    int parity;                       // which of the two accumulation buffers / mailbox halves this step uses
+    const double* own_now;            // own accumulation buffer of this step
+    uint64_t own_next;                // ... of the next step (cleared at the start of this one)
+    double* F_d;
+    uint8_t* owned_d;
+};
 int backward_grid(sgpr_context* h);
 int unpack_descriptors(sgpr_context* h, long long rows, const double* packed_d, const int* src_row_d, double* full_d,
                        cudaStream_t st);

@@ -53,6 +53,8 @@ EXPORTS = {
     "sgpr_predict_p2p": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "sgpr_p2p_collect": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sgpr_p2p_step": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_forward": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_jacobian": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -104,24 +106,27 @@ def _ptr(a):
 class PeerForceExchange:
     """Atom-sharded prediction without halo recompute: every rank evaluates the environments it owns and adds
     the forces on atoms of other ranks straight into their accumulation buffers over NVLink (peer-mapped
-    symmetric memory, ``sgpr_predict_p2p``).  The only collective is the all-reduce of E + 3x3 virial
-    (10 doubles), which doubles as the barrier after which each rank collects its own forces.
+    symmetric memory).  ``fused=True`` (default): the whole step is ONE library call, ``sgpr_p2p_step`` -- E and the
+    virial travel through peer-mapped mailboxes with stamped flags that double as the barrier, so there is no NCCL call,
+    no torch kernel and no host synchronisation in a warm step (it replays as one CUDA graph).  ``fused=False``:
+    ``sgpr_predict_p2p`` + an NCCL all-reduce of the 10 doubles (the barrier) + ``sgpr_p2p_collect``.
     Two accumulation buffers alternate between steps so that zeroing never races with remote adds."""
 
-    def __init__(self, engine, N, group=None):
+    def __init__(self, engine, N, group=None, fused=True):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
-        self.engine, self.N = engine, int(N)
+        self.engine, self.N, self.fused = engine, int(N), bool(fused)
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         dev = torch.device("cuda", engine.device)
         self.stride = 3 * self.N + 8
-        self.buf = symm.empty(2 * self.stride, dtype=torch.float64, device=dev)
+        self.buf = symm.empty(2 * self.stride + 2 * self.world * 16, dtype=torch.float64, device=dev)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._bases = np.array(self.ptrs, dtype=np.uint64)
         self.parity = 0
         self.ew = torch.zeros(10, dtype=torch.float64, device=dev)
         self.F = torch.zeros((self.N, 3), dtype=torch.float64, device=dev)
@@ -132,15 +137,18 @@ class PeerForceExchange:
     def step(self, pos_t, z_t, cell, pbc):
         """Device tensors in; returns (E, F_owned [N,3], W [3,3] tensor, owned mask) with E and W already summed
         over the ranks."""
-        import torch.distributed as dist
-
         eng = self.engine
         p = self.parity
-        # the other buffer was collected at the end of the previous step: clear it for the next one
-        self.buf[(1 - p) * self.stride:(2 - p) * self.stride].zero_()
-        eng.predict_p2p(pos_t, z_t, cell, pbc, self.rank, self.world, [ptr + 8 * p * self.stride for ptr in self.ptrs], self.ew)
-        dist.all_reduce(self.ew, group=self.group)   # E + virial; also: every rank's force kernel has finished
-        eng.p2p_collect(self.buf[p * self.stride:(p + 1) * self.stride], self.F, self.owned)
+        if self.fused:
+            eng.p2p_step(pos_t, z_t, cell, pbc, self.rank, self.world, self._bases, p, self.ew, self.F, self.owned)
+        else:
+            import torch.distributed as dist
+
+            # the other buffer was collected at the end of the previous step: clear it for the next one
+            self.buf[(1 - p) * self.stride:(2 - p) * self.stride].zero_()
+            eng.predict_p2p(pos_t, z_t, cell, pbc, self.rank, self.world, [ptr + 8 * p * self.stride for ptr in self.ptrs], self.ew)
+            dist.all_reduce(self.ew, group=self.group)   # E + virial; also: every rank's force kernel has finished
+            eng.p2p_collect(self.buf[p * self.stride:(p + 1) * self.stride], self.F, self.owned)
         self.parity = 1 - p
         return self.ew[0], self.F, self.ew[1:].view(3, 3), self.owned
 
@@ -316,15 +324,25 @@ class SgprEngine:
                                                    _ptr(cell_h), _ptr(pbc_h), int(rank), int(world), self._stream(), _ptr(peers),
                                                    c_void_p(ew.data_ptr()), c_void_p(ew.data_ptr() + 8)))
 
+    def p2p_step(self, pos_t, z_t, cell, pbc, rank, world, bases, parity, ew, F, owned):
+        """``sgpr_p2p_step``: the fused exchange step (include/sgpr_b200.h).  ``bases`` uint64 [world]: every rank's
+        symmetric block as mapped on this device; ``ew`` [10] receives the reduced E and 3x3 virial."""
+        cell_h, pbc_h = self._geom(cell, pbc)
+        bases = np.ascontiguousarray(bases, dtype=np.uint64)
+        _check(self.lib, self.lib.sgpr_p2p_step(self._h, z_t.numel(), c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()),
+                                                _ptr(cell_h), _ptr(pbc_h), int(rank), int(world), self._stream(), _ptr(bases),
+                                                int(parity), c_void_p(ew.data_ptr()), c_void_p(F.data_ptr()),
+                                                c_void_p(ew.data_ptr() + 8), c_void_p(owned.data_ptr())))
+
     def p2p_collect(self, own_buf, F, owned):
         """``sgpr_p2p_collect``: after every rank's ``predict_p2p`` has finished, copy this rank's accumulated forces
         (cell order) into ``F`` [N,3] (caller's order, rows of owned atoms) and fill the ``owned`` mask."""
         _check(self.lib, self.lib.sgpr_p2p_collect(self._h, self._stream(), c_void_p(own_buf.data_ptr()), c_void_p(F.data_ptr()),
                                                    c_void_p(owned.data_ptr())))
 
-    def peer_exchange(self, N, group=None):
+    def peer_exchange(self, N, group=None, fused=True):
         """Set up the peer-memory (NVLink) force exchange for structures of N atoms (torch symmetric memory)."""
-        return PeerForceExchange(self, N, group)
+        return PeerForceExchange(self, N, group, fused)
 
     def kernel_matrix(self, pos, numbers, cell, pbc):
         import torch

@@ -44,8 +44,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="atoms in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variants", type=int, default=4, help="pre-generated perturbed position sets cycled over the steps")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "halo"],
-                    help="multi-GPU force exchange: peer-memory adds over NVLink (default) or halo recompute")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2p-nccl", "halo"],
+                    help="multi-GPU force exchange: peer-memory adds over NVLink with the fused mailbox/flag exchange step "
+                         "(default), the same with an NCCL all-reduce of E + virial as the barrier, or halo recompute")
     return ap.parse_args()
 
 
@@ -326,14 +327,14 @@ def main():
         if world == 1:
             return "none", None
         mode, px_ = args.exchange, None
-        if mode == "p2p":
+        if mode in ("p2p", "p2p-nccl"):
             try:
-                px_ = engine.peer_exchange(n_atoms)
+                px_ = engine.peer_exchange(n_atoms, fused=(mode == "p2p"))
             except Exception as ex:  # symmetric memory unavailable -> halo recompute
                 if rank == 0:
                     print(f"bench: peer-memory exchange unavailable ({ex}); falling back to halo recompute", file=sys.stderr)
                 mode = "halo"
-        ok = torch.tensor([1 if mode == "p2p" else 0], device=dev)
+        ok = torch.tensor([1 if px_ is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             mode, px_ = "halo", None
@@ -550,7 +551,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic", "config": config_of(args.workload, w, N, model.M, world),
-            "exchange": {"p2p": "peer-memory adds over NVLink into the owner's buffer (no halo recompute)",
+            "exchange": {"p2p": "peer-memory adds over NVLink into the owner's buffer (no halo recompute); E + virial through "
+                                "peer-mapped mailboxes with stamped flags (sgpr_p2p_step: no NCCL call in the step, one CUDA graph)",
+                         "p2p-nccl": "peer-memory adds over NVLink into the owner's buffer; NCCL all-reduce of 10 doubles as barrier",
                          "halo": "owner-computes with one-cutoff halo recompute", "none": "single GPU"}[exchange],
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": wall_e2e / K,
                     "h2d_bytes_per_step": int(N * 24 + N * 4), "d2h_bytes_per_step": int(N * 24 + 16 * 8 + N)},

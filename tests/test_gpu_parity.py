@@ -668,3 +668,60 @@ def test_sync_free_steps_and_overflow_recovery():
         eng.check()
     eng.close()
     ref_eng.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_exchange_step_emulated_on_one_gpu(world):
+    """sgpr_p2p_step (no NCCL: mailboxes + stamped flags) with ``world`` ranks emulated on ONE GPU: one handle and one
+    stream per rank, the ranks' symmetric blocks are plain device buffers.  Several steps (sizing, warm, CUDA-graph
+    replay, both buffer parities, moving atoms) must reproduce the unsharded result on every rank."""
+    import torch
+
+    import autoforce_b200 as ab
+    from autoforce_b200 import synth
+
+    Zs = [3, 8]
+    model = synth.synth_model(Zs, 40, 5, lmax=3, nmax=3, rc=6.0)
+    pos0, cell, numbers = synth.fcc(6, Zs, 0.1, 1)
+    N = len(numbers)
+    dev = torch.device("cuda", 0)
+    ref = ab.SgprEngine(model, species=Zs)
+    engines = [ab.SgprEngine(model, species=Zs) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    stride = 3 * N + 8
+    blocks = torch.zeros((world, 2 * stride + 2 * world * 16), dtype=torch.float64, device=dev)
+    bases = np.array([blocks[r].data_ptr() for r in range(world)], dtype=np.uint64)
+    ews = [torch.zeros(10, dtype=torch.float64, device=dev) for _ in range(world)]
+    Fs = [torch.zeros((N, 3), dtype=torch.float64, device=dev) for _ in range(world)]
+    owns = [torch.zeros(N, dtype=torch.uint8, device=dev) for _ in range(world)]
+    z_t = torch.as_tensor(numbers.astype(np.int32), device=dev)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(5)
+    try:
+        for e in engines:
+            e.set_async(True)
+        for step in range(6):
+            pos = pos0 + rng.normal(0, 0.02, pos0.shape) if step % 2 else pos0   # steps 0, 2, 4 repeat: graph replay
+            pos_t = torch.as_tensor(pos, device=dev)
+            torch.cuda.synchronize()
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    engines[r].p2p_step(pos_t, z_t, cell, True, r, world, bases, step & 1, ews[r], Fs[r], owns[r])
+            torch.cuda.synchronize()
+            for e in engines:
+                e.check()
+            E0, F0, W0, _ = ref.predict(pos, numbers, cell, True)
+            F = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+            covered = torch.zeros(N, dtype=torch.int32, device=dev)
+            for r in range(world):
+                ew = ews[r].cpu().numpy()
+                assert abs(ew[0] - E0) / N < 1e-12, (step, r)
+                assert np.abs(ew[1:].reshape(3, 3) - W0).max() < 1e-9
+                assert np.array_equal(ew, ews[0].cpu().numpy()), "the reduction is bit-identical on every rank"
+                F += Fs[r] * owns[r].to(torch.float64)[:, None]
+                covered += owns[r].to(torch.int32)
+            assert bool((covered == 1).all())
+            assert np.abs(F.cpu().numpy() - F0).max() < 1e-10, step
+    finally:
+        for e in engines + [ref]:
+            e.close()

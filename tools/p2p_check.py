@@ -1,5 +1,7 @@
 """Developer/CI tool (>= 2 GPUs, torchrun): the peer-memory force exchange against the unsharded result.
-   torchrun --nproc-per-node 2 tools/p2p_check.py [workload]"""
+   torchrun --nproc-per-node 2 tools/p2p_check.py [workload] [nccl]
+   default: the fused exchange step (sgpr_p2p_step: mailboxes + stamped flags, no NCCL in the step);
+   "nccl": sgpr_predict_p2p + NCCL all-reduce + sgpr_p2p_collect."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,17 +20,23 @@ w = synth.WORKLOADS[wl]
 model = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"])
 pos, cell, numbers = synth.fcc(w["rep"], w["Zs"], 0.1, 0)
 N = len(pos)
+fused = not (len(sys.argv) > 2 and sys.argv[2] == "nccl")
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))             # warm steps replay as CUDA graphs (not on stream 0)
+ref = ab.SgprEngine(model, species=w["Zs"], device=local)        # unsharded reference on this GPU
 eng = ab.SgprEngine(model, species=w["Zs"], device=local)
-E0, F0, W0, _ = eng.predict(pos, numbers, cell, True)            # unsharded reference on this GPU
-px = eng.peer_exchange(N)
+eng.set_async(True)
+px = eng.peer_exchange(N, fused=fused)
 z_t = torch.as_tensor(numbers.astype(np.int32), device=dev)
 ok = True
 rng = np.random.default_rng(5)
-for it in range(4):                                              # several steps: buffer alternation
-    p = pos + (rng.normal(0, 0.02, pos.shape) if it else 0.0)
-    Er, Fr, Wr, _ = eng.predict(p, numbers, cell, True)
-    E, F, W, owned = px.step(torch.as_tensor(p, device=dev), z_t, cell, True)
+variants = [pos, pos + rng.normal(0, 0.02, pos.shape)]
+variants_d = [torch.as_tensor(p, device=dev) for p in variants]
+for it in range(8):                                              # sizing, warm, graph replay, both buffer parities
+    p = variants[(it // 2) % 2]
+    Er, Fr, Wr, _ = ref.predict(p, numbers, cell, True)
+    E, F, W, owned = px.step(variants_d[(it // 2) % 2], z_t, cell, True)
     torch.cuda.synchronize()
+    eng.check()
     owned = owned.cpu().numpy().astype(bool)
     F = F.cpu().numpy()
     dE = abs(float(E) - Er) / N
@@ -40,5 +48,6 @@ for it in range(4):                                              # several steps
     ok &= good
     print(f"rank {rank} step {it}: dE/N={dE:.2e} dW={dW:.2e} dF={dF:.2e} owned={int(owned.sum())} total_owned={int(cnt.item())} {'OK' if good else 'FAIL'}", flush=True)
 eng.close()
+ref.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

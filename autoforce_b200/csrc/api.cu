@@ -193,31 +193,25 @@ __global__ void vjp_finish_kernel(int64_t N, const AtomRec* __restrict__ atoms, 
 __global__ void final_reduce_kernel(int n_e, const double* __restrict__ epart, int n_x, const double* __restrict__ xpart,
                                     int n_w, const double* __restrict__ wpart, double* __restrict__ E,
                                     double* __restrict__ W) {
-    // one block, fixed summation order -> run-to-run reproducible E and W
-    __shared__ double red[256];
-    const int t = threadIdx.x;
+    // one block of 10 warps, fixed summation order -> run-to-run reproducible E and W:
+    // warp 0 sums the energy partials, warps 1..9 one virial component each (lane-strided partial sums, then a
+    // fixed shuffle tree); all ten sums run concurrently
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int i = t; i < n_e; i += 256) s += epart[i];
-    for (int i = t; i < n_x; i += 256) s += xpart[i];
-    red[t] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (t < o) red[t] += red[t + o];
-        __syncthreads();
+    if (warp == 0) {
+        for (int i = lane; i < n_e; i += 32) s += epart[i];
+        for (int i = lane; i < n_x; i += 32) s += xpart[i];
+    } else if (warp < 10) {
+        const int q = warp - 1;
+        for (int i = lane; i < n_w; i += 32) s += wpart[i * 9 + q];
     }
-    if (t == 0) E[0] = red[0];
-    __syncthreads();
-    for (int q = 0; q < 9; ++q) {
-        double w = 0.0;
-        for (int i = t; i < n_w; i += 256) w += wpart[i * 9 + q];
-        red[t] = w;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (t < o) red[t] += red[t + o];
-            __syncthreads();
-        }
-        if (t == 0) W[q] = red[0];
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (warp == 0)
+            E[0] = s;
+        else if (warp < 10)
+            W[warp - 1] = s;
     }
 }
 
@@ -1012,7 +1006,7 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
             scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(),
                                                                           owned, F_d, owned_d);
     }
-    final_reduce_kernel<<<1, 256, 0, st>>>(grid_g, h->epart.as<double>(), nblk_x,
+    final_reduce_kernel<<<1, 320, 0, st>>>(grid_g, h->epart.as<double>(), nblk_x,
                                            h->epart.as<double>() + (size_t)grid_g, nblk_b,
                                            h->wpart.as<double>(), E_d, W_d);
     h->stats.kernel_launches += 3;
@@ -1426,7 +1420,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_backward(sgpr_
     double* EW = h->epart.as<double>() + grid_e;   // [E, W(9)] scratch
     if (N > 0)
         vjp_finish_kernel<<<nblk_x, 128, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(), gpos_d, xf_part);
-    final_reduce_kernel<<<1, 256, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), EW, EW + 1);
+    final_reduce_kernel<<<1, 320, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), EW, EW + 1);
     double host[16 + 9 * 64];
     SGPR_CUDA(cudaMemcpyAsync(host, EW, sizeof(double) * (16 + 9 * nblk_x), cudaMemcpyDeviceToHost, st));
     SGPR_CUDA(cudaStreamSynchronize(st));
@@ -1494,7 +1488,7 @@ extern "C" __attribute__((visibility("default"))) int sgpr_kernel_jacobian(sgpr_
             h->xi, h->xi_int, h->gvec.as<double>(), h->erow.as<double>());
         SGPR_TRY(descriptor_backward_atoms(h, g, nullptr, st));
         vjp_finish_kernel<<<nblk_x, 128, 0, st>>>(N, h->atoms.as<AtomRec>(), h->fcell.as<double>(), Jm, scratch + 16);
-        final_reduce_kernel<<<1, 256, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), scratch, Wm);
+        final_reduce_kernel<<<1, 320, 0, st>>>(0, nullptr, 0, nullptr, nblk_b, h->wpart.as<double>(), scratch, Wm);
         h->stats.kernel_launches += 3;
     }
     SGPR_CUDA(cudaGetLastError());

@@ -202,8 +202,19 @@ __global__ void final_reduce_kernel(int n_e, const double* __restrict__ epart, i
         for (int i = lane; i < n_e; i += 32) s += epart[i];
         for (int i = lane; i < n_x; i += 32) s += xpart[i];
     } else if (warp < 10) {
+        // batches of 8 independent loads per lane (the additions stay in a fixed order): the loop is bound by the
+        // number of dependent L2 round trips, not by the 21 k values it reads
         const int q = warp - 1;
-        for (int i = lane; i < n_w; i += 32) s += wpart[i * 9 + q];
+        for (int base = lane; base < n_w; base += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + 32 * u;
+                v[u] = i < n_w ? wpart[(size_t)i * 9 + q] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

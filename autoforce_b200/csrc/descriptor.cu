@@ -325,7 +325,9 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
         if (p8) {
             // operand of the tcgen05 kernel-matrix GEMM: 6 balanced base-256 digits of q_hat * 2^46,
             // slice-major, 4 consecutive entries (one 32-bit store per slice) per lane
-            const long long prow = (long long)row_of[ENV ? env : c] * kp1;
+            // K-chunk-major operand layout of the tcgen05 GEMMs (i8gemm.cu: cm_off): [slice][chunk of 64][row][64]
+            const long long prow = (long long)row_of[ENV ? env : c] * 64;
+            const long long chunk_stride = p8_slice / kp1 * 64;   // rows per slice * 64
             for (int e4 = lane * 4; e4 < dp.D; e4 += 128) {
                 unsigned long long u[4];
 #pragma unroll
@@ -352,7 +354,9 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     packed[t] = __byte_perm(__byte_perm(w0, w1, sel), __byte_perm(w2, w3, sel), 0x5410);
                 }
 #pragma unroll
-                for (int t = 0; t < 6; ++t) *reinterpret_cast<unsigned*>(p8 + (long long)t * p8_slice + prow + e4) = packed[t];
+                const long long off = (long long)(e4 >> 6) * chunk_stride + prow + (e4 & 63);
+#pragma unroll
+                for (int t = 0; t < 6; ++t) *reinterpret_cast<unsigned*>(p8 + (long long)t * p8_slice + off) = packed[t];
             }
         }
         if (cbuf) {

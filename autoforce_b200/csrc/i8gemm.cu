@@ -36,11 +36,13 @@ int make_map(CUtensorMap* m, const void* base, int ns, long long rows, int Kpad,
         }
         g_encode = (EncodeFn)fn;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)(rows > 0 ? rows : 1), (cuuint64_t)ns};
-    cuuint64_t strides[2] = {(cuuint64_t)Kpad, (cuuint64_t)slice_stride_rows * Kpad};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)ns};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+    // K-chunk-major operand: element (slice t, row r, k) at  t * R * Kpad + (k / 64) * R * 64 + r * 64 + k % 64
+    // with R = slice_stride_rows (the allocated rows); `rows` valid rows from `base` (out-of-range rows read as zero)
+    cuuint64_t dims[4] = {64, (cuuint64_t)(rows > 0 ? rows : 1), (cuuint64_t)(Kpad / 64), (cuuint64_t)ns};
+    cuuint64_t strides[3] = {64, (cuuint64_t)slice_stride_rows * 64, (cuuint64_t)slice_stride_rows * Kpad};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, (cuuint32_t)ns};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -80,10 +82,16 @@ __device__ __forceinline__ void digits(double x, signed char* d) {   // most sig
 }
 
 // float64 rows -> digit slices:  out[t][r][k] for r < rows, k < K ; zero for K <= k < Kpad
+// chunk-major address of (row r, column k) inside one slice of an operand with R allocated rows
+__host__ __device__ __forceinline__ long long cm_off(long long R, long long r, int k) {
+    return (long long)(k >> 6) * (R * 64) + r * 64 + (k & 63);
+}
+
 template <int NS>
 __global__ void slice_rows_kernel(const double* __restrict__ X, long long ldx, int rows, int K, int Kpad, double scale,
                                   const double* __restrict__ col_scale, signed char* __restrict__ out,
                                   long long slice_stride, const double* __restrict__ row_div = nullptr) {
+    const long long R = slice_stride / Kpad;   // rows per slice
     const long long total = (long long)rows * Kpad;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Kpad), k = (int)(idx - (long long)r * Kpad);
@@ -93,7 +101,7 @@ __global__ void slice_rows_kernel(const double* __restrict__ X, long long ldx, i
         if (row_div) x /= row_div[r];   // power of two: exact
         digits<NS>(x, d);
 #pragma unroll
-        for (int t = 0; t < NS; ++t) out[(long long)t * slice_stride + (long long)r * Kpad + k] = d[t];
+        for (int t = 0; t < NS; ++t) out[(long long)t * slice_stride + cm_off(R, r, k)] = d[t];
     }
 }
 
@@ -121,6 +129,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
     int erow_ld;
     int Mp;
     long long g8_slice;                  // bytes between slices
+    long long cap_rows;                  // allocated rows of g8 / k8 (chunk-major layout)
     double xi;
     int xi_int;
     __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
@@ -171,7 +180,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
                 w.y = (int)gather_byte(u + 4, b);
                 w.z = (int)gather_byte(u + 8, b);
                 w.w = (int)gather_byte(u + 12, b);
-                *reinterpret_cast<int4*>(g8 + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+                *reinterpret_cast<int4*>(g8 + (long long)t * g8_slice + cm_off(cap_rows, row, col0)) = w;
             }
         }
         // energy partial of this 16-column chunk
@@ -187,7 +196,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
                 w.y = (int)gather_byte(u + 4, b);
                 w.z = (int)gather_byte(u + 8, b);
                 w.w = (int)gather_byte(u + 12, b);
-                *reinterpret_cast<int4*>(k8 + (long long)t * g8_slice + (long long)row * Mp + col0) = w;
+                *reinterpret_cast<int4*>(k8 + (long long)t * g8_slice + cm_off(cap_rows, row, col0)) = w;
             }
         }
     }
@@ -401,7 +410,7 @@ static int build_problems(sgpr_context* h, int which, std::vector<Problem>& prob
             P.N = m1 - m0;
             P.Kpad = h->i8_kp1;
             SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>(), kNS, cap, P.Kpad, cap, BM));
-            SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * h->i8_kp1, kNS, P.N, P.Kpad, (long long)h->M, BN));
+            SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * 64, kNS, P.N, P.Kpad, (long long)h->M, BN));
         } else if (which == 2) {
             P.N = dp.D;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
@@ -515,6 +524,7 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
     e.erow_ld = (int)h->n_active + 1;
     e.Mp = h->i8_mp;
     e.g8_slice = (long long)h->i8_cap_rows * h->i8_mp;
+    e.cap_rows = (long long)h->i8_cap_rows;
     e.xi = h->xi;
     e.xi_int = h->xi_int;
     return h->i8_tr == 8 ? launch<8>(h, common_d(h, 1), probs_d, e, st) : launch<7>(h, common_d(h, 1), probs_d, e, st);

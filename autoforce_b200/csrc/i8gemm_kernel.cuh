@@ -69,6 +69,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -131,9 +137,9 @@ __device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
 }
 
 struct Problem {
-    CUtensorMap mapA;    // int8 [NS][rowsA][Kpad], box {64, 128, NS}; covers the WHOLE operand buffer (all species' rows):
+    CUtensorMap mapA;    // int8 [NS][Kpad/64][rowsA][64], box {64, 128, 1, NS}; covers the WHOLE operand buffer (all species' rows):
                          // the problem's first row comes from Common::row0
-    CUtensorMap mapB;    // int8 [NS][rowsB][Kpad], box {64,  64, NS}
+    CUtensorMap mapB;    // int8 [NS][Kpad/64][rowsB][64], box {64,  64, 1, NS}
     int M, N, Kpad;      // N columns; Kpad multiple of 64 (zero padded); M unused (Common::M)
     const int* nk_tn;    // optional [ceil(N/64)]: K chunks (of 64) that can be non-zero for column tile tn; nullptr =
                          // Kpad / 64 for every tile.  Lets a triangular B (choli) skip its zero part; 0 = the tile
@@ -270,8 +276,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
                 if (elect_one()) {
                     uint8_t* sa = smem + (size_t)stage * SC::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], SC::STAGE_BYTES);
-                    tma_load_3d(sa, &P.mapA, &full_bar[stage], kt * BKB, cm.row0[pi] + tm * BM, 0);
-                    tma_load_3d(sa + SC::A_BYTES, &P.mapB, &full_bar[stage], kt * BKB, tn * BN, 0);
+                    // operands are stored K-chunk-major ([slice][chunk][row][64 B]): the 128 (64) rows of one chunk are
+                    // ONE contiguous 8 (4) KB block per slice, i.e. whole cache lines on the L2 -> SM path
+                    tma_load_4d(sa, &P.mapA, &full_bar[stage], 0, cm.row0[pi] + tm * BM, kt, 0);
+                    tma_load_4d(sa + SC::A_BYTES, &P.mapB, &full_bar[stage], 0, tn * BN, kt, 0);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {

@@ -30,6 +30,26 @@ static int make_map(CUtensorMap* m, void* base, int ns, int rows, int Kpad, int 
     return (int)r;
 }
 
+// production layout: K-chunk-major [slice][chunk of 64][row][64]  (4-D map, box {64, rows, 1, ns})
+static int make_map_cm(CUtensorMap* m, void* base, int ns, int rows, int Kpad, int box_rows) {
+    static EncodeFn enc = get_encode();
+    cuuint64_t dims[4] = {64, (cuuint64_t)rows, (cuuint64_t)(Kpad / 64), (cuuint64_t)ns};
+    cuuint64_t strides[3] = {64, (cuuint64_t)rows * 64, (cuuint64_t)rows * Kpad};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, (cuuint32_t)ns};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, getenv("PROMO") ? (CUtensorMapL2promotion)atoi(getenv("PROMO")) : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled (chunk-major) failed: %d\n", (int)r);
+    return (int)r;
+}
+static void to_chunk_major(const std::vector<int8_t>& in, int rows, int Kpad, int ns, std::vector<int8_t>& out) {
+    out.assign(in.size(), 0);
+    for (int t = 0; t < ns; ++t)
+        for (int r = 0; r < rows; ++r)
+            for (int k = 0; k < Kpad; ++k)
+                out[(size_t)t * rows * Kpad + (size_t)(k / 64) * rows * 64 + (size_t)r * 64 + k % 64] = in[((size_t)t * rows + r) * Kpad + k];
+}
+
 // host slicing: x in [-1,1] -> ns balanced base-128 digits, most significant first
 static void slice_rows(const std::vector<double>& X, int rows, int K, int Kpad, int ns, std::vector<int8_t>& out) {
     out.assign((size_t)ns * rows * Kpad, 0);
@@ -96,11 +116,22 @@ int main(int argc, char** argv) {
     cudaMemcpy(dA, As.data(), As.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dB, Bs.data(), Bs.size(), cudaMemcpyHostToDevice);
     cudaMemset(dC, 0, (size_t)M * N * 8);
+    // the production kernel reads K-chunk-major operands, the experimental A-in-TMEM kernel row-major ones
+    std::vector<int8_t> Ac, Bc;
+    to_chunk_major(As, M, Kpad, ns, Ac);
+    to_chunk_major(Bs, N, Kpad, ns, Bc);
+    int8_t *dAc, *dBc;
+    cudaMalloc(&dAc, Ac.size());
+    cudaMalloc(&dBc, Bc.size());
+    cudaMemcpy(dAc, Ac.data(), Ac.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(dBc, Bc.data(), Bc.size(), cudaMemcpyHostToDevice);
     Problem P;
     P.M = M; P.N = N; P.Kpad = Kpad;
-    if (make_map(&P.mapA, dA, ns, M, Kpad, BM) || make_map(&P.mapB, dB, ns, N, Kpad, BN)) return 1;
+    P.nk_tn = nullptr;
+    if (make_map_cm(&P.mapA, dAc, ns, M, Kpad, BM) || make_map_cm(&P.mapB, dBc, ns, N, Kpad, BN)) return 1;
     ProblemTA PT;
-    PT.mapA = P.mapA; PT.mapB = P.mapB; PT.M = M; PT.N = N; PT.Kpad = Kpad;
+    if (make_map(&PT.mapA, dA, ns, M, Kpad, BM) || make_map(&PT.mapB, dB, ns, N, Kpad, BN)) return 1;
+    PT.M = M; PT.N = N; PT.Kpad = Kpad;
     PT.A = (const signed char*)dA;
     PT.a_slice = (long long)M * Kpad;
     PT.a_ld = Kpad;

@@ -156,9 +156,12 @@ __global__ void row_energy_kernel(int n_rows, RowSpecies rs, const int* __restri
 
 __global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ atoms, const double* __restrict__ fcell,
                                       const unsigned char* __restrict__ owned, double* __restrict__ F,
-                                      unsigned char* __restrict__ owned_out) {
+                                      unsigned char* __restrict__ owned_out, const long long* __restrict__ parity_src = nullptr,
+                                      long long parity_stride = 0) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= N) return;
+    // fused exchange step: the buffer of the step that has just been published (counter already advanced)
+    if (parity_src && (((*parity_src) - 1) & 1)) fcell += parity_stride;
     const int i = meta_orig(atoms[c].meta);
     F[3 * (size_t)i] = fcell[3 * c];
     F[3 * (size_t)i + 1] = fcell[3 * c + 1];
@@ -323,10 +326,17 @@ __global__ void env_kernel_rows_kernel(int n_env, int M, int D, int ldp, const d
 // flag per (rank, step parity) doubles as the barrier after which a rank may read the forces its peers added to it
 // ---------------------------------------------------------------------------------
 // mailbox block of one rank: [2 parities][world slots][16 doubles]; slot r = {E, W[9], -, ..., stamp (int64 at [15])}
-__global__ void p2p_publish_kernel(int rank, int world, int parity, P2PPeers peers, const double* __restrict__ ew_local,
+__global__ void p2p_zero_next_kernel(double* __restrict__ own_base, long long stride, long long n,
+                                     const long long* __restrict__ step_counter) {
+    // the accumulation buffer of the NEXT step (the one this step does not use)
+    double* dst = own_base + ((((*step_counter) & 1) == 0) ? stride : 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = 0.0;
+}
+__global__ void p2p_publish_kernel(int rank, int world, P2PPeers peers, const double* __restrict__ ew_local,
                                    long long* __restrict__ step_counter) {
     // every earlier kernel of this stream (the force kernel with its remote red.add) has completed
     const long long stamp = *step_counter + 1;
+    const int parity = (int)((*step_counter) & 1);
     const int r = threadIdx.x;
     if (r < world) {
         double* slot = peers.mail[r] + ((size_t)parity * world + rank) * 16;
@@ -339,12 +349,13 @@ __global__ void p2p_publish_kernel(int rank, int world, int parity, P2PPeers pee
     __syncthreads();
     if (threadIdx.x == 0) *step_counter = stamp;
 }
-__global__ void p2p_wait_reduce_kernel(int world, int parity, const double* __restrict__ my_mail,
+__global__ void p2p_wait_reduce_kernel(int world, const double* __restrict__ my_mail,
                                        const long long* __restrict__ step_counter, double* __restrict__ E,
                                        double* __restrict__ W, long long* __restrict__ status) {
     __shared__ double acc[SGPR_MAX_RANKS][10];
     __shared__ int timed_out;
     const long long stamp = *step_counter;   // set by this step's publish kernel
+    const int parity = (int)((stamp - 1) & 1);
     const int r = threadIdx.x;
     if (r == 0) timed_out = 0;
     __syncthreads();
@@ -932,11 +943,13 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
         // fused exchange step: the accumulation buffer of the NEXT step is cleared now (its last readers finished in
         // the previous step of this stream; remote ranks touch it only after they have seen this step's flag)
         SGPR_TRY(h->p2p_local.ensure(sizeof(double) * 16 + sizeof(long long) * 2));
-        if (!h->p2p_counter_init) {
-            SGPR_CUDA(cudaMemsetAsync(h->p2p_local.p, 0, sizeof(double) * 16 + sizeof(long long) * 2, st));
+        if (!h->p2p_counter_init) {   // (always a sizing step: never inside a graph capture)
+            SGPR_CUDA(cudaStreamSynchronize(st));
+            SGPR_CUDA(cudaMemset(h->p2p_local.p, 0, sizeof(double) * 16 + sizeof(long long) * 2));
             h->p2p_counter_init = true;
         }
-        SGPR_CUDA(cudaMemsetAsync((void*)(uintptr_t)px->own_next, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
+        p2p_zero_next_kernel<<<h->sm_count, 256, 0, st>>>(px->own_base, px->stride, 3 * ((long long)N + 1),
+                                                          reinterpret_cast<const long long*>(h->p2p_local.as<double>() + 16));
         E_d = h->p2p_local.as<double>();        // this rank's partial sums
         W_d = h->p2p_local.as<double>() + 1;
     }
@@ -957,6 +970,8 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
             peers.bounds[r] = (int)((N * r) / world);
         }
         peers.bounds[world] = (int)N;
+        peers.parity_src = px ? reinterpret_cast<const long long*>(h->p2p_local.as<double>() + 16) : nullptr;
+        peers.parity_stride = px ? px->stride : 0;
         h->p2p_rank = rank;
     }
     const unsigned char* owned = h->active_all ? nullptr : h->owned.as<unsigned char>();
@@ -1047,12 +1062,12 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     }
     if (px) {
         long long* counter = reinterpret_cast<long long*>(h->p2p_local.as<double>() + 16);
-        p2p_publish_kernel<<<1, 32, 0, st>>>(rank, world, px->parity, px->peers, h->p2p_local.as<double>(), counter);
-        p2p_wait_reduce_kernel<<<1, 32, 0, st>>>(world, px->parity, px->peers.mail[rank], counter, E_out, W_out,
-                                                 h->status_d.as<long long>());
+        p2p_publish_kernel<<<1, 32, 0, st>>>(rank, world, px->peers, h->p2p_local.as<double>(), counter);
+        p2p_wait_reduce_kernel<<<1, 32, 0, st>>>(world, px->peers.mail[rank], counter, E_out, W_out, h->status_d.as<long long>());
         if (N > 0)
-            scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), px->own_now,
-                                                                          h->owned.as<unsigned char>(), px->F_d, px->owned_d);
+            scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), px->own_base,
+                                                                          h->owned.as<unsigned char>(), px->F_d, px->owned_d,
+                                                                          counter, px->stride);
         h->stats.kernel_launches += 3;
         SGPR_CUDA(cudaGetLastError());
     }
@@ -1103,10 +1118,10 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
     for (int r = 0; r < SGPR_MAX_RANKS; ++r) key.peer[r] = (peer_f_h && r < world) ? peer_f_h[r] : 0;
     for (int i = 0; i < 9; ++i) key.cell[i] = cell_h[i];
     if (px) {
-        key.px_parity = 1 + px->parity;
+        key.px_on = 1;
         key.px_ptr[0] = px->F_d;
         key.px_ptr[1] = px->owned_d;
-        key.px_ptr[2] = px->own_now;
+        key.px_ptr[2] = px->own_base;
         for (int r = 0; r < SGPR_MAX_RANKS; ++r) key.px_mail[r] = (uint64_t)(uintptr_t)px->peers.mail[r];
     }
     for (auto& e : h->graphs) {
@@ -1232,23 +1247,20 @@ extern "C" __attribute__((visibility("default"))) int sgpr_predict_p2p(sgpr_hand
 extern "C" __attribute__((visibility("default"))) int sgpr_p2p_step(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d,
                                                                     const double* cell_h, const int32_t* pbc_h, int32_t rank,
                                                                     int32_t world, void* stream, const uint64_t* peer_base_h,
-                                                                    int32_t parity, double* E_d, double* F_d, double* W_d,
-                                                                    uint8_t* owned_d) {
-    if (!h || !peer_base_h || !F_d || !E_d || !W_d || world < 2 || world > SGPR_MAX_RANKS || rank < 0 || rank >= world ||
-        (parity != 0 && parity != 1)) {
+                                                                    double* E_d, double* F_d, double* W_d, uint8_t* owned_d) {
+    if (!h || !peer_base_h || !F_d || !E_d || !W_d || world < 2 || world > SGPR_MAX_RANKS || rank < 0 || rank >= world) {
         set_error("sgpr_p2p_step: bad argument (2 <= world <= %d)", SGPR_MAX_RANKS);
         return SGPR_ERR_INVALID;
     }
     const size_t stride = 3 * (size_t)N + 8;                 // doubles per accumulation buffer
     uint64_t peer_f[SGPR_MAX_RANKS];
     P2PStep px{};
-    px.parity = parity;
     for (int r = 0; r < world; ++r) {
-        peer_f[r] = peer_base_h[r] + sizeof(double) * stride * (size_t)parity;
+        peer_f[r] = peer_base_h[r];                          // buffer 0; the step parity is applied on the device
         px.peers.mail[r] = reinterpret_cast<double*>((uintptr_t)(peer_base_h[r] + sizeof(double) * 2 * stride));
     }
-    px.own_now = reinterpret_cast<const double*>((uintptr_t)peer_f[rank]);
-    px.own_next = peer_base_h[rank] + sizeof(double) * stride * (size_t)(1 - parity);
+    px.own_base = reinterpret_cast<double*>((uintptr_t)peer_base_h[rank]);
+    px.stride = (long long)stride;
     px.F_d = F_d;
     px.owned_d = owned_d;
     return predict_impl(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, nullptr, W_d, nullptr, nullptr, peer_f,

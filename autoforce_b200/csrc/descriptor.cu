@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
     double Wacc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) Wacc[q] = 0.0;
+    // fused exchange step: which of the peers' two accumulation buffers this step adds into (device-side step parity)
+    const long long peer_off = (out.peers.world > 0 && out.peers.parity_src && ((*out.peers.parity_src) & 1)) ? out.peers.parity_stride : 0;
 
     // row of the environment after next (one iteration of lead time so that the prefetch below never waits on it)
     const int env_stride = gridDim.x * nwarps;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
 #pragma unroll
                 for (int q = 1; q < SGPR_MAX_RANKS; ++q)
                     if (q < out.peers.world && j >= out.peers.bounds[q]) r = q;
-                double* dst = out.peers.peer_f[r] + 3 * (size_t)j;
+                double* dst = out.peers.peer_f[r] + peer_off + 3 * (size_t)j;
                 atomicAdd(dst, -Gx);
                 atomicAdd(dst + 1, -Gy);
                 atomicAdd(dst + 2, -Gz);
@@ -565,9 +567,10 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         Fy = warp_sum(Fy);
         Fz = warp_sum(Fz);
         if (lane == 0 && own_i) {
-            atomicAdd(out.fcell + 3 * (size_t)c, Fx);
-            atomicAdd(out.fcell + 3 * (size_t)c + 1, Fy);
-            atomicAdd(out.fcell + 3 * (size_t)c + 2, Fz);
+            double* fown = out.fcell + peer_off;
+            atomicAdd(fown + 3 * (size_t)c, Fx);
+            atomicAdd(fown + 3 * (size_t)c + 1, Fy);
+            atomicAdd(fown + 3 * (size_t)c + 2, Fz);
         }
         __syncwarp();
     }

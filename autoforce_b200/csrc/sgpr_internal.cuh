@@ -186,7 +186,7 @@ struct sgpr_context {
         const void* ptr[7];                 // pos, Z, E, F, W, beta, owned
         uint64_t peer[SGPR_MAX_RANKS];      // peer force buffers (p2p exchange)
         double cell[9];
-        long long px_parity;                // fused exchange step: 1 + parity, else 0
+        long long px_on;                    // fused exchange step
         const void* px_ptr[3];
         uint64_t px_mail[SGPR_MAX_RANKS];
     };
@@ -253,6 +253,10 @@ struct PeerForces {
     double* peer_f[SGPR_MAX_RANKS];
     int bounds[SGPR_MAX_RANKS + 1];   // first cell-order index owned by each rank
     int world;                        // 0 = disabled
+    // fused exchange step: two accumulation buffers per rank alternate between steps; WHICH one is decided on the
+    // device (low bit of the step counter), so that the launch arguments -- and the CUDA graph -- never change
+    const long long* parity_src;      // nullptr: peer_f as given
+    long long parity_stride;          // doubles between the two buffers
 };
 int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned char* owned_d, cudaStream_t st,
                               const PeerForces* peers = nullptr);
@@ -262,9 +266,8 @@ struct P2PPeers {
 };
 struct P2PStep {
     P2PPeers peers;
-    int parity;                       // which of the two accumulation buffers / mailbox halves this step uses
-    const double* own_now;            // own accumulation buffer of this step
-    uint64_t own_next;                // ... of the next step (cleared at the start of this one)
+    double* own_base;                 // this rank's two accumulation buffers (stride doubles apart)
+    long long stride;
     double* F_d;
     uint8_t* owned_d;
 };

@@ -54,7 +54,7 @@ EXPORTS = {
                                    c_void_p, c_void_p, c_void_p]),
     "sgpr_p2p_collect": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_p2p_step": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
-                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_forward": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sgpr_kernel_jacobian": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -140,7 +140,7 @@ class PeerForceExchange:
         eng = self.engine
         p = self.parity
         if self.fused:
-            eng.p2p_step(pos_t, z_t, cell, pbc, self.rank, self.world, self._bases, p, self.ew, self.F, self.owned)
+            eng.p2p_step(pos_t, z_t, cell, pbc, self.rank, self.world, self._bases, self.ew, self.F, self.owned)
         else:
             import torch.distributed as dist
 
@@ -324,14 +324,14 @@ class SgprEngine:
                                                    _ptr(cell_h), _ptr(pbc_h), int(rank), int(world), self._stream(), _ptr(peers),
                                                    c_void_p(ew.data_ptr()), c_void_p(ew.data_ptr() + 8)))
 
-    def p2p_step(self, pos_t, z_t, cell, pbc, rank, world, bases, parity, ew, F, owned):
+    def p2p_step(self, pos_t, z_t, cell, pbc, rank, world, bases, ew, F, owned):
         """``sgpr_p2p_step``: the fused exchange step (include/sgpr_b200.h).  ``bases`` uint64 [world]: every rank's
         symmetric block as mapped on this device; ``ew`` [10] receives the reduced E and 3x3 virial."""
         cell_h, pbc_h = self._geom(cell, pbc)
         bases = np.ascontiguousarray(bases, dtype=np.uint64)
         _check(self.lib, self.lib.sgpr_p2p_step(self._h, z_t.numel(), c_void_p(pos_t.data_ptr()), c_void_p(z_t.data_ptr()),
                                                 _ptr(cell_h), _ptr(pbc_h), int(rank), int(world), self._stream(), _ptr(bases),
-                                                int(parity), c_void_p(ew.data_ptr()), c_void_p(F.data_ptr()),
+                                                c_void_p(ew.data_ptr()), c_void_p(F.data_ptr()),
                                                 c_void_p(ew.data_ptr() + 8), c_void_p(owned.data_ptr())))
 
     def p2p_collect(self, own_buf, F, owned):

@@ -163,8 +163,10 @@ int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double*
 /* The whole exchange step in ONE call and without any collective library: sgpr_predict_p2p + the all-reduce of E and the
  * 3x3 virial (calculator/active.py:562,602) + sgpr_p2p_collect.  Every rank owns one symmetric block of peer-mapped
  * memory (zero-initialised, e.g. torch symmetric memory), laid out in doubles as
- *     [2][3N + 8]      force accumulation buffers (cell order); steps alternate between them (`parity` = step & 1)
- *     [2][world][16]   mailboxes: slot r of half `parity` = rank r's {E, W[9]} and a 64-bit step stamp at [15]
+ *     [2][3N + 8]      force accumulation buffers (cell order); steps alternate between them
+ *     [2][world][16]   mailboxes: slot r of one half = rank r's {E, W[9]} and a 64-bit step stamp at [15]
+ * (which half a step uses is the low bit of a step counter that lives on the device: the arguments of a warm step are
+ * identical from step to step, so it replays as ONE CUDA graph)
  * peer_base_h[r] = base address of rank r's block as mapped on THIS device.  Per step each rank
  *   1. clears its accumulation buffer of the next step,  2. evaluates the environments it owns (forces on atoms of other
  *   ranks are added into their buffers over NVLink),  3. writes its E and virial into EVERY rank's mailbox and then
@@ -172,11 +174,11 @@ int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double*
  *   rank's force kernel has then finished -- and sums the world contributions in rank order (bit-identical on all
  *   ranks),  5. copies its own forces to F_d [N,3] (caller's order, rows of owned atoms) and fills owned_d [N].
  * E_d [1], W_d [9], F_d, owned_d are device pointers; everything is enqueued on `stream` (warm steps: one CUDA graph,
- * no host synchronisation -- see "Asynchronous steps").  All ranks must call it once per step with the same parity.
+ * no host synchronisation -- see "Asynchronous steps").  All ranks must call it once per step, the same number of times.
  * A peer that never arrives is given up after 10 s (reported by sgpr_check); the GPU is never left spinning. */
 int sgpr_p2p_step(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
                   const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, const uint64_t* peer_base_h,
-                  int32_t parity, double* E_d, double* F_d, double* W_d, uint8_t* owned_d);
+                  double* E_d, double* F_d, double* W_d, uint8_t* owned_d);
 
 /* Kernel matrix cov = model.gp.kern(atoms, model.X)  (calculator/active.py:464,
  * regression/gppotential.py:47-50,63-64; similarity/similarity.py:17-31).

@@ -706,7 +706,7 @@ def test_fused_exchange_step_emulated_on_one_gpu(world):
             torch.cuda.synchronize()
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
-                    engines[r].p2p_step(pos_t, z_t, cell, True, r, world, bases, step & 1, ews[r], Fs[r], owns[r])
+                    engines[r].p2p_step(pos_t, z_t, cell, True, r, world, bases, ews[r], Fs[r], owns[r])
             torch.cuda.synchronize()
             for e in engines:
                 e.check()

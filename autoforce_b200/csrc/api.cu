@@ -753,6 +753,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->i8_tr = (trs && atoi(trs) == 8) ? 8 : 7;
         const char* tr2 = getenv("SGPR_I8_TR2");   // back projection (forces only): like the kernel matrix, or 6 / 7 / 8
         h->i8_tr2 = tr2 ? (atoi(tr2) == 8 ? 8 : atoi(tr2) == 6 ? 6 : 7) : h->i8_tr;
+        const char* nss = getenv("SGPR_I8_NS");
+        h->i8_ns = (nss && atoi(nss) == 5) ? 5 : 6;
         if (h->use_i8) {
             st = i8_prepare_model(h, false);
             if (st == SGPR_OK) st = i8_prepare_covloss(h);
@@ -911,7 +913,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
 static bool warm_possible(sgpr_handle h, int64_t N, const int32_t* pbc_h, int32_t rank, int32_t world, bool p2p, bool beta) {
     const bool halo_mode = world > 1 && !p2p;
     return h->use_i8 && pbc_h[0] && pbc_h[1] && pbc_h[2] && !halo_mode && h->warm_ok && N == h->warm_N &&
-           rank == h->warm_rank && world == h->warm_world && beta == h->warm_beta && !h->timing;
+           rank == h->warm_rank && world == h->warm_world && beta == h->warm_beta;
 }
 
 static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int32_t* Z_d, const double* cell_h,
@@ -1104,7 +1106,7 @@ static int predict_impl(sgpr_handle h, int64_t N, const double* pos_d, const int
                         const int32_t* pbc_h, int32_t rank, int32_t world, void* stream, double* E_d, double* F_d,
                         double* W_d, double* beta_d, uint8_t* owned_d, const uint64_t* peer_f_h, bool allow_warm,
                         const P2PStep* px = nullptr) {
-    if (!h || !pbc_h || !cell_h || !h->use_graph || !allow_warm || world > SGPR_MAX_RANKS ||
+    if (!h || !pbc_h || !cell_h || !h->use_graph || h->timing || !allow_warm || world > SGPR_MAX_RANKS ||
         !warm_possible(h, N, pbc_h, rank, world, peer_f_h != nullptr, beta_d != nullptr))
         return predict_body(h, N, pos_d, Z_d, cell_h, pbc_h, rank, world, stream, E_d, F_d, W_d, beta_d, owned_d, peer_f_h, allow_warm, px);
     cudaStream_t st = (cudaStream_t)stream;

@@ -409,13 +409,14 @@ static int build_problems(sgpr_context* h, int which, std::vector<Problem>& prob
         if (which == 1) {
             P.N = m1 - m0;
             P.Kpad = h->i8_kp1;
-            SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>(), kNS, cap, P.Kpad, cap, BM));
-            SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * 64, kNS, P.N, P.Kpad, (long long)h->M, BN));
+            const int ns1 = (h->i8_ns == 5 && h->i8_tr == 7) ? 5 : kNS;
+            SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>(), ns1, cap, P.Kpad, cap, BM));
+            SGPR_TRY(make_map(&P.mapB, h->z8.as<signed char>() + (size_t)m0 * 64, ns1, P.N, P.Kpad, (long long)h->M, BN));
         } else if (which == 2) {
             P.N = dp.D;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
             // t + u <= 6 uses the 5 most significant digit slices of both operands (same buffers, same slice stride)
-            const int ns2 = h->i8_tr2 == 6 ? 5 : kNS;
+            const int ns2 = (h->i8_tr2 == 6 || (h->i8_ns == 5 && h->i8_tr2 == 7)) ? 5 : kNS;
             SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>(), ns2, cap, h->i8_mp, cap, BM));
             SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, ns2, dp.D, h->i8_mp, (long long)dp.D, BN));
         } else {
@@ -450,7 +451,7 @@ static void count_work(sgpr_context* h, int which) {
             h->stats.covloss_flops += 2.0 * M * (double)h->M * (m1 - m0);
         } else {
             const int tr = which == 2 ? h->i8_tr2 : h->i8_tr;
-            const int npairs = tr == 8 ? 26 : tr == 6 ? 15 : 21;
+            const int npairs = tr == 8 ? 26 : tr == 6 ? 15 : (h->i8_ns == 5 ? 19 : 21);
             const double N = which == 1 ? (m1 - m0) : dp.D;
             const double Kpad = which == 1 ? h->i8_kp1 : ((m1 - m0) + 63) / 64 * 64;
             h->stats.gemm_flops += 2.0 * M * N * (which == 1 ? dp.D : (m1 - m0));
@@ -470,7 +471,7 @@ static int device_problems(sgpr_context* h, int which, cudaStream_t st, const Pr
     mix((unsigned long long)(uintptr_t)h->p8.p); mix((unsigned long long)(uintptr_t)h->g8.p); mix((unsigned long long)(uintptr_t)h->k8.p);
     mix((unsigned long long)(uintptr_t)h->z8.p); mix((unsigned long long)(uintptr_t)h->zt8.p); mix((unsigned long long)(uintptr_t)h->c8.p);
     mix((unsigned long long)(uintptr_t)h->cov_nk.p); mix((unsigned long long)(uintptr_t)h->i8_probs.p);
-    mix(h->i8_cap_rows); mix(h->M); mix(h->i8_kp1); mix(h->i8_mp); mix(h->i8_tr2); mix(h->i8_model_version);
+    mix(h->i8_cap_rows); mix(h->M); mix(h->i8_kp1); mix(h->i8_mp); mix(h->i8_tr2); mix(h->i8_ns); mix(h->i8_model_version);
     for (int s = 0; s <= h->S; ++s) mix(h->m_first[s]);
     Problem* dev = h->i8_probs.as<Problem>() + slot * kMaxSpecies;
     if (h->i8_prob_sig[slot] != sig) {
@@ -527,6 +528,7 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
     e.cap_rows = (long long)h->i8_cap_rows;
     e.xi = h->xi;
     e.xi_int = h->xi_int;
+    if (h->i8_tr == 7 && h->i8_ns == 5) return launch_ns<5, 7>(h, common_d(h, 1), probs_d, e, st);
     return h->i8_tr == 8 ? launch<8>(h, common_d(h, 1), probs_d, e, st) : launch<7>(h, common_d(h, 1), probs_d, e, st);
 }
 
@@ -541,6 +543,7 @@ int i8_back_projection(sgpr_context* h, cudaStream_t st) {
     e.ldp = h->dp.ldp;
     e.mumax = h->i8_mumax;
     if (h->i8_tr2 == 6) return launch_ns<5, 6>(h, common_d(h, 2), probs_d, e, st);
+    if (h->i8_tr2 == 7 && h->i8_ns == 5) return launch_ns<5, 7>(h, common_d(h, 2), probs_d, e, st);
     return h->i8_tr2 == 8 ? launch<8>(h, common_d(h, 2), probs_d, e, st) : launch<7>(h, common_d(h, 2), probs_d, e, st);
 }
 

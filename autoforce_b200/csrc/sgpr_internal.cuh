@@ -151,6 +151,8 @@ struct sgpr_context {
     bool use_i8_now = false;    // ... for the current call (compat / K-matrix calls use the DMMA path)
     int i8_tr = 7;              // kernel matrix: truncation t + u <= i8_tr (7: 21 slice products, 8: 26)
     int i8_tr2 = 7;             // back projection: 7 / 8, or 6 (SGPR_I8_TR2=6: 15 products of 5 slices, ~4e-11 mumax on dE/dq_hat)
+    int i8_ns = 6;              // digit slices read by the GEMMs with t + u <= 7 (SGPR_I8_NS=5: the 5 most significant of the
+                                // 6 stored: 19 products, 38-bit operands)
     int i8_kp1 = 0, i8_mp = 0;  // K paddings (multiples of 64) of GEMM 1 (D) and GEMM 2 (max M_s)
     size_t i8_cap_rows = 0;     // row capacity of p8 / g8 (slice stride)
     double i8_mumax = 1.0;      // power of two >= max xi |mu|

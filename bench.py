@@ -403,7 +403,7 @@ def main():
     launches_per_step = eng.stats()["kernel_launches"] + (1 if px is not None else 0)
     # ---- stage split: a separate, untimed pass with CUDA events between the stages inside the library
     eng.enable_timing(True)
-    stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "i8_ops": 0.0}
+    stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_beta": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "i8_ops": 0.0}
     n_stage = max(1, min(args.steps, 10))
     for it in range(n_stage):
         step_device(it)
@@ -411,9 +411,12 @@ def main():
         for k in stage:
             stage[k] += st_[k]
         stage["n_active"], stage["n_pairs"] = st_["n_active"], st_["n_pairs"]
-    for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total", "gemm_flops", "i8_ops"):
+    for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_beta", "ms_total", "gemm_flops", "i8_ops"):
         stage[k] /= n_stage
     eng.enable_timing(False)
+    if os.environ.get("SGPR_BENCH_ALLRANKS"):
+        print(f"rank {rank}: " + " ".join(f"{k[3:]}={stage[k]:.4f}" for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_beta", "ms_total")),
+              file=sys.stderr, flush=True)
     # ---- end-to-end leg: host buffers through the public host API (H2D + D2H inside)
     ms_e2e, wall_e2e = timed(step_host, args.steps, args.warmup)
     eng.check()
@@ -566,7 +569,8 @@ def main():
                          "int8_ops_per_step": stage["i8_ops"], "useful_int8_ops_per_step": 21 * stage["gemm_flops"],
                          "flops_per_step": stage["gemm_flops"], "gemm_ms_per_step": stage["ms_gemm"]},
             "roofline_stages": stages,
-            "stages_ms_per_step": {k[3:]: stage[k] for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total")},
+            "stages_ms_per_step": dict({k[3:]: stage[k] for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_total")},
+                                       **({"exchange": stage["ms_beta"]} if world > 1 else {})),
             "pairs": int(stage.get("n_pairs", 0)), "active_envs_rank0": int(stage.get("n_active", 0)),
             "parity": parity,
         }

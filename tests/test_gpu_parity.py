@@ -725,3 +725,27 @@ def test_fused_exchange_step_emulated_on_one_gpu(world):
     finally:
         for e in engines + [ref]:
             e.close()
+
+
+def test_more_than_eight_species_is_refused_loudly():
+    """The dense species table holds at most SGPR_MAX_SPECIES = 8 species (the reference's sparse [120,120] layout has no
+    such limit): a ninth species must be an error at construction, never a silent truncation."""
+    import autoforce_b200 as ab
+
+    g = load_golden("lipso108")
+    with pytest.raises(ValueError, match="at most 8 species"):
+        ab.SgprEngine(model_from_golden(g), species=[1, 3, 6, 7, 8, 9, 15, 16, 17])
+    # ... and an atom of a species the handle does not know is an error of the call, not a wrong number
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    Z = np.asarray(g["numbers"]).copy()
+    Z[0] = 79
+    with pytest.raises(RuntimeError, match="species table"):
+        eng.predict(g["pos"], Z, g["cell"], g["meta"]["pbc"])
+    E, F, W, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])     # the handle stays usable
+    assert abs(E - float(g["energy"])) / len(Z) < TOL_E_PER_ATOM
+    # the same in a WARM step (the error flag is read with the results)
+    with pytest.raises(RuntimeError, match="species table"):
+        eng.predict(g["pos"], Z, g["cell"], g["meta"]["pbc"])
+    E2, _, _, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    assert E2 == E
+    eng.close()

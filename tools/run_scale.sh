@@ -3,9 +3,9 @@
 n=$1; shift
 for wl in "$@"; do
   if [ "$n" = "1" ]; then
-    python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02_scale_${wl}_${n}gpu.json 2> gpurun_out/r02_scale_${wl}_${n}gpu.err
+    python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_scale_${wl}_${n}gpu.json 2> gpurun_out/r02_scale_${wl}_${n}gpu.err
   else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --workload $wl --steps 20 --warmup 3 > gpurun_out/r02_scale_${wl}_${n}gpu.json 2> gpurun_out/r02_scale_${wl}_${n}gpu.err
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --workload $wl --steps 20 --warmup 5 > gpurun_out/r02_scale_${wl}_${n}gpu.json 2> gpurun_out/r02_scale_${wl}_${n}gpu.err
   fi
   python -c "
 import json,sys

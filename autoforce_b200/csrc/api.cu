@@ -753,6 +753,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->i8_tr = (trs && atoi(trs) == 8) ? 8 : 7;
         const char* tr2 = getenv("SGPR_I8_TR2");   // back projection (forces only): like the kernel matrix, or 6 / 7 / 8
         h->i8_tr2 = tr2 ? (atoi(tr2) == 8 ? 8 : atoi(tr2) == 6 ? 6 : 7) : h->i8_tr;
+        const char* c2 = getenv("SGPR_I8_CTA2");
+        h->i8_cta2 = c2 && atoi(c2) == 1;
         const char* nss = getenv("SGPR_I8_NS");
         h->i8_ns = (nss && atoi(nss) == 5) ? 5 : 6;
         if (h->use_i8) {
@@ -782,11 +784,12 @@ extern "C" __attribute__((visibility("default"))) void sgpr_destroy(sgpr_handle 
                       &h->nl_first, &h->nl_pairs, &h->scan_tmp, &h->phat, &h->cbuf, &h->pnorm, &h->sflag, &h->gmat,
                       &h->gvec, &h->epart, &h->wpart, &h->fcell, &h->misc, &h->stage_pos, &h->stage_z, &h->stage_out,
                       &h->rowmap, &h->owned, &h->shard_tmp, &h->row_owned, &h->choli_t, &h->vscale_d, &h->clone_d,
-                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk, &h->row_first_d, &h->status_d, &h->p2p_local};
+                      &h->kcmat, &h->cpart, &h->nl_masks, &h->erow_part, &h->erow, &h->prow, &h->ttab, &h->z8, &h->zt8, &h->p8, &h->g8, &h->i8_probs, &h->k8, &h->c8, &h->crs, &h->nl_run, &h->cov_nk, &h->row_first_d, &h->status_d, &h->p2p_local, &h->i8_probs2};
     for (DevBuf* b : bufs) b->release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->i8_probs_pinned) cudaFreeHost(h->i8_probs_pinned);
     if (h->status_pinned) cudaFreeHost(h->status_pinned);
+    if (h->i8_probs2_pinned) cudaFreeHost(h->i8_probs2_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (int i = 0; i < 6; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -869,7 +872,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
                        const int32_t* pbc_h, cudaStream_t st, Geom* g, int rank = 0, int world = 1, bool i8 = false,
                        bool with_halo = true, bool with_k8 = false, bool warm = false) {
     h->use_i8_now = i8 && h->use_i8;
-    h->stats.i8_ops = 0.0;
+    if (!warm) h->stats.i8_ops = 0.0;      // warm steps: the work counters of the sizing step stay (same shape)
     h->fwd_valid = false;
     // geometry -> cell sort -> neighbour list -> descriptors (rows in species-major order)
     if (N < 0 || N > 0x7fffff00ll) {
@@ -878,7 +881,7 @@ static int stage_front(sgpr_context* h, int64_t N, const double* pos_d, const in
     }
     h->stats.n_atoms = N;
     h->stats.kernel_launches = 0;
-    h->stats.gemm_flops = 0.0;
+    if (!warm) h->stats.gemm_flops = 0.0;
     h->last_N = N;
     SGPR_TRY(build_geometry(h, N, pos_d, cell_h, pbc_h, st, g));
     h->last_geom = *g;
@@ -1040,7 +1043,7 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     h->stats.kernel_launches += 3;
     SGPR_CUDA(cudaGetLastError());
     if (h->timing) cudaEventRecord(h->ev[4], st);
-    h->stats.covloss_flops = 0.0;
+    if (!warm) h->stats.covloss_flops = 0.0;
     if (beta_d) {
         NvtxRange covloss_range("sgpr:covloss");
         const int n_part = h->use_i8_now ? i8_covloss_parts(h) : gemm_covloss_parts(h);

@@ -12,6 +12,7 @@
 // descriptors are normalised (|k| <= 1 by Cauchy-Schwarz); un-normalised models use the DMMA path.
 #include <math.h>
 
+#include "i8gemm2_kernel.cuh"
 #include "i8gemm_kernel.cuh"
 #include "sgpr_internal.cuh"
 
@@ -260,6 +261,23 @@ int launch(sgpr_context* h, const Common* cm_d, const Problem* probs_d, const Ep
     return launch_ns<kNS, TR, Epi>(h, cm_d, probs_d, epi, st);
 }
 
+// CTA-pair variant (i8gemm2_kernel.cuh): static cluster dims (2,1,1), one pair per TPC
+template <int NS, int TR, class Epi>
+int launch2(sgpr_context* h, const Common* cm_d, const Problem2* probs_d, const Epi& epi, cudaStream_t st) {
+    constexpr int STAGES = 3;
+    auto kern = i8gemm2_kernel<NS, TR, STAGES, Epi>;
+    const size_t smem = smem_bytes2<NS, STAGES>();
+    static bool done = false;
+    if (!done) {
+        SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    kern<<<h->sm_count & ~1, NTHREADS, smem, st>>>(cm_d, probs_d, epi);
+    SGPR_CUDA(cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return SGPR_OK;
+}
+
 // Work lists of the three grouped GEMMs from the species row ranges on the device (one warp).
 typedef I8Setup SetupDesc;
 __global__ void i8_setup_kernel(SetupDesc sd, const int* __restrict__ row_first, Common* __restrict__ out) {
@@ -491,6 +509,46 @@ static int device_problems(sgpr_context* h, int which, cudaStream_t st, const Pr
     return SGPR_OK;
 }
 
+// Problem2 descriptors (CTA-pair kernel) of GEMM 1 / 2, same caching rule as device_problems
+static int device_problems2(sgpr_context* h, int which, cudaStream_t st, const Problem2** out) {
+    const DescParams& dp = h->dp;
+    SGPR_TRY(h->i8_probs2.ensure(sizeof(Problem2) * 2 * kMaxSpecies));
+    if (!h->i8_probs2_pinned) SGPR_CUDA(cudaMallocHost(&h->i8_probs2_pinned, sizeof(Problem2) * 2 * kMaxSpecies));
+    const int slot = which - 1;
+    Problem2* dev = h->i8_probs2.as<Problem2>() + slot * kMaxSpecies;
+    const unsigned long long sig = h->i8_prob_sig[slot] ^ (unsigned long long)(uintptr_t)h->i8_probs2.p;
+    if (h->i8_prob2_sig[slot] != sig || sig == 0) {
+        const long long cap = (long long)h->i8_cap_rows;
+        std::vector<Problem2> probs;
+        for (int s = 0; s < h->S; ++s) {
+            const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
+            if (m1 == m0 || !dp.central_enabled[s]) continue;
+            Problem2 P;
+            if (which == 1) {
+                const int ns1 = (h->i8_ns == 5 && h->i8_tr == 7) ? 5 : kNS;
+                P.N = m1 - m0;
+                P.Kpad = h->i8_kp1;
+                SGPR_TRY(make_map(&P.mapA, h->p8.as<signed char>(), ns1, cap, P.Kpad, cap, BM));
+                SGPR_TRY(make_map(&P.mapBh, h->z8.as<signed char>() + (size_t)m0 * 64, ns1, P.N, P.Kpad, (long long)h->M, BNH));
+            } else {
+                const int ns2 = (h->i8_tr2 == 6 || (h->i8_ns == 5 && h->i8_tr2 == 7)) ? 5 : kNS;
+                P.N = dp.D;
+                P.Kpad = ((m1 - m0) + 63) / 64 * 64;
+                SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>(), ns2, cap, h->i8_mp, cap, BM));
+                SGPR_TRY(make_map(&P.mapBh, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, ns2, dp.D, h->i8_mp, (long long)dp.D, BNH));
+            }
+            probs.push_back(P);
+        }
+        Problem2* pin = (Problem2*)h->i8_probs2_pinned + slot * kMaxSpecies;
+        SGPR_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < probs.size(); ++i) pin[i] = probs[i];
+        if (!probs.empty()) SGPR_CUDA(cudaMemcpyAsync(dev, pin, sizeof(Problem2) * probs.size(), cudaMemcpyHostToDevice, st));
+        h->i8_prob2_sig[slot] = sig;
+    }
+    *out = dev;
+    return SGPR_OK;
+}
+
 static Common* common_d(sgpr_context* h, int which) {
     return reinterpret_cast<Common*>(h->i8_probs.as<Problem>() + 3 * kMaxSpecies) + (which - 1);
 }
@@ -528,6 +586,11 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
     e.cap_rows = (long long)h->i8_cap_rows;
     e.xi = h->xi;
     e.xi_int = h->xi_int;
+    if (h->i8_cta2 && h->i8_tr == 7) {
+        const Problem2* p2 = nullptr;
+        SGPR_TRY(device_problems2(h, 1, st, &p2));
+        return h->i8_ns == 5 ? launch2<5, 7>(h, common_d(h, 1), p2, e, st) : launch2<6, 7>(h, common_d(h, 1), p2, e, st);
+    }
     if (h->i8_tr == 7 && h->i8_ns == 5) return launch_ns<5, 7>(h, common_d(h, 1), probs_d, e, st);
     return h->i8_tr == 8 ? launch<8>(h, common_d(h, 1), probs_d, e, st) : launch<7>(h, common_d(h, 1), probs_d, e, st);
 }
@@ -542,6 +605,11 @@ int i8_back_projection(sgpr_context* h, cudaStream_t st) {
     e.gvec = h->gvec.as<double>();
     e.ldp = h->dp.ldp;
     e.mumax = h->i8_mumax;
+    if (h->i8_cta2 && h->i8_tr2 == 7) {
+        const Problem2* p2 = nullptr;
+        SGPR_TRY(device_problems2(h, 2, st, &p2));
+        return h->i8_ns == 5 ? launch2<5, 7>(h, common_d(h, 2), p2, e, st) : launch2<6, 7>(h, common_d(h, 2), p2, e, st);
+    }
     if (h->i8_tr2 == 6) return launch_ns<5, 6>(h, common_d(h, 2), probs_d, e, st);
     if (h->i8_tr2 == 7 && h->i8_ns == 5) return launch_ns<5, 7>(h, common_d(h, 2), probs_d, e, st);
     return h->i8_tr2 == 8 ? launch<8>(h, common_d(h, 2), probs_d, e, st) : launch<7>(h, common_d(h, 2), probs_d, e, st);

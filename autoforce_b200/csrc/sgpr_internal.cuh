@@ -165,6 +165,10 @@ struct sgpr_context {
     unsigned long long i8_prob_sig[3] = {0, 0, 0};   // what the uploaded descriptors were built from (addresses, shapes)
     sgpr::I8Setup i8_setup[3];
     int i8_nprob = 0;
+    bool i8_cta2 = false;        // SGPR_I8_CTA2=1: CTA-pair (cta_group::2) variant of the two hot GEMMs
+    sgpr::DevBuf i8_probs2;      // its problem descriptors
+    void* i8_probs2_pinned = nullptr;
+    unsigned long long i8_prob2_sig[2] = {0, 0};
     unsigned long long i8_model_version = 0;
     // ---- species row ranges / pair count stay on the device (sync-free steps)
     sgpr::DevBuf row_first_d;   // [S+1] first descriptor row of each central species (device copy of row_first)

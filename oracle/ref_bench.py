@@ -96,10 +96,13 @@ def run(workload, steps, warmup, procs=None, rep=None, variants=4, keep_dir=None
             p.kill()
             rc |= 1
         log.close()
-    if rc != 0 or not os.path.isfile(os.path.join(work, "result.json")):
-        tail = open(os.path.join(work, "worker0.log")).read()[-2000:]
-        raise RuntimeError(f"reference workers failed (rc={rc}):\n{tail}")
+    if not os.path.isfile(os.path.join(work, "result.json")):
+        tails = "\n".join(f"--- worker{r}.log\n" + open(os.path.join(work, f"worker{r}.log")).read()[-600:] for r in range(min(procs, 4)))
+        raise RuntimeError(f"reference workers failed (rc={rc}):\n{tails}")
+    # (rank 0 writes result.json atomically after the timed region and all collectives; a worker that trips over a
+    # closed socket while shutting down does not invalidate the measurement)
     out = json.load(open(os.path.join(work, "result.json")))
+    out["worker_exit_codes_ok"] = rc == 0
     out.update(work=work, procs=procs, rep=rep, M=int(model.M), workload=workload)
     return out
 
@@ -163,8 +166,22 @@ def _worker(args):
                    steps=args.steps, warmup=args.warmup, torch_threads=torch.get_num_threads(),
                    omp=os.environ.get("OMP_NUM_THREADS"), reference=ref_runner.reference_kind(),
                    node_seconds=dict(zip(["nl_desc", "kernel", "results", "covloss", "post"], nodes.mean(axis=0).tolist())))
-        with open(os.path.join(args.work, "result.json"), "w") as fh:
+        with open(os.path.join(args.work, "result.json.tmp"), "w") as fh:
             json.dump(res, fh)
+        os.replace(os.path.join(args.work, "result.json.tmp"), os.path.join(args.work, "result.json"))
+    # orderly shutdown of the gloo world behind the mpi4py stand-in: nobody leaves while a peer still talks, and the
+    # interpreter exits without running the process-group destructors (they abort if a peer's socket is already gone)
+    distrib.barrier()
+    try:
+        import torch.distributed as tdist
+
+        if tdist.is_initialized():
+            tdist.destroy_process_group()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

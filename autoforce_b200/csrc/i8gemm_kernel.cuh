@@ -171,6 +171,46 @@ struct Scheme {
     }
 };
 
+// MMA schedule of one 32-byte k-step.  The accumulator of slice pair (t, u) is group t + u - 2 at TMEM columns
+// (t + u - 2) * BN, and the B slices sit one after the other in shared memory ([slice][64 rows][64 B]).  For a fixed A
+// slice t the pairs u = 1 .. U_t therefore read CONSECUTIVE B rows and write CONSECUTIVE accumulator columns: they are
+// issued as ONE wide MMA (N = 64 * nu <= 256) instead of nu narrow ones.  A 128 x 64 x 32 MMA reads 4 KB of A and 2 KB of
+// B from shared memory in 32 cycles -- more than the 128 B/clk the SM can deliver -- so the narrow schedule (21 MMAs,
+// 126 KB of operand reads per k-step) is bound by shared-memory bandwidth, not by the tensor pipe; the wide schedule
+// (8 MMAs for NS = 6, TR = 7) reads each A slice once or twice: 74 KB per k-step.
+// Segments never mix accumulator groups that are written for the first time in a tile (overwrite) with groups that
+// already hold partial sums (accumulate).
+struct MmaSeg {
+    int t, u0, nu, fresh;
+};
+template <int NS, int TR>
+struct MmaPlan {
+    static constexpr int MAXSEG = 4 * NS;
+    MmaSeg seg[MAXSEG];
+    int n;
+    constexpr MmaPlan() : seg(), n(0) {
+        for (int t = 1; t <= NS; ++t) {
+            const int U = (TR - t < NS) ? (TR - t) : NS;
+            // highest group touched by the slices before t (nondecreasing in t)
+            const int prevmax = (t == 1) ? -1 : ((t + NS - 3 < TR - 2) ? (t + NS - 3) : (TR - 2));
+            int u0 = 1;
+            while (u0 <= U) {
+                const int g0 = t + u0 - 2;
+                const int fresh = g0 > prevmax;
+                int nu = U - u0 + 1;
+                if (nu > 4) nu = 4;
+                if (!fresh && g0 + nu - 1 > prevmax) nu = prevmax - g0 + 1;
+                seg[n].t = t;
+                seg[n].u0 = u0;
+                seg[n].nu = nu;
+                seg[n].fresh = fresh;
+                ++n;
+                u0 += nu;
+            }
+        }
+    }
+};
+
 // 16 TMEM columns of every accumulator group -> float64:  T = sum_g acc_g 256^(NG-1-g), combined exactly in
 // two int64 halves (|acc_g| < 2^27: hi < 2^51, lo < 2^43), one fma; result = T * 2^-(8 (NG-1) + 12).
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
@@ -291,7 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
     } else if (warp == 1) {
         // ===================== MMA issuer (converged warp, one elected lane issues; fully unrolled) ==========
         {
-            const uint32_t idesc = make_idesc_i8(BM, BN);
+            constexpr MmaPlan<NS, TR> plan{};
+            const uint32_t idesc_n[4] = {make_idesc_i8(BM, BN), make_idesc_i8(BM, 2 * BN), make_idesc_i8(BM, 3 * BN),
+                                         make_idesc_i8(BM, 4 * BN)};
             const uint64_t desc_hi = make_desc_sw64(0);      // everything but the start address
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
@@ -315,17 +357,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
 #pragma unroll
                     for (int ks = 0; ks < BKB / 32; ++ks) {
 #pragma unroll
-                        for (int t = 1; t <= NS; ++t) {
-#pragma unroll
-                            for (int u = 1; u <= NS; ++u) {
-                                if (t + u <= TR) {
-                                    // the first product of a tile into a group's accumulator overwrites it:
-                                    // groups 0..NS-1 are first reached at t == 1, the others at u == NS
-                                    const uint32_t accum = (ks == 0 && (t == 1 || u == NS)) ? later : 1u;
-                                    mma_i8(tmem_base + (t + u - 2) * BN, adesc + (((t - 1) * (BM * BKB) + ks * 32) >> 4),
-                                           bdesc + (((u - 1) * (BN * BKB) + ks * 32) >> 4), idesc, accum);
-                                }
-                            }
+                        for (int i = 0; i < plan.n; ++i) {
+                            const int t = plan.seg[i].t, u0 = plan.seg[i].u0, nu = plan.seg[i].nu;
+                            // the first product of a tile into a group's accumulator overwrites it
+                            const uint32_t accum = (ks == 0 && plan.seg[i].fresh) ? later : 1u;
+                            mma_i8(tmem_base + (t + u0 - 2) * BN, adesc + (((t - 1) * (BM * BKB) + ks * 32) >> 4),
+                                   bdesc + (((u0 - 1) * (BN * BKB) + ks * 32) >> 4), idesc_n[nu - 1], accum);
                         }
                     }
                     tc_commit(&empty_bar[stage]);       // smem stage is free once these MMAs retire

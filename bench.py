@@ -405,14 +405,15 @@ def main():
     eng.enable_timing(True)
     stage = {"ms_nl": 0.0, "ms_desc": 0.0, "ms_gemm": 0.0, "ms_force": 0.0, "ms_beta": 0.0, "ms_total": 0.0, "gemm_flops": 0.0, "i8_ops": 0.0}
     n_stage = max(1, min(args.steps, 10))
+    samples = {k: [] for k in stage}
     for it in range(n_stage):
         step_device(it)
         st_ = eng.stats()
-        for k in stage:
-            stage[k] += st_[k]
+        for k in samples:
+            samples[k].append(st_[k])
         stage["n_active"], stage["n_pairs"] = st_["n_active"], st_["n_pairs"]
     for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_beta", "ms_total", "gemm_flops", "i8_ops"):
-        stage[k] /= n_stage
+        stage[k] = statistics.median(samples[k])   # (the pass synchronises every step: a median, not a mean)
     eng.enable_timing(False)
     if os.environ.get("SGPR_BENCH_ALLRANKS"):
         print(f"rank {rank}: " + " ".join(f"{k[3:]}={stage[k]:.4f}" for k in ("ms_nl", "ms_desc", "ms_gemm", "ms_force", "ms_beta", "ms_total")),

@@ -116,24 +116,30 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // Phase B (expansion coefficients c[s][n][lm] = sum_j f_n(j) Y_lm(j)): one small GEMM per neighbour species on the
 // FP64 tensor cores -- M = lm (8-row tiles), N = n (8-column tiles), K = neighbours of the species (4 per step),
 // fragments read from the chunk buffer.  (TN, TL only shape the chunk-buffer rows.)
-template <int LMAX, int TN, int TL, bool ENV>
+// EXNB > 0: dp.nb == EXNB and dp.lmax == LMAX (bounds, strides and tile predicates fold at compile time)
+template <int LMAX, int TN, int TL, bool ENV, int EXNB>
 __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                            const int* __restrict__ row_of,
                                                            const unsigned* __restrict__ ptab,
                                                            const double* __restrict__ nnlk, double* __restrict__ phat,
                                                            double* __restrict__ cbuf, double* __restrict__ prow,
                                                            unsigned char* __restrict__ sflag, int per_warp_doubles,
-                                                           int stride, int nbp, signed char* __restrict__ p8,
+                                                           int stride_, int nbp_, signed char* __restrict__ p8,
                                                            long long p8_slice, int kp1) {
     extern __shared__ __align__(16) double smem[];
+    constexpr bool EXACT = EXNB > 0;
+    constexpr int kNbp = ((EXNB + TN - 1) / TN) * TN, kL2 = (LMAX + 1) * (LMAX + 1);
+    constexpr int kStride = (kNbp + ((kL2 + TL - 1) / TL) * TL) | 1;      // launch_forward's row stride
+    const int nbv = EXACT ? EXNB : dp.nb, lmaxv = EXACT ? LMAX : dp.lmax, L2v = EXACT ? kL2 : dp.L2;
+    const int L2p = EXACT ? (kL2 | 1) : dp.L2p, nbp = EXACT ? kNbp : nbp_, stride = EXACT ? kStride : stride_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* c_s = smem + (size_t)warp * per_warp_doubles;
     double* buf = c_s + ((dp.csize + 1) & ~1);          // [32][stride]: f[0..nb) | pad | Y[0..L2) | pad
     int* sp_s = reinterpret_cast<int*>(buf + 32 * stride);
     const int g8 = lane >> 2, t4 = lane & 3;   // DMMA fragment coordinates
     const bool all_species = dp.A <= 8 * ((kMaxNB + 7) / 8);
-    const int sp_stride = dp.nb * dp.L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
-    const int L = dp.lmax + 1;
+    const int sp_stride = nbv * L2p;  // c[s][n][lm] at (s*nb + n)*L2p + lm
+    const int L = lmaxv + 1;
     const int npairs = dp.A * (dp.A + 1) / 2;
     const bool cache_q = dp.D <= 32 * stride;            // packed row fits the (then idle) chunk buffer
     // column (s, n) of this lane's B fragments in the all-species product (loop invariant: no integer division inside)
@@ -142,8 +148,8 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
 #pragma unroll
     for (int nt = 0; nt < NT_; ++nt) {
         const int col = nt * 8 + (lane >> 2);
-        col_s[nt] = col / dp.nb;
-        col_n[nt] = col - col_s[nt] * dp.nb;
+        col_s[nt] = col / nbv;
+        col_n[nt] = col - col_s[nt] * nbv;
     }
     for (int env = blockIdx.x * nwarps + warp; env < n_env; env += gridDim.x * nwarps) {
         long long beg, end;
@@ -184,9 +190,9 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int lm = mt * 8 + g8, n = nt * 8 + 2 * t4;
-                    if (lm < dp.L2) {
-                        if (n < dp.nb) c_s[sp * sp_stride + n * dp.L2p + lm] += acc[mt][nt][0];
-                        if (n + 1 < dp.nb) c_s[sp * sp_stride + (n + 1) * dp.L2p + lm] += acc[mt][nt][1];
+                    if (lm < L2v) {
+                        if (n < nbv) c_s[sp * sp_stride + n * L2p + lm] += acc[mt][nt][0];
+                        if (n + 1 < nbv) c_s[sp * sp_stride + (n + 1) * L2p + lm] += acc[mt][nt][1];
                     }
                     acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
                 }
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                 if (!dp.nbr_enabled[sp]) R = 0.0;   // species outside the descriptor's `b` list
                 double* my = buf + lane * stride;
                 double fn = R;
-                for (int n = 0; n < dp.nb; ++n) {
+                for (int n = 0; n < nbv; ++n) {
                     my[n] = fn;
                     fn *= d2;
                 }
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     zs = kTinyAngle * y + z;
                 }
                 double* yo = my + nbp;
-                solid_harmonics<LMAX, false>(c_harm, dp.lmax, x, ys, zs,
+                solid_harmonics<LMAX, false>(c_harm, lmaxv, x, ys, zs,
                                              [&](int idx, double Y, double, double, double) { yo[idx] = Y; });
                 sp_s[lane] = sp;
             }
@@ -236,8 +242,8 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     }
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        if (mt * 8 < dp.L2) {
-                            const double av = (ok && mt * 8 + g8 < dp.L2) ? row[nbp + mt * 8 + g8] : 0.0;
+                        if (mt * 8 < L2v) {
+                            const double av = (ok && mt * 8 + g8 < L2v) ? row[nbp + mt * 8 + g8] : 0.0;
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt)
                                 if (nt * 8 < dp.A) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bv[nt]);
@@ -262,14 +268,14 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     const double* row = buf + jj * stride;
                     double bv[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) bv[nt] = (ok && nt * 8 + g8 < dp.nb) ? row[nt * 8 + g8] : 0.0;
+                    for (int nt = 0; nt < NT; ++nt) bv[nt] = (ok && nt * 8 + g8 < nbv) ? row[nt * 8 + g8] : 0.0;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        if (mt * 8 < dp.L2) {
-                            const double av = (ok && mt * 8 + g8 < dp.L2) ? row[nbp + mt * 8 + g8] : 0.0;
+                        if (mt * 8 < L2v) {
+                            const double av = (ok && mt * 8 + g8 < L2v) ? row[nbp + mt * 8 + g8] : 0.0;
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt)
-                                if (nt * 8 < dp.nb) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bv[nt]);
+                                if (nt * 8 < nbv) dmma884(acc[mt][nt][0], acc[mt][nt][1], av, bv[nt]);
                         }
                     }
                 }
@@ -283,9 +289,9 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int lm = mt * 8 + g8, col = nt * 8 + 2 * t4;   // column (s, n) = row s*nb + n of c
-                    if (lm < dp.L2) {
-                        if (col < dp.A) c_s[col * dp.L2p + lm] = acc[mt][nt][0];
-                        if (col + 1 < dp.A) c_s[(col + 1) * dp.L2p + lm] = acc[mt][nt][1];
+                    if (lm < L2v) {
+                        if (col < dp.A) c_s[col * L2p + lm] = acc[mt][nt][0];
+                        if (col + 1 < dp.A) c_s[(col + 1) * L2p + lm] = acc[mt][nt][1];
                     }
                 }
         } else if (cur_s >= 0) {
@@ -297,11 +303,11 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
         double ss = 0.0;
         for (int pair = lane; pair < npairs; pair += 32) {
             const unsigned w = ptab[pair * L];
-            const double* ca = c_s + (w & 0xff) * dp.L2p;
-            const double* cb = c_s + ((w >> 8) & 0xff) * dp.L2p;
+            const double* ca = c_s + (w & 0xff) * L2p;
+            const double* cb = c_s + ((w >> 8) & 0xff) * L2p;
 #pragma unroll
             for (int l = 0; l <= LMAX; ++l) {
-                if (l <= dp.lmax) {
+                if (l <= lmaxv) {
                     double sum = 0.0;
 #pragma unroll
                     for (int kk = l * l; kk < (l + 1) * (l + 1); ++kk) sum += ca[kk] * cb[kk];
@@ -383,7 +389,8 @@ struct BackOut {
     const unsigned char* sp_on;  // [S] species has usable inducing points
 };
 
-template <int LMAX, int NB>
+// EXACT: dp.lmax == LMAX and dp.nb == NB (the loop bounds, strides and radial-index predicates fold at compile time)
+template <int LMAX, int NB, bool EXACT>
 __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(DescParams dp, Geom g, int n_env, EnvSrc src,
                                                             const int* __restrict__ row_of,
                                                             const double* __restrict__ tvec,
@@ -400,7 +407,36 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
     double* T_s = smem + (size_t)warp * per_warp_doubles;   // [D]   dE/dq * kappa*nnl * (1 + [a==b])
     double* c_s = T_s + ((dp.D + 1) & ~1);                  // [csize]
     double* D_s = c_s + ((dp.csize + 1) & ~1);              // [csize] dE/dc
-    const int L = dp.lmax + 1;
+    const int L = EXACT ? LMAX + 1 : dp.lmax + 1;
+    const int nbv = EXACT ? NB : dp.nb;
+    const int L2p = EXACT ? (((LMAX + 1) * (LMAX + 1)) | 1) : dp.L2p;
+    const int lmaxv = EXACT ? LMAX : dp.lmax;
+    // per-lane operand addresses of the dE/dc micro-GEMM below for A <= 16 (2 row tiles x 4 k-steps): the packed
+    // symmetric index tri(a,b) and the row strides do not depend on the environment
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const bool small_A = dp.A <= 16;
+    int toff[2][4], boff[4], doff[2];
+    unsigned okm = 0;  // bit ki: b = 4 ki + t4 < A; bit 4 + mi: a = 8 mi + g8 < A
+#pragma unroll
+    for (int ki = 0; ki < 4; ++ki) {
+        const int b = ki * 4 + t4;
+        const bool b_ok = b < dp.A;
+        okm |= (b_ok ? 1u : 0u) << ki;
+        boff[ki] = b_ok ? b * L2p : 0;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            const int a = mi * 8 + g8;
+            const int lo = min(a, b), hi = max(a, b);
+            const int tri = lo * dp.A - ((lo * (lo - 1)) >> 1) + (hi - lo);
+            toff[mi][ki] = (a < dp.A && b_ok) ? tri * L : 0;   // masked entries read a finite value times bv = 0
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int a = mi * 8 + g8;
+        okm |= (a < dp.A ? 1u : 0u) << (4 + mi);
+        doff[mi] = a * L2p + 2 * t4;
+    }
     double Wacc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) Wacc[q] = 0.0;
@@ -446,8 +482,35 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         __syncwarp();
         // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm],  tri(a,b) = rs(min) + |a-b|, rs(x) = x A - x(x-1)/2
         // = per l one symmetric [A x A] . [A x (2l+1)] product on the FP64 tensor cores (M = a, N = m, K = b)
-        {
-            const int g8 = lane >> 2, t4 = lane & 3;
+        if (small_A) {
+#pragma unroll
+            for (int l = 0; l <= LMAX; ++l) {
+                if (l > lmaxv) break;
+                const int nm = 2 * l + 1, lm0 = l * l;
+#pragma unroll
+                for (int nn0 = 0; nn0 < nm; nn0 += 8) {
+                    // columns n >= nm and rows a >= A of the product are never stored; k-entries b >= A are zeroed
+                    const double* cl = c_s + lm0 + nn0 + g8;
+                    double bv[4];
+#pragma unroll
+                    for (int ki = 0; ki < 4; ++ki) bv[ki] = ((okm >> ki) & 1u) ? cl[boff[ki]] : 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) {
+                        if (mi * 8 < dp.A) {
+                            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                            for (int ki = 0; ki < 4; ++ki)
+                                if (ki * 4 < dp.A) dmma884(d0, d1, T_s[toff[mi][ki] + l], bv[ki]);
+                            const int n = nn0 + 2 * t4;
+                            if ((okm >> (4 + mi)) & 1u) {
+                                if (n < nm) D_s[doff[mi] + lm0 + nn0] = d0;
+                                if (n + 1 < nm) D_s[doff[mi] + lm0 + nn0 + 1] = d1;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
             for (int l = 0; l < L; ++l) {
                 const int nm = 2 * l + 1, lm0 = l * l;
                 for (int nn0 = 0; nn0 < nm; nn0 += 8) {
@@ -463,13 +526,13 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
                             const int lo = min(a, b), hi = max(a, b);
                             const int tri = lo * dp.A - ((lo * (lo - 1)) >> 1) + (hi - lo);
                             const double av = (a_ok && b_ok) ? T_s[tri * L + l] : 0.0;
-                            const double bv = (nB_ok && b_ok) ? cl[b * dp.L2p] : 0.0;
+                            const double bv = (nB_ok && b_ok) ? cl[b * L2p] : 0.0;
                             dmma884(d0, d1, av, bv);
                         }
                         const int n = nn0 + 2 * t4;
                         if (a_ok) {
-                            if (n < nm) D_s[a * dp.L2p + lm0 + n] = d0;
-                            if (n + 1 < nm) D_s[a * dp.L2p + lm0 + n + 1] = d1;
+                            if (n < nm) D_s[a * L2p + lm0 + n] = d0;
+                            if (n + 1 < nm) D_s[a * L2p + lm0 + n + 1] = d1;
                         }
                     }
                 }
@@ -512,15 +575,15 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
                 ys = y - kTinyAngle * z;
                 zs = kTinyAngle * y + z;
             }
-            const double* Dj = D_s + sp * dp.nb * dp.L2p;
+            const double* Dj = D_s + sp * nbv * L2p;
             double gx = 0.0, gy = 0.0, gz = 0.0;
-            solid_harmonics<LMAX, true>(c_harm, dp.lmax, x, ys, zs,
+            solid_harmonics<LMAX, true>(c_harm, lmaxv, x, ys, zs,
                                         [&](int idx, double Y, double dYx, double dYy, double dYz) {
                                             double B = 0.0;
 #pragma unroll
                                             for (int n = 0; n < NB; ++n) {
-                                                if (n < dp.nb) {
-                                                    const double dc = Dj[n * dp.L2p + idx];
+                                                if (n < nbv) {
+                                                    const double dc = Dj[n * L2p + idx];
                                                     B += dc * f[n];
                                                     Tn[n] += dc * Y;
                                                 }
@@ -537,7 +600,7 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
             double rad = 0.0;
 #pragma unroll
             for (int n = 0; n < NB; ++n)
-                if (n < dp.nb) rad += Tn[n] * hh[n];
+                if (n < nbv) rad += Tn[n] * hh[n];
             const double Gx = (rad * x + gx) * ru, Gy = (rad * y + gy) * ru, Gz = (rad * z + gz) * ru;
             if (own_i) {
                 Fx += Gx;
@@ -629,7 +692,7 @@ Launch plan_backward(const DescParams& dp) {
     return {warps, (size_t)warps * per_warp * 8, per_warp};
 }
 
-template <int LMAX, int TN, int TL, bool ENV>
+template <int LMAX, int TN, int TL, bool ENV, int EXNB>
 int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const int* row_of, double* phat,
                    double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
     const DescParams& dp = h->dp;
@@ -646,7 +709,7 @@ int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src,
         set_error("descriptor too large for shared memory (S=%d nmax=%d lmax=%d)", dp.S, dp.nb - 1, dp.lmax);
         return SGPR_ERR_INVALID;
     }
-    auto kern = desc_forward_kernel<LMAX, TN, TL, ENV>;
+    auto kern = desc_forward_kernel<LMAX, TN, TL, ENV, EXNB>;
     SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     int grid = (n_env + L.warps - 1) / L.warps;
     const int maxgrid = h->sm_count * 16;
@@ -666,7 +729,9 @@ int dispatch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& sr
                      double* cbuf, double* pnorm, unsigned char* sflag, cudaStream_t st) {
     const int lmax = h->dp.lmax, nb = h->dp.nb;
     // (LMAX bucket, n-tile, lm-tile): ceil(L2/TL) * ceil(nb/TN) <= 32 lanes
-#define FWD(LM, TN, TL) return launch_forward<LM, TN, TL, ENV>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st)
+#define FWD(LM, TN, TL) return launch_forward<LM, TN, TL, ENV, 0>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st)
+    if (lmax == 3 && nb == 4)   // the reference's default descriptor
+        return launch_forward<3, 2, 1, ENV, 4>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st);
     if (lmax <= 3 && nb <= 4) FWD(3, 2, 1);
     if (lmax <= 3 && nb <= 8) FWD(3, 4, 1);
     if (lmax <= 3) FWD(3, 6, 1);
@@ -679,7 +744,7 @@ int dispatch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& sr
     return SGPR_ERR_INVALID;
 }
 
-template <int LMAX, int NB>
+template <int LMAX, int NB, bool EXACT>
 int launch_backward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src, const BackOut& out, int grid,
                     cudaStream_t st) {
     const DescParams& dp = h->dp;
@@ -688,7 +753,7 @@ int launch_backward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src
         set_error("descriptor too large for shared memory (S=%d nmax=%d lmax=%d)", dp.S, dp.nb - 1, dp.lmax);
         return SGPR_ERR_INVALID;
     }
-    auto kern = desc_backward_kernel<LMAX, NB>;
+    auto kern = desc_backward_kernel<LMAX, NB, EXACT>;
     SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, h->rowof.as<int>() + (h->last_N + 1),
                                              h->gvec.as<double>(), h->phat.as<double>(), h->ttab.as<double>(),
@@ -746,7 +811,8 @@ int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned cha
     out.sp_on = h->sp_on.as<unsigned char>();
     const int grid = backward_grid(h);
     const int lmax = h->dp.lmax, nb = h->dp.nb;
-#define BWD(LM, NBB) return launch_backward<LM, NBB>(h, g, na, src, out, grid, st)
+#define BWD(LM, NBB) return launch_backward<LM, NBB, false>(h, g, na, src, out, grid, st)
+    if (lmax == 3 && nb == 4) return launch_backward<3, 4, true>(h, g, na, src, out, grid, st);   // the reference's default
     if (lmax <= 3 && nb <= 4) BWD(3, 4);
     if (lmax <= 3 && nb <= 8) BWD(3, 8);
     if (lmax <= 6 && nb <= 6) BWD(6, 6);

@@ -92,6 +92,13 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 // packed-entry table word: a | b << 8 | l << 16
 __device__ __forceinline__ double pspec_entry(const DescParams& dp, const double* c_s, unsigned w, double scale) {
     const int a = w & 0xff, b = (w >> 8) & 0xff, l = (w >> 16) & 0xff;
@@ -301,19 +308,61 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
         // power spectrum: lanes over pairs (a <= b), all l of a pair from one pass over c_a, c_b;
         // norm over ALL blocks (sesoap.py:249-251); packed row out
         double ss = 0.0;
-        for (int pair = lane; pair < npairs; pair += 32) {
-            const unsigned w = ptab[pair * L];
-            const double* ca = c_s + (w & 0xff) * L2p;
-            const double* cb = c_s + ((w >> 8) & 0xff) * L2p;
+        if (cache_q) {
+            // p[a, b, l] = sum_m c[a][l m] c[b][l m]: per l a symmetric [A x (2l+1)] . [(2l+1) x A] product on the FP64
+            // tensor cores, upper-triangle 8 x 8 tiles only; a lane's two outputs of a tile go to packed entries
+            // (tri(a, b), l) -- the same packed order as ptab
+            const int AT = (dp.A + 7) >> 3;
+            for (int mt = 0; mt < AT; ++mt) {
+                const int a = mt * 8 + g8;
+                const double* ca = c_s + a * L2p + t4;
+                const int tri_a = a * dp.A - ((a * (a - 1)) >> 1) - a;   // tri(a, b) = tri_a + b for b >= a
+                for (int nt = mt; nt < AT; ++nt) {
+                    const double* cb = c_s + (nt * 8 + g8) * L2p + t4;
+                    const int b0 = nt * 8 + 2 * t4;
+                    const bool ok0 = a <= b0 && b0 < dp.A, ok1 = a <= b0 + 1 && b0 + 1 < dp.A;
+                    const int e0 = (tri_a + b0) * L;
 #pragma unroll
-            for (int l = 0; l <= LMAX; ++l) {
-                if (l <= lmaxv) {
-                    double sum = 0.0;
+                    for (int l = 0; l <= LMAX; ++l) {
+                        if (l <= lmaxv) {
+                            double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                    for (int kk = l * l; kk < (l + 1) * (l + 1); ++kk) sum += ca[kk] * cb[kk];
-                    const double q = sum * nnlk[pair * L + l];
-                    ss += q * q;
-                    if (cache_q) buf[pair * L + l] = q;
+                            for (int kk = 0; kk < 2 * l + 1; kk += 4) {
+                                // k >= 2l+1 belongs to the next l: zero it in both operands (rows >= A only reach
+                                // outputs that are dropped)
+                                const bool kok = kk + t4 < 2 * l + 1;
+                                const double av = kok ? ca[l * l + kk] : 0.0;
+                                const double bv = (nt == mt) ? av : (kok ? cb[l * l + kk] : 0.0);
+                                dmma884(d0, d1, av, bv);
+                            }
+                            if (ok0) {
+                                const double q = d0 * nnlk[e0 + l];
+                                ss += q * q;
+                                buf[e0 + l] = q;
+                            }
+                            if (ok1) {
+                                const double q = d1 * nnlk[e0 + L + l];
+                                ss += q * q;
+                                buf[e0 + L + l] = q;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int pair = lane; pair < npairs; pair += 32) {
+                const unsigned w = ptab[pair * L];
+                const double* ca = c_s + (w & 0xff) * L2p;
+                const double* cb = c_s + ((w >> 8) & 0xff) * L2p;
+#pragma unroll
+                for (int l = 0; l <= LMAX; ++l) {
+                    if (l <= lmaxv) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int kk = l * l; kk < (l + 1) * (l + 1); ++kk) sum += ca[kk] * cb[kk];
+                        const double q = sum * nnlk[pair * L + l];
+                        ss += q * q;
+                    }
                 }
             }
         }
@@ -359,7 +408,6 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     const unsigned sel = bb | ((4u + bb) << 4);
                     packed[t] = __byte_perm(__byte_perm(w0, w1, sel), __byte_perm(w2, w3, sel), 0x5410);
                 }
-#pragma unroll
                 const long long off = (long long)(e4 >> 6) * chunk_stride + prow + (e4 & 63);
 #pragma unroll
                 for (int t = 0; t < 6; ++t) *reinterpret_cast<unsigned*>(p8 + (long long)t * p8_slice + off) = packed[t];
@@ -404,8 +452,9 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
     extern __shared__ __align__(16) double smem[];
     __shared__ double wred[8][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double* T_s = smem + (size_t)warp * per_warp_doubles;   // [D]   dE/dq * kappa*nnl * (1 + [a==b])
-    double* c_s = T_s + ((dp.D + 1) & ~1);                  // [csize]
+    double* T_s = smem + (size_t)warp * per_warp_doubles;   // [D]   dE/dq_hat row, then dE/dq * kappa*nnl * (1 + [a==b])
+    double* P_s = T_s + ((dp.D + 1) & ~1);                  // [D]   q_hat row
+    double* c_s = P_s + ((dp.D + 1) & ~1);                  // [csize]
     double* D_s = c_s + ((dp.csize + 1) & ~1);              // [csize] dE/dc
     const int L = EXACT ? LMAX + 1 : dp.lmax + 1;
     const int nbv = EXACT ? NB : dp.nb;
@@ -443,30 +492,42 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
     // fused exchange step: which of the peers' two accumulation buffers this step adds into (device-side step parity)
     const long long peer_off = (out.peers.world > 0 && out.peers.parity_src && ((*out.peers.parity_src) & 1)) ? out.peers.parity_stride : 0;
 
-    // row of the environment after next (one iteration of lead time so that the prefetch below never waits on it)
+    // The three input rows of an environment (dE/dq_hat, q_hat, expansion coefficients) are only read before the
+    // neighbour loop, which is most of an environment's time: the NEXT environment's rows are copied into the same
+    // shared-memory buffers asynchronously (cp.async, no register round trip) while that loop runs.
     const int env_stride = gridDim.x * nwarps;
     auto row_of_env = [&](int e) -> int { return e < n_env ? row_of[src.active ? src.active[e] : e] : -1; };
-    int r_ahead = row_of_env(blockIdx.x * nwarps + warp + env_stride);
-    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += env_stride) {
-        // pull the next environment's inputs (dE/dq_hat row, q_hat row, expansion coefficients) towards the SM
-        // while this one is processed: the prologue below is otherwise a pure DRAM-latency stall
-        if (r_ahead >= 0) {
-            const char* p0 = reinterpret_cast<const char*>(tvec + (size_t)r_ahead * dp.ldp);
-            const char* p1 = reinterpret_cast<const char*>(phat + (size_t)r_ahead * dp.ldp);
-            const char* p2 = reinterpret_cast<const char*>(cbuf + (size_t)(env + env_stride) * dp.csize);
-            for (int o = lane * 128; o < dp.D * 8; o += 32 * 128) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
+    const bool al16 = ((dp.D | dp.ldp | dp.csize) & 1) == 0;
+    auto fetch_rows = [&](int e, int r) {
+        const double* tv = tvec + (size_t)r * dp.ldp;
+        const double* ph = phat + (size_t)r * dp.ldp;
+        const double* cb = cbuf + (size_t)e * dp.csize;
+        if (al16) {
+            for (int i = 2 * lane; i < dp.D; i += 64) {
+                cp_async16(T_s + i, tv + i);
+                cp_async16(P_s + i, ph + i);
             }
-            for (int o = lane * 128; o < dp.csize * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + o));
+            for (int i = 2 * lane; i < dp.csize; i += 64) cp_async16(c_s + i, cb + i);
+        } else {
+            for (int i = lane; i < dp.D; i += 32) {
+                cp_async8(T_s + i, tv + i);
+                cp_async8(P_s + i, ph + i);
+            }
+            for (int i = lane; i < dp.csize; i += 32) cp_async8(c_s + i, cb + i);
         }
-        r_ahead = row_of_env(env + 2 * env_stride);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    {
+        const int e0 = blockIdx.x * nwarps + warp, r0 = row_of_env(e0);
+        if (r0 >= 0) fetch_rows(e0, r0);
+    }
+    for (int env = blockIdx.x * nwarps + warp; env < n_env; env += env_stride) {
+        const int r_next = row_of_env(env + env_stride);
         const int c = src.active ? src.active[env] : env;
         const AtomRec ai = src.atoms[c];
         const int si = meta_species(ai.meta);
         const long long beg = src.nl_first[env], end = src.nl_first[env + 1];
-        if (end == beg || !out.sp_on[si]) continue;   // warp-uniform
-        const size_t row = (size_t)row_of[c] * dp.ldp;
+        const bool skip = end == beg || !out.sp_on[si];   // warp-uniform
         const bool flag = sflag[env] != 0;
         // chain rule through the normalisation (sesoap.py:229-235): dE/dq = (g - q_hat (q_hat.g)) / P with
         // q_hat.g = sum_m G_im k_im = xi e_i (the local energy from the kernel-matrix GEMM) -> no dot pass
@@ -475,14 +536,17 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         const double Pn = dp.normalize ? prow[r] : 1.0;
         const double pg = dp.normalize ? xi * erow[r] * (Pn > 2.0 * kEps ? Pn / (Pn - kEps) : 1.0) : 0.0;
         const double rP = 1.0 / Pn;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (!skip) {
 #pragma unroll 4
-        for (int e = lane; e < dp.D; e += 32) T_s[e] = (tvec[row + e] - phat[row + e] * pg) * rP * ttab[e];
-#pragma unroll 4
-        for (int t = lane; t < dp.csize; t += 32) c_s[t] = cbuf[(size_t)env * dp.csize + t];
+            for (int e = lane; e < dp.D; e += 32) T_s[e] = (T_s[e] - P_s[e] * pg) * rP * ttab[e];
+        }
         __syncwarp();
         // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm],  tri(a,b) = rs(min) + |a-b|, rs(x) = x A - x(x-1)/2
         // = per l one symmetric [A x A] . [A x (2l+1)] product on the FP64 tensor cores (M = a, N = m, K = b)
-        if (small_A) {
+        if (skip) {
+        } else if (small_A) {
 #pragma unroll
             for (int l = 0; l <= LMAX; ++l) {
                 if (l > lmaxv) break;
@@ -539,6 +603,8 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
             }
         }
         __syncwarp();
+        if (r_next >= 0) fetch_rows(env + env_stride, r_next);
+        if (skip) continue;
         double Fx = 0.0, Fy = 0.0, Fz = 0.0;
         const bool own_i = out.owned ? (out.owned[c] != 0) : true;
         for (long long k = beg + lane; k < end; k += 32) {
@@ -686,7 +752,7 @@ Launch plan_forward(const DescParams& dp, int stride) {
     return {warps, (size_t)warps * per_warp * 8, per_warp};
 }
 Launch plan_backward(const DescParams& dp) {
-    int per_warp = ((dp.D + 1) & ~1) + 2 * ((dp.csize + 1) & ~1);
+    int per_warp = 2 * ((dp.D + 1) & ~1) + 2 * ((dp.csize + 1) & ~1);
     int warps = 4;
     while (warps > 1 && (size_t)warps * per_warp * 8 > 200 * 1024) warps >>= 1;
     return {warps, (size_t)warps * per_warp * 8, per_warp};
@@ -712,7 +778,17 @@ int launch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& src,
     auto kern = desc_forward_kernel<LMAX, TN, TL, ENV, EXNB>;
     SGPR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     int grid = (n_env + L.warps - 1) / L.warps;
-    const int maxgrid = h->sm_count * 16;
+    // one resident wave: environments are dealt round-robin to warps, so a grid that is not a whole number of waves
+    // leaves the machine partly idle for the whole last wave
+    static thread_local size_t occ_smem = ~(size_t)0;
+    static thread_local int occ_blocks = 0;
+    if (occ_smem != L.smem) {
+        int nb = 0;
+        SGPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L.warps * 32, L.smem));
+        occ_blocks = nb > 0 ? nb : 1;
+        occ_smem = L.smem;
+    }
+    const int maxgrid = h->sm_count * occ_blocks;
     if (grid > maxgrid) grid = maxgrid;
     if (grid < 1) grid = 1;
     kern<<<grid, L.warps * 32, L.smem, st>>>(dp, g, n_env, src, row_of, h->ptab.as<unsigned>(), h->nnlk.as<double>(), phat,

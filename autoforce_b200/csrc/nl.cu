@@ -541,8 +541,10 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                                                                    const long long* __restrict__ nl_first,
                                                                    PairRec* __restrict__ pairs, unsigned char* __restrict__ mark,
                                                                    unsigned* __restrict__ masks, int* __restrict__ nl_run) {
-    __shared__ double xs[kBinCap], ys[kBinCap], zs[kBinCap];
-    __shared__ float cmag[kBinCap];          // |x| + |y| + |z| of the unshifted and shifted candidate (rounding bound)
+    // candidate image relative to the bin's first atom, in float (x, y, z), and w = |x| + |y| + |z| of the unshifted and
+    // shifted absolute coordinates (rounding bound of the double-precision test)
+    __shared__ float4 rel[kBinCap];
+    __shared__ unsigned maxabs_u;            // running max of the relative coordinates' 1-norm (float bits)
     __shared__ int pj[kBinCap];
     __shared__ unsigned code[kBinCap];       // bin shift (3 x int8) | species << 24
     __shared__ int run_beg[kRunChunk], run_pre[kRunChunk + 1];
@@ -552,6 +554,16 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
     if (lo >= hi) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kBinThreads / 32;
+    if (threadIdx.x == 0) maxabs_u = 0u;
+    double refx, refy, refz;   // the bin's first atom, wrapped into the box: origin of the float coordinates
+    {
+        const AtomRec a0 = atoms[lo];
+        double w0, w1, w2;
+        shift_vec(g, meta_w(a0.meta, 0), meta_w(a0.meta, 1), meta_w(a0.meta, 2), w0, w1, w2);
+        refx = a0.x - w0;
+        refy = a0.y - w1;
+        refz = a0.z - w2;
+    }
     const int bz = bin % g.nb[2], by = (bin / g.nb[2]) % g.nb[1], bx = bin / (g.nb[2] * g.nb[1]);
     const int zlo = bz - g.reach[2], zhi = bz + g.reach[2];
     const bool merged = (zlo >= 0 && zhi < g.nb[2]);   // z stencil contiguous in cell order: one run per column
@@ -595,6 +607,7 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
             const int n = min(kBinCap, total - t0);
             const bool last_tile = (r0 + kRunChunk >= nruns) && (t0 + kBinCap >= total);
             if (t0 > 0) __syncthreads();   // the previous tile is still being read
+            float my_max = 0.0f;
             for (int q = threadIdx.x; q < n; q += kBinThreads) {
                 const int gq = t0 + q;
                 int a = 0, b = nr;          // last run with run_pre[a] <= gq
@@ -609,14 +622,19 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                 double s0, s1, s2;
                 shift_vec(g, (int)(signed char)(sh & 0xff) - meta_w(aj.meta, 0), (int)(signed char)((sh >> 8) & 0xff) - meta_w(aj.meta, 1),
                           (int)(signed char)((sh >> 16) & 0xff) - meta_w(aj.meta, 2), s0, s1, s2);
-                xs[q] = aj.x + s0;
-                ys[q] = aj.y + s1;
-                zs[q] = aj.z + s2;
-                cmag[q] = (float)(fabs(aj.x) + fabs(aj.y) + fabs(aj.z) + fabs(s0) + fabs(s1) + fabs(s2)) * 1.0001f;
+                const float fx = (float)((aj.x + s0) - refx), fy = (float)((aj.y + s1) - refy), fz = (float)((aj.z + s2) - refz);
+                rel[q] = make_float4(fx, fy, fz,
+                                     (float)(fabs(aj.x) + fabs(aj.y) + fabs(aj.z) + fabs(s0) + fabs(s1) + fabs(s2)) * 1.0001f);
+                my_max = fmaxf(my_max, fabsf(fx) + fabsf(fy) + fabsf(fz));
                 pj[q] = p;
                 code[q] = sh | ((unsigned)meta_species(aj.meta) << 24);
             }
+            {
+                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(my_max));   // floats >= 0 order as uints
+                if (lane == 0 && m > 0u) atomicMax(&maxabs_u, m);
+            }
             __syncthreads();
+            const float maxabs = __uint_as_float(maxabs_u);
             // accept bits of an environment: one 64-bit word per lane, bit k = candidate (slot k, this lane)
             const int nb_tile = (n + 31) >> 5;
             const int nb_masked = max(0, min(nb_tile, kMaskSlots - slot_base));   // batches of this tile covered by the word
@@ -642,19 +660,34 @@ __global__ void __launch_bounds__(kBinThreads, 4) neighbor_bin_kernel(int c_begi
                 // shared-memory test may disagree with the reference's rounding sequence grows with the coordinates'
                 // magnitude (unwrapped trajectories far from the origin)
                 const double imag = fabs(ai.x) + fabs(ai.y) + fabs(ai.z) + fabs(w0) + fabs(w1) + fabs(w2);
-                // distance test of candidate q (shared-memory tile); exact rounding sequence only near rc
+                // distance test of candidate q.  Float coordinates relative to the bin decide everything farther from the
+                // cutoff sphere than their rounding error: with coordinates of 1-norm <= m the float d2 is off by less
+                // than 2^-24 (7 m |d| + 5 d^2) <= 2^-19 (m^2 + rc^2) wherever a decision is taken -- the margin is 4x
+                // that.  Inside the margin (and for d2 ~ 0: the atom itself) the double-precision test decides, with the
+                // reference's exact rounding sequence only in its own, much narrower band.
+                const float fxi = (float)(xi - refx), fyi = (float)(yi - refy), fzi = (float)(zi - refz);
+                const float mx = fmaxf(maxabs, fabsf(fxi) + fabsf(fyi) + fabsf(fzi));
+                const float margin = 7.62939453125e-6f * (mx * mx + (float)rc2);   // 2^-17
+                const float lo_f = (float)rc2 - margin, hi_f = (float)rc2 + margin;
                 auto test = [&](int q) -> bool {
-                    const double dx = xs[q] - xi, dy = ys[q] - yi, dz = zs[q] - zi;
-                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    const float4 cq = rel[q];
+                    const float ex = cq.x - fxi, ey = cq.y - fyi, ez = cq.z - fzi;
+                    const float d2f = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+                    if (d2f > hi_f) return false;
+                    if (d2f < lo_f && d2f > margin) return true;
                     const unsigned cd = code[q];
                     const int p = pj[q];
                     if (p == c && (cd & 0xffffffu) == 0u) return false;   // the atom itself (zero image shift)
-                    const double band = 3.6e-15 * g.rc * ((double)cmag[q] + imag);   // 2^-48 rc (|x_j| + |x_i| + shifts)
-                    if (d2 < fast_lo - band) return true;
-                    if (d2 > fast_hi + band) return false;
                     const AtomRec aj = atoms[p];
                     const int sx = (int)(signed char)(cd & 0xff), sy = (int)(signed char)((cd >> 8) & 0xff),
                               sz = (int)(signed char)((cd >> 16) & 0xff);
+                    double s0, s1, s2;
+                    shift_vec(g, sx - meta_w(aj.meta, 0), sy - meta_w(aj.meta, 1), sz - meta_w(aj.meta, 2), s0, s1, s2);
+                    const double dx = (aj.x + s0) - xi, dy = (aj.y + s1) - yi, dz = (aj.z + s2) - zi;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    const double band = 3.6e-15 * g.rc * ((double)cq.w + imag);   // 2^-48 rc (|x_j| + |x_i| + shifts)
+                    if (d2 < fast_lo - band) return true;
+                    if (d2 > fast_hi + band) return false;
                     double sh0, sh1, sh2;
                     shift_vec(g, sx, sy, sz, sh0, sh1, sh2);
                     return pair_test(g, ai, aj, sx, sy, sz, sh0, sh1, sh2, rc2_lo, rc2_hi, false);

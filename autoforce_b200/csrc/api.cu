@@ -755,6 +755,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
         h->i8_tr2 = tr2 ? (atoi(tr2) == 8 ? 8 : atoi(tr2) == 6 ? 6 : 7) : h->i8_tr;
         const char* c2 = getenv("SGPR_I8_CTA2");
         h->i8_cta2 = c2 && atoi(c2) == 1;
+        const char* epw = getenv("SGPR_I8_EPW");
+        h->i8_epw = epw ? atoi(epw) : 0;
         const char* nss = getenv("SGPR_I8_NS");
         h->i8_ns = (nss && atoi(nss) == 5) ? 5 : 6;
         if (h->use_i8) {

@@ -59,7 +59,10 @@ int make_map(CUtensorMap* m, const void* base, int ns, long long rows, int Kpad,
 template <int NS>
 __device__ __forceinline__ unsigned long long digit_bytes(double x) {
     constexpr unsigned long long BIAS = 0x0080808080808080ull & ((1ull << (8 * NS)) - 1ull);
-    const long long v = __double2ll_rn(x * (double)(1ll << (8 * NS - 2)));
+    // rint(x 2^(8 NS - 2)) without the 64-bit conversion unit: |x| <= 1, so adding 1.5 2^52 leaves the (round-to-nearest-
+    // even) integer in the mantissa, offset by 2^51
+    static_assert(8 * NS - 2 < 51, "the magic-number rounding needs |x 2^(8 NS - 2)| < 2^51");
+    const long long v = __double_as_longlong(x * (double)(1ll << (8 * NS - 2)) + 6755399441055744.0) - 0x4338000000000000ll;
     return ((unsigned long long)(v + (long long)BIAS)) ^ BIAS;   // byte t = digit t (t = 0 least significant)
 }
 // byte b of four digit words -> one 32-bit word (columns j .. j+3 of one slice)
@@ -122,8 +125,9 @@ __global__ void row_pow2_kernel(const double* __restrict__ X, long long ldx, int
 
 constexpr int kNS = 6;
 
-struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
-    const double* mu[kMaxSpecies];       // per problem: mu of the species' inducing block
+// XI = 4 (the reference's default exponent): k^(xi-1) is two multiplies and nothing else is compiled in; XI = 0: any xi
+template <int XI>
+struct Epi1T {   // kernel matrix: energies + digits of k^(xi-1)
     double* erow_part;                   // [parts][erow_ld]
     signed char* g8;                     // slice 0, row 0
     signed char* k8;                     // digits of k^xi for the covloss GEMM (nullptr: not wanted)
@@ -133,15 +137,16 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
     long long cap_rows;                  // allocated rows of g8 / k8 (chunk-major layout)
     double xi;
     int xi_int;
-    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
+    // mup (Problem::aux): mu of the species' inducing block
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N, const double* mup) const {
         if (row >= M) return;
         row += row0;
-        const double* mup = mu[p];
         double pw[16];
         // k^(xi-1): the usual exponents unrolled (independent multiplies), anything else by pow()
-        if (xi_int == 4) {
+        if (XI == 4 || xi_int == 4) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pw[j] = v[j] * v[j] * v[j];
+        } else if (XI != 0) {
         } else if (xi_int == 2) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pw[j] = v[j];
@@ -152,6 +157,7 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) pw[j] = 1.0;
         } else {
+#pragma unroll   // (a run-time index would put pw[] -- for every exponent -- into local memory)
             for (int j = 0; j < 16; ++j) {
                 if (xi_int >= 1) {
                     double r = 1.0;
@@ -164,12 +170,20 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
         }
         double e = 0.0;
         unsigned long long u[16];
+        if (col0 + 16 <= N) {   // whole chunk inside the matrix: no per-column masks
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const bool in = col0 + j < N;
-            const double pj = in ? pw[j] : 0.0;
-            e += (in ? mup[col0 + j] : 0.0) * pj * v[j];
-            u[j] = digit_bytes<kNS>(pj);
+            for (int j = 0; j < 16; ++j) {
+                e += __ldg(mup + col0 + j) * pw[j] * v[j];
+                u[j] = digit_bytes<kNS>(pw[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const bool in = col0 + j < N;
+                const double pj = in ? pw[j] : 0.0;
+                e += (in ? __ldg(mup + col0 + j) : 0.0) * pj * v[j];
+                u[j] = digit_bytes<kNS>(pj);
+            }
         }
         // one 16-byte store per slice (columns beyond N get zero digits: the K padding of GEMM 2)
         if (col0 < Mp) {
@@ -204,13 +218,12 @@ struct Epi1 {   // kernel matrix: energies + digits of k^(xi-1)
 };
 
 struct Epi3 {   // covloss: per-row partial sums of squares of b = K . choli^T  (calculator/active.py:781-783)
-    const double* rs[kMaxSpecies];       // power-of-two scales of the choli rows (= output columns)
     double* part;                        // [parts][part_ld]
     int part_ld;
-    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
+    // r (Problem::aux): power-of-two scales of the choli rows (= output columns)
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N, const double* r) const {
         if (row >= M) return;
         row += row0;
-        const double* r = rs[p];
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -225,7 +238,7 @@ struct Epi2 {   // back projection: g = mumax * C
     double* gvec;                        // [rows][ldp]
     int ldp;
     double mumax;
-    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N) const {
+    __device__ void operator()(int p, int row0, int row, int col0, const double* v, int M, int N, const double*) const {
         if (row >= M) return;
         double* dst = gvec + (long long)(row0 + row) * ldp + col0;
         if (col0 + 16 <= N) {
@@ -239,10 +252,10 @@ struct Epi2 {   // back projection: g = mumax * C
     }
 };
 
-template <int NS, int TR, class Epi>
+template <int NS, int TR, class Epi, int EPW = 2>
 int launch_ns(sgpr_context* h, const Common* cm_d, const Problem* probs_d, const Epi& epi, cudaStream_t st) {
     constexpr int STAGES = 3;
-    auto kern = i8gemm_kernel<NS, TR, STAGES, Epi>;
+    auto kern = i8gemm_kernel<NS, TR, STAGES, Epi, 0, EPW>;
     const size_t smem = smem_bytes<NS, STAGES>();
     static bool done = false;   // per instantiation
     if (!done) {
@@ -250,7 +263,7 @@ int launch_ns(sgpr_context* h, const Common* cm_d, const Problem* probs_d, const
         done = true;
     }
     // persistent: one CTA per SM; the tile count lives on the device (CTAs beyond it exit at once)
-    kern<<<h->sm_count, NTHREADS, smem, st>>>(cm_d, probs_d, epi);
+    kern<<<h->sm_count, 64 + 128 * EPW, smem, st>>>(cm_d, probs_d, epi);
     SGPR_CUDA(cudaGetLastError());
     h->stats.kernel_launches += 1;
     return SGPR_OK;
@@ -423,8 +436,10 @@ static int build_problems(sgpr_context* h, int which, std::vector<Problem>& prob
         if (m1 == m0 || !dp.central_enabled[s]) continue;
         Problem P;
         P.nk_tn = nullptr;
+        P.aux = nullptr;
         P.M = 0;
         if (which == 1) {
+            P.aux = h->mu.as<double>() + m0;
             P.N = m1 - m0;
             P.Kpad = h->i8_kp1;
             const int ns1 = (h->i8_ns == 5 && h->i8_tr == 7) ? 5 : kNS;
@@ -438,6 +453,7 @@ static int build_problems(sgpr_context* h, int which, std::vector<Problem>& prob
             SGPR_TRY(make_map(&P.mapA, h->g8.as<signed char>(), ns2, cap, h->i8_mp, cap, BM));
             SGPR_TRY(make_map(&P.mapB, h->zt8.as<signed char>() + (size_t)s * kNS * dp.D * h->i8_mp, ns2, dp.D, h->i8_mp, (long long)dp.D, BN));
         } else {
+            P.aux = h->crs.as<double>() + (size_t)s * h->M;
             P.N = h->M;
             P.Kpad = ((m1 - m0) + 63) / 64 * 64;
             SGPR_TRY(make_map(&P.mapA, h->k8.as<signed char>(), kNS, cap, h->i8_mp, cap, BM));
@@ -489,6 +505,7 @@ static int device_problems(sgpr_context* h, int which, cudaStream_t st, const Pr
     mix((unsigned long long)(uintptr_t)h->p8.p); mix((unsigned long long)(uintptr_t)h->g8.p); mix((unsigned long long)(uintptr_t)h->k8.p);
     mix((unsigned long long)(uintptr_t)h->z8.p); mix((unsigned long long)(uintptr_t)h->zt8.p); mix((unsigned long long)(uintptr_t)h->c8.p);
     mix((unsigned long long)(uintptr_t)h->cov_nk.p); mix((unsigned long long)(uintptr_t)h->i8_probs.p);
+    mix((unsigned long long)(uintptr_t)h->mu.p); mix((unsigned long long)(uintptr_t)h->crs.p);
     mix(h->i8_cap_rows); mix(h->M); mix(h->i8_kp1); mix(h->i8_mp); mix(h->i8_tr2); mix(h->i8_ns); mix(h->i8_model_version);
     for (int s = 0; s <= h->S; ++s) mix(h->m_first[s]);
     Problem* dev = h->i8_probs.as<Problem>() + slot * kMaxSpecies;
@@ -524,6 +541,7 @@ static int device_problems2(sgpr_context* h, int which, cudaStream_t st, const P
             const int m0 = h->m_first[s], m1 = h->m_first[s + 1];
             if (m1 == m0 || !dp.central_enabled[s]) continue;
             Problem2 P;
+            P.aux = which == 1 ? h->mu.as<double>() + m0 : nullptr;
             if (which == 1) {
                 const int ns1 = (h->i8_ns == 5 && h->i8_tr == 7) ? 5 : kNS;
                 P.N = m1 - m0;
@@ -569,14 +587,9 @@ int i8_setup_step(sgpr_context* h, cudaStream_t st) {
     return SGPR_OK;
 }
 
-int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
-    const Problem* probs_d = nullptr;
-    SetupDesc sd{};
-    SGPR_TRY(device_problems(h, 1, st, &probs_d, &sd));
-    if (sd.n_prob == 0) return SGPR_OK;
-    count_work(h, 1);
+template <class Epi1>
+static int kernel_matrix_impl(sgpr_context* h, cudaStream_t st, bool store_k8, const Problem* probs_d, const SetupDesc& sd) {
     Epi1 e{};
-    for (int p = 0; p < sd.n_prob; ++p) e.mu[p] = h->mu.as<double>() + h->m_first[sd.species[p]];
     e.erow_part = h->erow_part.as<double>();
     e.g8 = h->g8.as<signed char>();
     e.k8 = store_k8 ? h->k8.as<signed char>() : nullptr;
@@ -592,7 +605,20 @@ int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
         return h->i8_ns == 5 ? launch2<5, 7>(h, common_d(h, 1), p2, e, st) : launch2<6, 7>(h, common_d(h, 1), p2, e, st);
     }
     if (h->i8_tr == 7 && h->i8_ns == 5) return launch_ns<5, 7>(h, common_d(h, 1), probs_d, e, st);
+    // descriptors of one K chunk (a single species with the default lmax/nmax): the main loop is one stage per tile and
+    // the fused epilogue is the kernel -- twice the epilogue warps
+    if (h->i8_tr == 7 && h->i8_kp1 <= 64 && h->i8_epw != 2) return launch_ns<kNS, 7, Epi1, 4>(h, common_d(h, 1), probs_d, e, st);
     return h->i8_tr == 8 ? launch<8>(h, common_d(h, 1), probs_d, e, st) : launch<7>(h, common_d(h, 1), probs_d, e, st);
+}
+
+int i8_kernel_matrix(sgpr_context* h, cudaStream_t st, bool store_k8) {
+    const Problem* probs_d = nullptr;
+    SetupDesc sd{};
+    SGPR_TRY(device_problems(h, 1, st, &probs_d, &sd));
+    if (sd.n_prob == 0) return SGPR_OK;
+    count_work(h, 1);
+    if (h->xi_int == 4) return kernel_matrix_impl<Epi1T<4>>(h, st, store_k8, probs_d, sd);
+    return kernel_matrix_impl<Epi1T<0>>(h, st, store_k8, probs_d, sd);
 }
 
 int i8_back_projection(sgpr_context* h, cudaStream_t st) {
@@ -626,7 +652,6 @@ int i8_covloss(sgpr_context* h, int64_t n_rows, cudaStream_t st) {
     if (sd.n_prob == 0) return SGPR_OK;
     count_work(h, 3);
     Epi3 e{};
-    for (int p = 0; p < sd.n_prob; ++p) e.rs[p] = h->crs.as<double>() + (size_t)sd.species[p] * h->M;
     e.part = h->cpart.as<double>();
     e.part_ld = (int)n_rows;
     return launch<8>(h, common_d(h, 3), probs_d, e, st);

@@ -66,6 +66,7 @@ struct Problem2 {
     CUtensorMap mapA;     // as Problem::mapA (box 128 rows)
     CUtensorMap mapBh;    // B operand with a box of BN/2 = 32 rows
     int N, Kpad;
+    const double* aux;    // as Problem::aux
 };
 
 template <int NS, int TR>
@@ -230,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             tphase ^= 1;
             const int row = tm * 2 * BM + (int)rank * BM + row_in_tile;
 #pragma unroll
-            for (int cc = 0; cc < HC; cc += 16) epi(pi, cm.row0[pi], row, tn * BN + half * HC + cc, v + cc, cm.M[pi], probs[pi].N);
+            for (int cc = 0; cc < HC; cc += 16) epi(pi, cm.row0[pi], row, tn * BN + half * HC + cc, v + cc, cm.M[pi], probs[pi].N, probs[pi].aux);
         }
     }
     tc_fence_before();

@@ -141,6 +141,7 @@ struct Problem {
                          // the problem's first row comes from Common::row0
     CUtensorMap mapB;    // int8 [NS][Kpad/64][rowsB][64], box {64,  64, 1, NS}
     int M, N, Kpad;      // N columns; Kpad multiple of 64 (zero padded); M unused (Common::M)
+    const double* aux;   // per-problem vector handed to the epilogue functor (mu block / choli row scales); may be null
     const int* nk_tn;    // optional [ceil(N/64)]: K chunks (of 64) that can be non-zero for column tile tn; nullptr =
                          // Kpad / 64 for every tile.  Lets a triangular B (choli) skip its zero part; 0 = the tile
                          // is identically zero: no loads, no MMAs, the epilogue runs on zeros.
@@ -220,50 +221,61 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
                  : "memory");
 }
 
-template <int NG>
+// int32 -> float64, exact, on the ALU + FP64 pipes (the I2F/F2I conversion unit has a fraction of their throughput and
+// was the limiter of the single-K-chunk kernel-matrix GEMM): 2^52 + 2^31 + x has the mantissa word x ^ 0x80000000.
+__device__ __forceinline__ double i32_to_f64(int32_t x) {
+    return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+// T = sum_g acc_g 256^(NG-1-g) in float64 with ONE rounding: Horner over the (up to) four most significant groups is
+// exact (|.| < 2^52), so is the rest (< 2^43); the final fma rounds once -- same value as an int64 evaluation.
+template <int NG, bool SMALLK>
+__device__ __forceinline__ double combine_groups(const int32_t (*r)[16], int j) {
+    constexpr double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
+    if (SMALLK && NG == 6) {
+        // one K chunk: |acc_g| <= 64 . 127^2 . (g + 1) < 2^23, so neighbouring groups pair up exactly in int32
+        const double p01 = i32_to_f64(r[0][j] * 256 + r[1][j]), p23 = i32_to_f64(r[2][j] * 256 + r[3][j]);
+        const double p45 = i32_to_f64(r[4][j] * 256 + r[5][j]);
+        return fma(fma(p01, 65536.0, p23), 65536.0, p45) * sc;   // inner fma exact (< 2^46), outer rounds once
+    }
+    constexpr int NH = NG < 4 ? NG : 4;
+    double hi = i32_to_f64(r[0][j]);
+#pragma unroll
+    for (int g = 1; g < NH; ++g) hi = fma(hi, 256.0, i32_to_f64(r[g][j]));
+    if (NG == NH) return hi * sc;
+    double lo = i32_to_f64(r[NH][j]);
+#pragma unroll
+    for (int g = NH + 1; g < NG; ++g) lo = fma(lo, 256.0, i32_to_f64(r[g][j]));
+    return fma(hi, (double)(1ll << (8 * (NG - NH))), lo) * sc;
+}
+
+template <int NG, bool SMALLK = false>
 __device__ __forceinline__ void combine8(uint32_t taddr_lane_col, double* v) {
-    int32_t r[NG][8];
+    int32_t r[NG][16];
 #pragma unroll
     for (int g = 0; g < NG; ++g) tmem_ld8(taddr_lane_col + g * BN, r[g]);
     tmem_ld_wait();
-    constexpr int NH = NG < 4 ? NG : 4;
-    const double hs = (double)(1ll << (8 * (NG - NH)));
-    const double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        long long hi = 0, lo = 0;
-#pragma unroll
-        for (int g = 0; g < NH; ++g) hi = hi * 256 + (long long)r[g][j];
-#pragma unroll
-        for (int g = NH; g < NG; ++g) lo = lo * 256 + (long long)r[g][j];
-        v[j] = fma((double)hi, hs, (double)lo) * sc;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = combine_groups<NG, SMALLK>(r, j);
 }
 
-template <int NG>
+template <int NG, bool SMALLK = false>
 __device__ __forceinline__ void combine16(uint32_t taddr_lane_col, double* v) {
     int32_t r[NG][16];
 #pragma unroll
     for (int g = 0; g < NG; ++g) tmem_ld16(taddr_lane_col + g * BN, r[g]);
     tmem_ld_wait();
-    constexpr int NH = NG < 4 ? NG : 4;      // groups in the high half
-    const double hs = (double)(1ll << (8 * (NG - NH)));
-    const double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        long long hi = 0, lo = 0;
-#pragma unroll
-        for (int g = 0; g < NH; ++g) hi = hi * 256 + (long long)r[g][j];
-#pragma unroll
-        for (int g = NH; g < NG; ++g) lo = lo * 256 + (long long)r[g][j];
-        v[j] = fma((double)hi, hs, (double)lo) * sc;
-    }
+    for (int j = 0; j < 16; ++j) v[j] = combine_groups<NG, SMALLK>(r, j);
 }
 
-// Epilogue functor:  epi(prob, row0, row, col0, v[16], M, N)  called by each of the 128 epilogue threads (one
+// Epilogue functor:  epi(prob, row0, row, col0, v[16], M, N, aux)  (aux = Problem::aux)  called by each of the 128 epilogue threads (one
 // output row each: row0 + row in the buffers, row < M valid) for every 16-column chunk of its row.
-template <int NS, int TR, int STAGES, class Epi, int DEBUG_SKIP = 0>
-__global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __restrict__ cmp,
+// EPW = epilogue warps per TMEM lane quarter (each takes BN / EPW columns of its 32 rows): 2 when the main loop is long
+// (the epilogue hides behind the next tile's MMAs), 4 for single-chunk K, where the kernel IS its epilogue.  EPW = 4
+// REQUIRES Kpad <= 64 for every problem of the launch (its accumulator read-out relies on the bound, combine_groups).
+template <int NS, int TR, int STAGES, class Epi, int DEBUG_SKIP = 0, int EPW = 2>
+__global__ void __launch_bounds__(64 + 128 * EPW, 1) i8gemm_kernel(const Common* __restrict__ cmp,
                                                              const Problem* __restrict__ probs, Epi epi) {
     // the work list is read once per CTA into shared memory: every role indexes it with run-time indices, which
     // would otherwise put a per-thread copy into local memory on the tile-scheduling path
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 8);               // one arrive per epilogue warp
+        mbar_init(tmem_empty, 4 * EPW);         // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -378,10 +390,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
             }
         }
     } else {
-        // ===================== epilogue: warps 2..9; TMEM lanes 32*(warp%4)..+31, column half (warp-2)/4 ==========
+        // ===================== epilogue: warps 2..; TMEM lanes 32*(warp%4)..+31, column part (warp-2)/4 ==========
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int row_in_tile = q * 32 + lane;
-        constexpr int HC = BN / 2;                     // columns per epilogue warp
+        constexpr int HC = BN / EPW;                   // columns per epilogue warp
+        static_assert(HC % 16 == 0, "the epilogue functor takes 16-column chunks");
         uint32_t tphase = 0;
         for (int gt = blockIdx.x; gt < n_tiles; gt += gridDim.x) {
             int pi = 0;
@@ -397,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
                 for (int j = 0; j < HC; ++j) v[j] = 0.0;
 #pragma unroll
                 for (int cc = 0; cc < HC; cc += 16)
-                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N);
+                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N, P.aux);
                 continue;
             }
             mbar_wait(tmem_full, tphase);
@@ -407,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
             // then run the (expensive) fused epilogue: it overlaps with the next tile's main loop
             if (DEBUG_SKIP != 2) {
 #pragma unroll
-                for (int cc = 0; cc < HC; cc += 8) combine8<SC::NG>(lane_addr + cc, v + cc);
+                for (int cc = 0; cc < HC; cc += 8) combine8<SC::NG, EPW == 4>(lane_addr + cc, v + cc);
             }
             tc_fence_before();
             __syncwarp();
@@ -416,11 +429,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) i8gemm_kernel(const Common* __res
             if (DEBUG_SKIP == 0) {
 #pragma unroll
                 for (int cc = 0; cc < HC; cc += 16)
-                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N);
+                    epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC + cc, v + cc, cm.M[pi], P.N, P.aux);
             } else if (DEBUG_SKIP == 1) {
                 double s = 0;
                 for (int j = 0; j < HC; ++j) s += v[j];
-                if (s == 123.456) epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC, v, cm.M[pi], P.N);
+                if (s == 123.456) epi(pi, cm.row0[pi], tm * BM + row_in_tile, tn * BN + half * HC, v, cm.M[pi], P.N, P.aux);
             }
         }
     }

@@ -165,6 +165,7 @@ struct sgpr_context {
     unsigned long long i8_prob_sig[3] = {0, 0, 0};   // what the uploaded descriptors were built from (addresses, shapes)
     sgpr::I8Setup i8_setup[3];
     int i8_nprob = 0;
+    int i8_epw = 0;              // SGPR_I8_EPW=2: never use the 4-epilogue-warps-per-quarter kernel (A/B switch)
     bool i8_cta2 = false;        // SGPR_I8_CTA2=1: CTA-pair (cta_group::2) variant of the two hot GEMMs
     sgpr::DevBuf i8_probs2;      // its problem descriptors
     void* i8_probs2_pinned = nullptr;

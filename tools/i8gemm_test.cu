@@ -75,7 +75,7 @@ struct StoreEpi {
             if (col0 + j < N) C[(size_t)row * ldc + col0 + j] = v[j];
     }
     // production kernel: rows are offsets from the problem's first row (Common::row0)
-    __device__ void operator()(int prob, int row0, int row, int col0, const double* v, int M, int N) const {
+    __device__ void operator()(int prob, int row0, int row, int col0, const double* v, int M, int N, const double* = nullptr) const {
         if (row < M) (*this)(prob, row0 + row, col0, v, row0 + M, N);
     }
 };
@@ -128,6 +128,7 @@ int main(int argc, char** argv) {
     Problem P;
     P.M = M; P.N = N; P.Kpad = Kpad;
     P.nk_tn = nullptr;
+    P.aux = nullptr;
     if (make_map_cm(&P.mapA, dAc, ns, M, Kpad, BM) || make_map_cm(&P.mapB, dBc, ns, N, Kpad, BN)) return 1;
     ProblemTA PT;
     if (make_map(&PT.mapA, dA, ns, M, Kpad, BM) || make_map(&PT.mapB, dB, ns, N, Kpad, BN)) return 1;

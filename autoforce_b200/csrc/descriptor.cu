@@ -65,7 +65,13 @@ struct Nbr {
             sp = src.env_sp[k];
             j = -1;
         } else {
-            const PairRec pr = src.pairs[k];
+            load_pair(src, g, ai, src.pairs[k], rx, ry, rz, sp, j);
+        }
+    }
+    // atoms mode with the pair record already in registers (software-pipelined loops)
+    __device__ static __forceinline__ void load_pair(const EnvSrc& src, const Geom& g, const AtomRec& ai, const PairRec pr,
+                                                     double& rx, double& ry, double& rz, int& sp, int& j) {
+        {
             const AtomRec aj = src.atoms[pr.j];
             j = pr.j;
             sp = pr.sp;
@@ -391,7 +397,8 @@ __global__ void __launch_bounds__(128, (LMAX <= 3 ? 7 : 4)) desc_forward_kernel(
                     double x = 0.0;
                     if (e < dp.D) x = (cache_q ? buf[e] : pspec_entry(dp, c_s, ptab[e], nnlk[e])) * rP;
                     // bytes of (rint(x 2^46) + bias) ^ bias are the balanced base-256 digits (i8gemm.cu)
-                    const long long v = __double2ll_rn(x * 70368744177664.0);
+                    // rint(x 2^46) via the 1.5 2^52 magic number (|x| <= 1; the 64-bit F2I unit is ~30x slower than a DADD)
+                    const long long v = __double_as_longlong(x * 70368744177664.0 + 6755399441055744.0) - 0x4338000000000000ll;
                     u[q] = ((unsigned long long)(v + 0x808080808080ll)) ^ 0x808080808080ull;
                 }
                 unsigned packed[6];
@@ -536,12 +543,17 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         const double Pn = dp.normalize ? prow[r] : 1.0;
         const double pg = dp.normalize ? xi * erow[r] * (Pn > 2.0 * kEps ? Pn / (Pn - kEps) : 1.0) : 0.0;
         const double rP = 1.0 / Pn;
+        PairRec pr_n;
+        pr_n.j = 0;
+        const bool have0 = !skip && beg + lane < end;
+        if (have0) pr_n = src.pairs[beg + lane];
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         if (!skip) {
 #pragma unroll 4
             for (int e = lane; e < dp.D; e += 32) T_s[e] = (T_s[e] - P_s[e] * pg) * rP * ttab[e];
         }
+        if (have0) asm volatile("prefetch.global.L1 [%0];" ::"l"(src.atoms + pr_n.j));
         __syncwarp();
         // dE/dc[a][lm] = sum_b T[tri(a,b), l] c[b][lm],  tri(a,b) = rs(min) + |a-b|, rs(x) = x A - x(x-1)/2
         // = per l one symmetric [A x A] . [A x (2l+1)] product on the FP64 tensor cores (M = a, N = m, K = b)
@@ -610,7 +622,12 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
         for (long long k = beg + lane; k < end; k += 32) {
             double rx, ry, rz;
             int sp, j;
-            Nbr<false>::load(src, g, ai, k, rx, ry, rz, sp, j);
+            // the pair record of this pass was fetched one pass ahead and its atom record prefetched: the dependent
+            // pairs -> atoms gather is otherwise two exposed L2 round trips per pass
+            const PairRec pr = pr_n;
+            const bool more = k + 32 < end;
+            if (more) pr_n = src.pairs[k + 32];
+            Nbr<false>::load_pair(src, g, ai, pr, rx, ry, rz, sp, j);
             const double u = dp.radii[sp], ru = dp.rinv[sp];
             const double x = rx * ru, y = ry * ru, z = rz * ru;
             const double d2 = x * x + y * y + z * z;
@@ -622,6 +639,7 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
                 R = 0.0;
                 Rpd = 0.0;
             }
+            if (more) asm volatile("prefetch.global.L1 [%0];" ::"l"(src.atoms + pr_n.j));
             double f[NB], hh[NB], Tn[NB];
             {
                 double pw = 1.0;  // d2^(n-1)

@@ -163,10 +163,12 @@ __global__ void scatter_forces_kernel(int64_t N, const AtomRec* __restrict__ ato
     // fused exchange step: the buffer of the step that has just been published (counter already advanced)
     if (parity_src && (((*parity_src) - 1) & 1)) fcell += parity_stride;
     const int i = meta_orig(atoms[c].meta);
-    F[3 * (size_t)i] = fcell[3 * c];
-    F[3 * (size_t)i + 1] = fcell[3 * c + 1];
-    F[3 * (size_t)i + 2] = fcell[3 * c + 2];
-    if (owned_out) owned_out[i] = owned ? owned[c] : 1;
+    // atoms of other ranks: zero (the peer-memory exchange leaves what was pushed to their owners in this buffer)
+    const bool mine = owned ? owned[c] != 0 : true;
+    F[3 * (size_t)i] = mine ? fcell[3 * c] : 0.0;
+    F[3 * (size_t)i + 1] = mine ? fcell[3 * c + 1] : 0.0;
+    F[3 * (size_t)i + 2] = mine ? fcell[3 * c + 2] : 0.0;
+    if (owned_out) owned_out[i] = mine ? 1 : 0;
 }
 
 // dL/dx = -F in the caller's order, plus per-block partials of sum_k x_k (x) F_k (for dL/dcell)
@@ -331,6 +333,24 @@ __global__ void p2p_zero_next_kernel(double* __restrict__ own_base, long long st
     // the accumulation buffer of the NEXT step (the one this step does not use)
     double* dst = own_base + ((((*step_counter) & 1) == 0) ? stride : 0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = 0.0;
+}
+// Halo forces of the atom-sharded path: what this rank accumulated for atoms it does not own goes to the owners'
+// buffers (peer-mapped), coalesced over the cell order -- adjacent x-slabs are contiguous index ranges.
+__global__ void p2p_push_kernel(long long n3, PeerForces peers, int rank) {
+    const long long off = (peers.parity_src && ((*peers.parity_src) & 1)) ? peers.parity_stride : 0;
+    const double* mine = peers.peer_f[rank] + off;
+    const long long lo = 3ll * peers.bounds[rank], hi = 3ll * peers.bounds[rank + 1];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
+        if (i >= lo && i < hi) continue;
+        const double v = mine[i];
+        if (v == 0.0) continue;
+        const int j = (int)(i / 3);
+        int r = 0;
+#pragma unroll
+        for (int q = 1; q < SGPR_MAX_RANKS; ++q)
+            if (q < peers.world && j >= peers.bounds[q]) r = q;
+        atomicAdd(peers.peer_f[r] + off + i, v);
+    }
 }
 __global__ void p2p_publish_kernel(int rank, int world, P2PPeers peers, const double* __restrict__ ew_local,
                                    long long* __restrict__ step_counter) {
@@ -1030,6 +1050,10 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     nvtxRangePop();
     NvtxRange force_range("sgpr:force");
     SGPR_TRY(descriptor_backward_atoms(h, g, owned, st, peer_f_h ? &peers : nullptr));
+    if (peer_f_h && N > 0) {
+        p2p_push_kernel<<<h->sm_count * 2, 256, 0, st>>>(3 * (long long)N, peers, h->p2p_rank);
+        h->stats.kernel_launches += 1;
+    }
     if (N > 0) {
         atom_terms_kernel<<<nblk_x, 256, 0, st>>>(N, (int)h->n_active, active, h->atoms.as<AtomRec>(),
                                                   h->nl_first.as<long long>(), owned, h->mean_w_d.as<double>(),

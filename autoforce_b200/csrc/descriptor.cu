@@ -695,12 +695,10 @@ __global__ void __launch_bounds__(128, (NB <= 4 ? 4 : 3)) desc_backward_kernel(D
                 Wacc[6] += rz * Gx; Wacc[7] += rz * Gy; Wacc[8] += rz * Gz;
             }
             if (out.peers.world > 0) {
-                // owner of neighbour j: rank r with bounds[r] <= j < bounds[r+1]; its buffer is peer-mapped
-                int r = 0;
-#pragma unroll
-                for (int q = 1; q < SGPR_MAX_RANKS; ++q)
-                    if (q < out.peers.world && j >= out.peers.bounds[q]) r = q;
-                double* dst = out.peers.peer_f[r] + peer_off + 3 * (size_t)j;
+                // atom-sharded: everything is accumulated in THIS rank's buffer (indexed by the global cell order); the
+                // entries of atoms other ranks own are pushed to their owners afterwards, one remote add per atom and
+                // component instead of one per pair (p2p_push_kernel, api.cu)
+                double* dst = out.fcell + peer_off + 3 * (size_t)j;
                 atomicAdd(dst, -Gx);
                 atomicAdd(dst + 1, -Gy);
                 atomicAdd(dst + 2, -Gz);

@@ -352,12 +352,18 @@ __global__ void p2p_push_kernel(long long n3, PeerForces peers, int rank) {
         atomicAdd(peers.peer_f[r] + off + i, v);
     }
 }
-__global__ void p2p_publish_kernel(int rank, int world, P2PPeers peers, const double* __restrict__ ew_local,
-                                   long long* __restrict__ step_counter) {
-    // every earlier kernel of this stream (the force kernel with its remote red.add) has completed
+// One block: publish this rank's E + virial (and the step's stamp) to every peer's mailbox, then wait for every peer's
+// stamp and reduce in rank order.  The step counter advances in between (scatter_forces_kernel reads it afterwards).
+__global__ void p2p_publish_wait_kernel(int rank, int world, P2PPeers peers, const double* __restrict__ ew_local,
+                                        long long* __restrict__ step_counter, double* __restrict__ E, double* __restrict__ W,
+                                        long long* __restrict__ status) {
+    __shared__ double acc[SGPR_MAX_RANKS][10];
+    __shared__ int timed_out;
+    // every earlier kernel of this stream (the force kernel, the halo push with its remote red.add) has completed
     const long long stamp = *step_counter + 1;
-    const int parity = (int)((*step_counter) & 1);
+    const int parity = (int)((stamp - 1) & 1);
     const int r = threadIdx.x;
+    if (r == 0) timed_out = 0;
     if (r < world) {
         double* slot = peers.mail[r] + ((size_t)parity * world + rank) * 16;
         for (int q = 0; q < 10; ++q) slot[q] = ew_local[q];
@@ -368,19 +374,8 @@ __global__ void p2p_publish_kernel(int rank, int world, P2PPeers peers, const do
     }
     __syncthreads();
     if (threadIdx.x == 0) *step_counter = stamp;
-}
-__global__ void p2p_wait_reduce_kernel(int world, const double* __restrict__ my_mail,
-                                       const long long* __restrict__ step_counter, double* __restrict__ E,
-                                       double* __restrict__ W, long long* __restrict__ status) {
-    __shared__ double acc[SGPR_MAX_RANKS][10];
-    __shared__ int timed_out;
-    const long long stamp = *step_counter;   // set by this step's publish kernel
-    const int parity = (int)((stamp - 1) & 1);
-    const int r = threadIdx.x;
-    if (r == 0) timed_out = 0;
-    __syncthreads();
     if (r < world) {
-        const double* slot = my_mail + ((size_t)parity * world + r) * 16;
+        const double* slot = peers.mail[rank] + ((size_t)parity * world + r) * 16;
         unsigned long long t0, t1, seen = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (;;) {
@@ -1022,8 +1017,12 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     SGPR_TRY(h->epart.ensure(sizeof(double) * ((size_t)grid_g + nblk_x)));
     SGPR_TRY(h->wpart.ensure(sizeof(double) * 9 * nblk_b));
     SGPR_TRY(h->fcell.ensure(sizeof(double) * 3 * ((size_t)N + 1)));
-    SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)grid_g + nblk_x), st));
-    SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
+    // every partial is written by its producer (row_energy_kernel, atom_terms_kernel, the backward kernel: one entry per
+    // block, grids fixed) unless a rank has nothing to do
+    if (N == 0 || h->n_active == 0) {
+        SGPR_CUDA(cudaMemsetAsync(h->epart.p, 0, sizeof(double) * ((size_t)grid_g + nblk_x), st));
+        SGPR_CUDA(cudaMemsetAsync(h->wpart.p, 0, sizeof(double) * 9 * nblk_b, st));
+    }
     if (!peer_f_h) SGPR_CUDA(cudaMemsetAsync(h->fcell.p, 0, sizeof(double) * 3 * ((size_t)N + 1), st));
     if (beta_d && !h->use_i8_now) SGPR_TRY(h->kcmat.ensure(sizeof(double) * nrows * h->ldg));
     nvtxRangePushA("sgpr:gemm");
@@ -1093,13 +1092,13 @@ static int predict_body(sgpr_handle h, int64_t N, const double* pos_d, const int
     }
     if (px) {
         long long* counter = reinterpret_cast<long long*>(h->p2p_local.as<double>() + 16);
-        p2p_publish_kernel<<<1, 32, 0, st>>>(rank, world, px->peers, h->p2p_local.as<double>(), counter);
-        p2p_wait_reduce_kernel<<<1, 32, 0, st>>>(world, px->peers.mail[rank], counter, E_out, W_out, h->status_d.as<long long>());
+        p2p_publish_wait_kernel<<<1, 32, 0, st>>>(rank, world, px->peers, h->p2p_local.as<double>(), counter, E_out, W_out,
+                                                  h->status_d.as<long long>());
         if (N > 0)
             scatter_forces_kernel<<<(int)((N + 255) / 256), 256, 0, st>>>(N, h->atoms.as<AtomRec>(), px->own_base,
                                                                           h->owned.as<unsigned char>(), px->F_d, px->owned_d,
                                                                           counter, px->stride);
-        h->stats.kernel_launches += 3;
+        h->stats.kernel_launches += 2;
         SGPR_CUDA(cudaGetLastError());
     }
     if (warm) {

@@ -280,6 +280,131 @@ __global__ void gather_atoms_kernel(int64_t N, const double* __restrict__ pos, c
     rowof[c] = rstartT[s * g.ncell + bin] + (int)(c - cstart[k]);
 }
 
+// Exclusive prefix sum of n items by ONE block of 1024 threads, in tiles of 8192 with a running carry.  Lanes read
+// consecutive items (coalesced: one block has one load pipeline, an access pattern that touches 32 lines per instruction
+// costs 32 of its cycles); a warp owns 8 consecutive 32-item rows of the tile.  Returns the total (to every thread).
+template <class T, class Item, class Out>
+__device__ __forceinline__ T block_scan_exclusive(int n, Item item, Out out) {
+    constexpr int R = 8;
+    __shared__ T warp_tot[32];
+    __shared__ T carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024 * R) {
+        const int i0 = base + warp * (32 * R) + lane;
+        T v[R], inc[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = (i0 + 32 * j < n) ? item(i0 + 32 * j) : T(0);
+        T off = 0;   // sum of the warp's earlier rows
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            T x = v[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const T u = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += u;
+            }
+            inc[j] = off + x;
+            off += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) warp_tot[warp] = off;
+        __syncthreads();
+        if (warp == 0) {
+            T w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const T u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_tot[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const T carry = carry_s;
+        const T before = carry + (warp > 0 ? warp_tot[warp - 1] : T(0));
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (i0 + 32 * j < n) out(i0 + 32 * j, before + inc[j] - v[j]);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    return carry_s;
+}
+
+// Both prefix sums of the cell sort in ONE launch (the per-key counts are short: bins x species): block 0 scans the
+// counts in key order (bin-major) -> cstart, block 1 scans them species-major -> rstartT (first row of (species, bin)).
+constexpr int kScanThreads = 1024, kScanMaxKeys = 1 << 18;
+__global__ void __launch_bounds__(kScanThreads) key_scan_kernel(int nkeys, int ncell, int S, const int* __restrict__ cnt,
+                                                               int* __restrict__ cstart, int* __restrict__ rstartT) {
+    if (blockIdx.x == 0) {
+        block_scan_exclusive<int>(
+            nkeys + 1, [&](int t) { return t < nkeys ? cnt[t] : 0; }, [&](int t, int v) { cstart[t] = v; });
+    } else {
+        block_scan_exclusive<int>(
+            nkeys + 1,
+            [&](int t) {
+                if (t >= nkeys) return 0;
+                const int s = t / ncell, bin = t - s * ncell;   // species-major position t = s * ncell + bin
+                return cnt[bin * S + s];
+            },
+            [&](int t, int v) { rstartT[t] = v; });
+    }
+}
+
+// One warp per bin: order every (bin, species) run by original index (the atomics of bin_count_kernel hand out arbitrary
+// ranks; the cell order must not depend on them) and write the cell-ordered atom records of the bin.
+__global__ void sort_gather_kernel(int ncell, int64_t N, const double* __restrict__ pos, const int* __restrict__ cstart,
+                                   const int* __restrict__ rstartT, Geom g, int S, int* __restrict__ order,
+                                   AtomRec* __restrict__ atoms, int* __restrict__ abin, int* __restrict__ rowof) {
+    const int lane = threadIdx.x & 31;
+    const int bin = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bin >= ncell) return;
+    for (int s = 0; s < S; ++s) {
+        const int k = bin * S + s;
+        const int b = cstart[k], e = cstart[k + 1];
+        if (e - b > 32) {                                  // rare: insertion sort by one lane, as long as it takes
+            if (lane == 0) {
+                for (int i = b + 1; i < e; ++i) {
+                    const int v = order[i];
+                    int j = i - 1;
+                    while (j >= b && order[j] > v) {
+                        order[j + 1] = order[j];
+                        --j;
+                    }
+                    order[j + 1] = v;
+                }
+            }
+            __syncwarp();
+        } else if (e - b > 1) {
+            const int len = e - b;
+            const int v = lane < len ? order[b + lane] : 0x7fffffff;
+            int rank = 0;
+            for (int t = 0; t < len; ++t) rank += (__shfl_sync(0xffffffffu, v, t) < v) ? 1 : 0;   // indices are distinct
+            __syncwarp();
+            if (lane < len) order[b + rank] = v;
+            __syncwarp();
+        }
+        const int row0 = rstartT[s * ncell + bin];
+        for (int c = b + lane; c < e; c += 32) {
+            const int i = order[c];
+            const double x = pos[3 * (int64_t)i], y = pos[3 * (int64_t)i + 1], z = pos[3 * (int64_t)i + 2];
+            int b3[3], w[3];
+            frac_bin(g, x, y, z, b3, w);
+            AtomRec r;
+            r.x = x;
+            r.y = y;
+            r.z = z;
+            r.meta = (unsigned long long)(unsigned int)i | ((unsigned long long)s << 32) |
+                     ((unsigned long long)(w[0] + 128) << 40) | ((unsigned long long)(w[1] + 128) << 48) |
+                     ((unsigned long long)(w[2] + 128) << 56);
+            atoms[c] = r;
+            abin[c] = bin;
+            rowof[c] = row0 + (c - b);
+        }
+    }
+}
+
 static int scan_exclusive_int(sgpr_context* h, const int* in, int* out, int n, cudaStream_t st) {
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st);
@@ -322,13 +447,26 @@ int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_
     int* rank = key + (N + 1);
     int* err = h->errflag.as<int>();
     SGPR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (nkeys + 1), st));
-    SGPR_CUDA(cudaMemsetAsync(cntT, 0, sizeof(int) * (nkeys + 1), st));
     SGPR_CUDA(cudaMemsetAsync(err, 0, sizeof(int) * 4, st));
     const int T = 256;
     const int nblkN = (int)((N + T - 1) / T);
     const int nblkK = (nkeys + T - 1) / T;
     if (N > 0)
         bin_count_kernel<<<nblkN, T, 0, st>>>(N, pos_d, Z_d, h->ztab.as<int>(), g, S, cnt, key, rank, err);
+    if (nkeys + 1 <= kScanMaxKeys) {
+        // lean path (< 2^18 bin x species keys): 4 kernels instead of 9
+        key_scan_kernel<<<2, kScanThreads, 0, st>>>(nkeys, g.ncell, S, cnt, cstart, rstartT);
+        if (N > 0) {
+            scatter_order_kernel<<<nblkN, T, 0, st>>>(N, key, rank, cstart, h->order.as<int>());
+            sort_gather_kernel<<<(g.ncell + 7) / 8, 256, 0, st>>>(g.ncell, N, pos_d, cstart, rstartT, g, S, h->order.as<int>(),
+                                                               h->atoms.as<AtomRec>(), h->rowof.as<int>(),
+                                                               h->rowof.as<int>() + (N + 1));
+        }
+        h->stats.kernel_launches += 4;
+        SGPR_CUDA(cudaGetLastError());
+        return SGPR_OK;
+    }
+    SGPR_CUDA(cudaMemsetAsync(cntT, 0, sizeof(int) * (nkeys + 1), st));
     transpose_cnt_kernel<<<nblkK, T, 0, st>>>(g.ncell, S, cnt, cntT);
     SGPR_TRY(scan_exclusive_int(h, cnt, cstart, nkeys + 1, st));
     SGPR_TRY(scan_exclusive_int(h, cntT, rstartT, nkeys + 1, st));
@@ -899,6 +1037,49 @@ __global__ void nl_clamp_kernel(int na, long long* __restrict__ first, const lon
     if (i <= na) first[i] = 0;
 }
 
+// Lean form of row totals -> exclusive scan -> species row ranges -> (sync-free steps) status + clamp: one block walks the
+// rows in coalesced tiles of 1024 with a running carry.  (A few microseconds for 1e5 rows, and one graph node instead of
+// six: what matters for small systems and for the per-rank share of a sharded one.)
+constexpr int kRowsScanMax = 1 << 16;   // beyond: row_total + cub scan + status + clamp (one SM would be the bottleneck)
+__global__ void __launch_bounds__(1024) rows_scan_kernel(int na, int S, const int* __restrict__ nl_cnt,
+                                                         long long* __restrict__ first, const int* __restrict__ row_first_src,
+                                                         int row_first_pitch_ints, int* __restrict__ row_first_d, int do_status,
+                                                         long long cap, const int* __restrict__ err,
+                                                         long long* __restrict__ status) {
+    __shared__ int bad_s;
+    if ((int)threadIdx.x <= S) row_first_d[threadIdx.x] = row_first_src[(size_t)threadIdx.x * row_first_pitch_ints];
+    const long long total = block_scan_exclusive<long long>(
+        na + 1,
+        [&](int i) -> long long {
+            if (i >= na) return 0;
+            if (S == 4) {
+                const int4 c = *reinterpret_cast<const int4*>(nl_cnt + 4 * (long long)i);
+                return (long long)c.x + c.y + c.z + c.w;
+            }
+            long long t = 0;
+            for (int s = 0; s < S; ++s) t += nl_cnt[(long long)i * S + s];
+            return t;
+        },
+        [&](int i, long long v) { first[i] = v; });
+    if (!do_status) return;
+    if (threadIdx.x == 0) {
+        const bool bad = total > cap || err[0] != 0;
+        status[0] = total;
+        status[6] = bad ? 1 : 0;
+        if (bad) {
+            status[1] += 1;
+            status[2] = err[0];
+            status[3] = err[1];
+            status[4] = total;
+            status[5] = cap;
+        }
+        bad_s = bad ? 1 : 0;
+    }
+    __syncthreads();
+    if (bad_s)
+        for (int i = threadIdx.x; i <= na; i += 1024) first[i] = 0;
+}
+
 // row totals -> exclusive scan -> (sizing step: sync for pair count, error flags, species row ranges) -> fill
 static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int* row_first_src, int row_first_pitch,
                      int64_t* n_pairs, int contig_c0, int n_contig, bool warm) {
@@ -910,17 +1091,27 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
     long long* first = h->nl_first.as<long long>();
     long long* tot = first + (na + 1);
     const int T = 256;
-    row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
-    SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
-    // species row ranges in their canonical device location (read by the GEMM set-up kernel and row_energy_kernel)
-    SGPR_CUDA(cudaMemcpy2DAsync(h->row_first_d.p, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
-                                cudaMemcpyDeviceToDevice, st));
+    const bool lean = na + 1 <= kRowsScanMax && row_first_pitch % (int)sizeof(int) == 0;
+    if (lean) {
+        rows_scan_kernel<<<1, 1024, 0, st>>>(na, S, h->nl_cnt.as<int>(), first, row_first_src,
+                                             row_first_pitch / (int)sizeof(int), h->row_first_d.as<int>(), warm ? 1 : 0,
+                                             h->pairs_cap, h->errflag.as<int>(), h->status_d.as<long long>());
+        h->stats.kernel_launches += 1;
+    } else {
+        row_total_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, S, h->nl_cnt.as<int>(), tot);
+        SGPR_TRY(scan_exclusive_ll(h, tot, first, na + 1, st));
+        // species row ranges in their canonical device location (read by the GEMM set-up kernel and row_energy_kernel)
+        SGPR_CUDA(cudaMemcpy2DAsync(h->row_first_d.p, sizeof(int), row_first_src, (size_t)row_first_pitch, sizeof(int), S + 1,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
     long long total = 0;
     if (warm) {
         h->row_first_host_valid = false;
-        nl_status_kernel<<<1, 1, 0, st>>>(na, first, h->pairs_cap, h->errflag.as<int>(), h->status_d.as<long long>());
-        nl_clamp_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, first, h->status_d.as<long long>());
-        h->stats.kernel_launches += 2;
+        if (!lean) {
+            nl_status_kernel<<<1, 1, 0, st>>>(na, first, h->pairs_cap, h->errflag.as<int>(), h->status_d.as<long long>());
+            nl_clamp_kernel<<<(na + 1 + T - 1) / T, T, 0, st>>>(na, first, h->status_d.as<long long>());
+            h->stats.kernel_launches += 2;
+        }
     } else {
         int err[4] = {0, 0, 0, 0};
         int rf[SGPR_MAX_SPECIES + 1];
@@ -953,7 +1144,7 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
                               h->atoms.as<AtomRec>(), h->rowof.as<int>(), h->cstart.as<int>(), g, h->nl_cnt.as<int>(), first,
                               h->nl_pairs.as<PairRec>(), nullptr, h->nl_masks.as<unsigned>());
     }
-    h->stats.kernel_launches += 4;  // row totals, cub scan (2), fill
+    h->stats.kernel_launches += lean ? 1 : 4;  // fill (+ row totals, cub scan (2) when not the one-kernel scan)
     SGPR_CUDA(cudaGetLastError());
     *n_pairs = total;
     return SGPR_OK;

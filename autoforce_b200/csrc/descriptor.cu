@@ -825,6 +825,8 @@ int dispatch_forward(sgpr_context* h, const Geom& g, int n_env, const EnvSrc& sr
     if (lmax == 3 && nb == 4)   // the reference's default descriptor
         return launch_forward<3, 2, 1, ENV, 4>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st);
     if (lmax <= 3 && nb <= 4) FWD(3, 2, 1);
+    if (lmax == 6 && nb == 9)   // the high-resolution configuration (lmax 6, nmax 8)
+        return launch_forward<6, 3, 5, ENV, 9>(h, g, n_env, src, row_of, phat, cbuf, pnorm, sflag, st);
     if (lmax <= 3 && nb <= 8) FWD(3, 4, 1);
     if (lmax <= 3) FWD(3, 6, 1);
     if (lmax <= 6 && nb <= 6) FWD(6, 2, 5);
@@ -906,6 +908,7 @@ int descriptor_backward_atoms(sgpr_context* h, const Geom& g, const unsigned cha
 #define BWD(LM, NBB) return launch_backward<LM, NBB, false>(h, g, na, src, out, grid, st)
     if (lmax == 3 && nb == 4) return launch_backward<3, 4, true>(h, g, na, src, out, grid, st);   // the reference's default
     if (lmax <= 3 && nb <= 4) BWD(3, 4);
+    if (lmax == 6 && nb == 9) return launch_backward<6, 9, true>(h, g, na, src, out, grid, st);
     if (lmax <= 3 && nb <= 8) BWD(3, 8);
     if (lmax <= 6 && nb <= 6) BWD(6, 6);
     if (lmax <= 6 && nb <= 9) BWD(6, 9);

@@ -229,9 +229,11 @@ __device__ __forceinline__ double i32_to_f64(int32_t x) {
 
 // T = sum_g acc_g 256^(NG-1-g) in float64 with ONE rounding: Horner over the (up to) four most significant groups is
 // exact (|.| < 2^52), so is the rest (< 2^43); the final fma rounds once -- same value as an int64 evaluation.
+__host__ __device__ constexpr double pow2_neg(int e) { return e <= 0 ? 1.0 : 0.5 * pow2_neg(e - 1); }   // 2^-e
+
 template <int NG, bool SMALLK>
 __device__ __forceinline__ double combine_groups(const int32_t (*r)[16], int j) {
-    constexpr double sc = 1.0 / (double)(1ll << (8 * (NG - 1) + 12));
+    constexpr double sc = pow2_neg(8 * (NG - 1) + 12);
     if (SMALLK && NG == 6) {
         // one K chunk: |acc_g| <= 64 . 127^2 . (g + 1) < 2^23, so neighbouring groups pair up exactly in int32
         const double p01 = i32_to_f64(r[0][j] * 256 + r[1][j]), p23 = i32_to_f64(r[2][j] * 256 + r[3][j]);

@@ -1,12 +1,14 @@
 // Developer tool (GPU box): correctness + speed of the tcgen05 int8-sliced GEMM vs float64.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I autoforce_b200/csrc -I tools tools/i8gemm_test.cu -o tools/i8gemm_test.bin -lcuda
 //   stages 63 / 62 select the experimental A-in-TMEM kernel (tools/i8gemm_ta_kernel.cuh)
+//   stages 72 / 74 select the cluster kernel with multicast A (i8gemm_mc_kernel.cuh), 2 / 4 CTAs
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "i8gemm_kernel.cuh"
 #include "i8gemm_ta_kernel.cuh"
+#include "i8gemm_mc_kernel.cuh"
 using namespace sgpr::i8g;
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -40,6 +42,17 @@ static int make_map_cm(CUtensorMap* m, void* base, int ns, int rows, int Kpad, i
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_64B, getenv("PROMO") ? (CUtensorMapL2promotion)atoi(getenv("PROMO")) : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled (chunk-major) failed: %d\n", (int)r);
+    return (int)r;
+}
+static int make_map_cm_part(CUtensorMap* m, void* base, int ns, int rows, int Kpad, int box_rows) {
+    static EncodeFn enc = get_encode();
+    cuuint64_t dims[4] = {64, (cuuint64_t)rows, (cuuint64_t)(Kpad / 64), (cuuint64_t)ns};
+    cuuint64_t strides[3] = {64, (cuuint64_t)rows * 64, (cuuint64_t)rows * Kpad};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled (part) failed: %d\n", (int)r);
     return (int)r;
 }
 static void to_chunk_major(const std::vector<int8_t>& in, int rows, int Kpad, int ns, std::vector<int8_t>& out) {
@@ -152,11 +165,26 @@ int main(int argc, char** argv) {
     cudaMalloc(&dcm, sizeof(Common));
     cudaMemcpy(dcm, &cm, sizeof(Common), cudaMemcpyHostToDevice);
     StoreEpi epi{dC, N};
+    void (*kern_mc)(const Common*, const ProblemMC*, StoreEpi) = nullptr;
+    ProblemMC* dPM = nullptr;
+    int mc = 0;
+    if (ns == 6 && tr == 7 && (stages == 72 || stages == 74)) {
+        mc = stages == 72 ? 2 : 4;
+        ProblemMC PM;
+        PM.N = N; PM.Kpad = Kpad; PM.aux = nullptr;
+        PM.mapB = P.mapB;
+        if (make_map_cm_part(&PM.mapAs, dAc, ns, M, Kpad, BM / mc)) return 1;
+        cudaMalloc(&dPM, sizeof(ProblemMC));
+        cudaMemcpy(dPM, &PM, sizeof(ProblemMC), cudaMemcpyHostToDevice);
+        if (mc == 2) kern_mc = i8gemm_mc_kernel<6, 7, 3, StoreEpi, 2>;
+        else kern_mc = i8gemm_mc_kernel<6, 7, 3, StoreEpi, 4>;
+    }
     void (*kern)(const Common*, const Problem*, StoreEpi) = nullptr;
     void (*kern_ta)(const Common, const ProblemTA*, StoreEpi) = nullptr;
     size_t smem = 0;
     int nthreads = NTHREADS;
-    if (ns == 6 && tr == 7 && stages == 63) { kern_ta = i8gemm_ta_kernel<6, 7, 3, StoreEpi, 3>; smem = smem_bytes_ta<6, 3, 3>(); nthreads = NTHREADS_TA; }
+    if (mc) { smem = smem_bytes<6, 3>(); }
+    else if (ns == 6 && tr == 7 && stages == 63) { kern_ta = i8gemm_ta_kernel<6, 7, 3, StoreEpi, 3>; smem = smem_bytes_ta<6, 3, 3>(); nthreads = NTHREADS_TA; }
     else if (ns == 6 && tr == 7 && stages == 62) { kern_ta = i8gemm_ta_kernel<6, 7, 4, StoreEpi, 2>; smem = smem_bytes_ta<6, 4, 2>(); nthreads = NTHREADS_TA; }
     else if (ns == 6 && tr == 8 && stages == 31) { kern = i8gemm_kernel<6, 8, 3, StoreEpi, 1>; smem = smem_bytes<6, 3>(); }
     else if (ns == 6 && tr == 8 && stages == 32) { kern = i8gemm_kernel<6, 8, 3, StoreEpi, 2>; smem = smem_bytes<6, 3>(); }
@@ -167,12 +195,24 @@ int main(int argc, char** argv) {
     else if (ns == 5 && tr == 7) { kern = i8gemm_kernel<5, 7, 3, StoreEpi>; smem = smem_bytes<5, 3>(); }
     else if (ns == 5 && tr == 6) { kern = i8gemm_kernel<5, 6, 4, StoreEpi>; smem = smem_bytes<5, 4>(); }
     else { printf("unsupported scheme\n"); return 1; }
-    cudaError_t e = kern_ta ? cudaFuncSetAttribute(kern_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+    cudaError_t e = mc ? cudaFuncSetAttribute(kern_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : kern_ta ? cudaFuncSetAttribute(kern_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     printf("smem %zu bytes: %s\n", smem, cudaGetErrorString(e));
     int grid = std::min(prop.multiProcessorCount, cm.tile_start[1]);
     if (getenv("GRID")) grid = std::min(grid, atoi(getenv("GRID")));
-    if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
+    if (mc) {
+        grid = prop.multiProcessorCount / mc * mc;
+        if (getenv("GRID")) grid = std::min(grid, atoi(getenv("GRID")) / mc * mc);
+        int ncl = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(nthreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = mc; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        cudaOccupancyMaxActiveClusters(&ncl, kern_mc, &cfg);
+        printf("cluster size %d: grid %d, max active clusters %d\n", mc, grid, ncl);
+        kern_mc<<<grid, nthreads, smem>>>(dcm, dPM, epi);
+    } else if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
     else kern<<<grid, nthreads, smem>>>(dcm, dP, epi);
     e = cudaDeviceSynchronize();
     printf("kernel: %s\n", cudaGetErrorString(e));
@@ -196,7 +236,8 @@ int main(int argc, char** argv) {
     cudaEventRecord(e0);
     const int reps = 5;
     for (int r = 0; r < reps; ++r) {
-        if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
+        if (mc) kern_mc<<<grid, nthreads, smem>>>(dcm, dPM, epi);
+        else if (kern_ta) kern_ta<<<grid, nthreads, smem>>>(cm, dPT, epi);
         else kern<<<grid, nthreads, smem>>>(dcm, dP, epi);
     }
     cudaEventRecord(e1);

@@ -116,6 +116,57 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class NvmlSampler:
+    """SM clock + throttle reasons through NVML from a polling thread (every ~2 ms): the timed region of a sharded run is
+    a few milliseconds, shorter than the start-up of an `nvidia-smi -lms` process.  Same result keys as ClockSampler."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, torch_index):
+        import threading
+
+        import pynvml
+        import torch
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.sm, self.bits, self.stop_flag = [], 0, False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _once(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        try:
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _run(self):
+        while not self.stop_flag:
+            self._once()
+            time.sleep(0.002)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self._once()          # at least one sample, taken while the last steps are still in flight or just retired
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
+                "reasons": sorted(k for k, b in self.REASONS.items() if self.bits & b), "source": "nvml"}
+
+
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 def dgemm_peak_tflops():
     """FP64 GEMM peak of this GPU measured in-run (cuBLAS DGEMM 8192^3, best of 5):
     MEASURED_PEAKS.json only lists bf16, and the kernel GEMMs run on the FP64 pipe."""
@@ -395,7 +446,7 @@ def main():
     # ---- device-resident leg (value): no in-library events, no stats calls inside the timed region; after the first
     # (sizing) step the library enqueues every step without host synchronisation -- validated after the timed region
     eng.set_async(True)
-    sampler = ClockSampler(local_rank)
+    sampler = make_sampler(local_rank)
     sampler.start()
     ms_dev, wall_dev = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop()

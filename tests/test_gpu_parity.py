@@ -418,6 +418,31 @@ def test_neighbor_list_far_from_the_origin(mode, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", ["bins", "warp"])
+def test_neighbor_list_with_crowded_bins(mode, monkeypatch):
+    """More than 32 atoms of one species in one bin (the warp-per-bin ordering of the cell sort falls back to an insertion
+    sort there) and candidate tiles that span several batches: a dense droplet in a large periodic box, and the same
+    droplet in an open box.  Rows and their order-independent content must equal the oracle's."""
+    import autoforce_b200 as ab
+
+    monkeypatch.setenv("SGPR_NL", mode)
+    g = load_golden("lipso108")
+    rc = g["meta"]["kernel"]["rc"]
+    rng = np.random.default_rng(11)
+    n = 2400                                    # > 2048 candidates per atom: beyond the accept-bit words of the count pass
+    pos = rng.uniform(0.0, 1.6 * rc, size=(n, 3)) + np.array([7.0, 9.0, 5.0])
+    sp = np.asarray(g["meta"]["species"])
+    Z = sp[rng.integers(0, 2, size=n)]          # two species: hundreds of atoms per (bin, species) key
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    for cell, pbc in ((np.diag([41.0, 39.0, 43.0]), True), (np.diag([41.0, 39.0, 43.0]), False)):
+        first, J, S = eng.neighbors(pos, Z, cell, pbc)
+        f0, J0, S0 = o.neighbor_list(pos, cell, pbc, rc)
+        assert np.array_equal(first, f0)
+        a, b = sorted_rows(first, J, S), sorted_rows(f0, J0, S0)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    eng.close()
+
+
 def test_kernel_sum_with_different_hyperparameters():
     """EnergyForceKernel sums similarity kernels (regression/gppotential.py:81-84); kernels with different lmax / nmax /
     exponent / cutoff run as one handle each and add up.  The golden structure has an isolated atom and a pair whose

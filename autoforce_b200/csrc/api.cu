@@ -760,6 +760,8 @@ extern "C" __attribute__((visibility("default"))) int sgpr_create(const sgpr_mod
     {   // GEMM engine: tcgen05 int8-sliced (default, needs normalised descriptors) or FP64 DMMA
         const char* nlm = getenv("SGPR_NL");
         h->nl_mode = !nlm ? 0 : strcmp(nlm, "warp") == 0 ? 1 : strcmp(nlm, "bins") == 0 ? 2 : 0;
+        const char* lean = getenv("SGPR_NL_LEAN");
+        h->nl_lean = !(lean && atoi(lean) == 0);
         const char* gr = getenv("SGPR_GRAPH");
         h->use_graph = !(gr && atoi(gr) == 0);
         const char* eng = getenv("SGPR_GEMM");

@@ -453,7 +453,7 @@ int cell_sort(sgpr_context* h, int64_t N, const double* pos_d, const int32_t* Z_
     const int nblkK = (nkeys + T - 1) / T;
     if (N > 0)
         bin_count_kernel<<<nblkN, T, 0, st>>>(N, pos_d, Z_d, h->ztab.as<int>(), g, S, cnt, key, rank, err);
-    if (nkeys + 1 <= kScanMaxKeys) {
+    if (h->nl_lean && nkeys + 1 <= kScanMaxKeys) {
         // lean path (< 2^18 bin x species keys): 4 kernels instead of 9
         key_scan_kernel<<<2, kScanThreads, 0, st>>>(nkeys, g.ncell, S, cnt, cstart, rstartT);
         if (N > 0) {
@@ -1091,7 +1091,7 @@ static int nl_finish(sgpr_context* h, const Geom& g, cudaStream_t st, const int*
     long long* first = h->nl_first.as<long long>();
     long long* tot = first + (na + 1);
     const int T = 256;
-    const bool lean = na + 1 <= kRowsScanMax && row_first_pitch % (int)sizeof(int) == 0;
+    const bool lean = h->nl_lean && na + 1 <= kRowsScanMax && row_first_pitch % (int)sizeof(int) == 0;
     if (lean) {
         rows_scan_kernel<<<1, 1024, 0, st>>>(na, S, h->nl_cnt.as<int>(), first, row_first_src,
                                              row_first_pitch / (int)sizeof(int), h->row_first_d.as<int>(), warm ? 1 : 0,

@@ -145,6 +145,7 @@ struct sgpr_context {
     sgpr::DevBuf erow_part, erow, prow;  // per-row energy partials / local energies / descriptor norms
     sgpr::DevBuf ttab;          // [D] kappa*nnl*(1 + [a==b]) per packed entry
     // ---- tcgen05 int8-sliced GEMM path (i8gemm.cu)
+    bool nl_lean = true;        // SGPR_NL_LEAN=0: force the many-kernel cell sort / row scan that very large systems use -- test hook
     int nl_mode = 0;            // SGPR_NL: 0 auto, 1 "warp" (one warp per environment), 2 "bins" (one block per bin) -- test hook
     sgpr::DevBuf nl_run;        // running per-species fill offsets across candidate tiles (block-per-bin fill)
     bool use_i8 = false;        // GEMMs on tcgen05 (int8 digit slices) instead of FP64 DMMA

@@ -418,6 +418,27 @@ def test_neighbor_list_far_from_the_origin(mode, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["lipso108", "tric_oh"])
+def test_many_kernel_front_end_of_very_large_systems(name, monkeypatch):
+    """Above 2^18 bin x species keys / 2^16 rows the cell sort and the row scan use cub scans and separate kernels instead
+    of the one-block versions; SGPR_NL_LEAN=0 forces that path on a small case.  Same lists, same results, also on
+    sync-free (warm) steps."""
+    import autoforce_b200 as ab
+
+    monkeypatch.setenv("SGPR_NL_LEAN", "0")
+    g = load_golden(name)
+    eng = ab.SgprEngine(model_from_golden(g), species=g["meta"]["species"])
+    first, J, S = eng.neighbors(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+    f0, J0, S0 = o.neighbor_list(g["pos"], g["cell"], g["meta"]["pbc"], g["meta"]["kernel"]["rc"])
+    assert np.array_equal(first, f0)
+    assert all(np.array_equal(x, y) for x, y in zip(sorted_rows(first, J, S), sorted_rows(f0, J0, S0)))
+    for _ in range(3):    # sizing step, then warm steps
+        E, F, W, _ = eng.predict(g["pos"], g["numbers"], g["cell"], g["meta"]["pbc"])
+        assert abs(E - float(g["energy"])) / len(g["numbers"]) < TOL_E_PER_ATOM
+        assert np.abs(F - g["forces"]).max() < TOL_F
+    eng.close()
+
+
 @pytest.mark.parametrize("mode", ["bins", "warp"])
 def test_neighbor_list_with_crowded_bins(mode, monkeypatch):
     """More than 32 atoms of one species in one bin (the warp-per-bin ordering of the cell sort falls back to an insertion

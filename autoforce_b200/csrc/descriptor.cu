@@ -10,10 +10,13 @@
 //            as in sesoap.py:204-246 and ylm.py:191-222).
 //
 // One warp per environment.  Forward is two-phase per chunk of 32 neighbours: lanes
-// first own one neighbour each (radial + harmonics into shared memory), then own
-// components (n,lm) and accumulate over the chunk, so no cross-lane reduction is needed.
-// Backward keeps lanes on neighbours; the per-atom coefficients dE/dc live in shared
-// memory and are broadcast-read.
+// first own one neighbour each (radial + harmonics into shared memory); the chunk is then
+// contracted into the expansion coefficients as an FP64 tensor-core micro-GEMM
+// (mma.sync.m8n8k4.f64: M = lm, N = (species, n), K = neighbours), and so is the power
+// spectrum (per l: c . c^T on the upper-triangle tiles).  Backward stages the next
+// environment's rows with cp.async, forms dE/dc as DMMA micro-GEMMs per l, then keeps
+// lanes on neighbours; dE/dc lives in shared memory and is broadcast-read.  Both kernels
+// have compile-time specialisations for the common descriptor sizes (EXNB / EXACT).
 //
 // Packed descriptor: the power spectrum is symmetric under (s1,n1)<->(s2,n2)
 // (descriptor/sesoap.py:195-203), so only pairs a<=b of a=(s,n) are stored, off-diagonal

@@ -212,8 +212,8 @@ struct MmaPlan {
     }
 };
 
-// 16 TMEM columns of every accumulator group -> float64:  T = sum_g acc_g 256^(NG-1-g), combined exactly in
-// two int64 halves (|acc_g| < 2^27: hi < 2^51, lo < 2^43), one fma; result = T * 2^-(8 (NG-1) + 12).
+// 8 / 16 TMEM columns of every accumulator group -> float64:  T = sum_g acc_g 256^(NG-1-g), combined exactly in
+// two halves (|acc_g| < 2^27: hi < 2^51, lo < 2^43, see combine_groups), one rounding; result = T * 2^-(8 (NG-1) + 12).
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])

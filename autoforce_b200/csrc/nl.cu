@@ -8,6 +8,8 @@
 // The distance is evaluated from the caller's (unwrapped) positions in the reference's
 // operation order (r = (x_j - x_i) + sum_k S_k cell_k, no FMA contraction), so the
 // accept/reject decision is the same floating-point comparison the reference makes.
+// (Candidates farther from the cutoff sphere than the rounding error of a float test on
+// bin-relative coordinates are decided by that test; see neighbor_bin_kernel.)
 //
 // Layout: atoms are counting-sorted by key = bin*S + species ("cell order"); a bin's
 // atoms are one contiguous run, ordered by species then by original index

@@ -79,7 +79,14 @@ def run(workload, steps, warmup, procs=None, rep=None, variants=4, keep_dir=None
     port = _free_port()
     env = thread_env()
     env.update(SGPR_SHIM_WORLD=str(procs), SGPR_SHIM_PORT=str(port), PYTHONPATH=ROOT + os.pathsep + env.get("PYTHONPATH", ""))
-    env.pop("RANK", None), env.pop("WORLD_SIZE", None), env.pop("LOCAL_RANK", None)
+    # under torchrun the parent carries the launcher's rendezvous variables; with TORCHELASTIC_USE_AGENT_STORE set,
+    # init_process_group("tcp://...") in the workers would connect to the agent's store instead of hosting their own
+    # and wait forever
+    for k in list(env):
+        if k.startswith(("TORCHELASTIC_", "TORCH_NCCL_", "NCCL_")) or k in (
+                "RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK",
+                "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k)
     env["CUDA_VISIBLE_DEVICES"] = ""          # the reference arm must not touch a GPU
     ps = []
     for r in range(procs):

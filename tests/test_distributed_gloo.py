@@ -119,3 +119,28 @@ def test_two_rank_covloss_gather(tmp_path):
         assert np.abs(r[k]["beta"][fin] - ref[fin]).max() < 1e-15
     assert r[0]["covlog"] == r[1]["covlog"] == "nan"      # max() propagates NaN like torch.max
     assert r[0]["seen"] == [] and r[1]["seen"] == []       # nan > ediff is False
+
+
+def test_reference_arm_under_torchrun():
+    """`bench.py --impl reference` launched the way the driver launches every N > 1 run: under torchrun.  Rank 0 alone
+    runs the CPU arm and prints ONE JSON line; its worker processes must not inherit the launcher's rendezvous variables
+    (with TORCHELASTIC_USE_AGENT_STORE set they would wait on the agent's store forever)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c2",
+           "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(x) for x in r.stdout.splitlines() if x.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    line = lines[0]
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")

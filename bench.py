@@ -653,6 +653,10 @@ def main():
                                         "sample": "2 timed steps after 1 warm-up: " + r["sample"]}
             except Exception as ex:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        elif world > 1:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": "timed at N = 1 only (it does not depend on the number of GPUs): see the N = 1 line, "
+                                              "or `bench.py --impl reference`"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -144,13 +144,14 @@ int sgpr_predict_host(sgpr_handle h, int64_t N, const double* pos_h, const int32
                       double* E_h, double* F_h, double* W_h, double* beta_h, uint8_t* owned_h);
 
 /* Atom-sharded prediction with a PEER-MEMORY force exchange over NVLink instead of the halo recompute
- * of sgpr_predict(rank, world): every rank evaluates only the environments it owns; the force each
- * environment exerts on a neighbour owned by another rank is added (red.global.add.f64) straight into
- * that rank's accumulation buffer through a peer mapping.  Replaces the reference's all_reduce of the
+ * of sgpr_predict(rank, world): every rank evaluates only the environments it owns and accumulates all
+ * pair forces in its own buffer; what it accumulated for atoms of other ranks (the halo) is then added
+ * (red.global.add.f64, once per atom and component) into their owners' accumulation buffers through
+ * the peer mappings.  Replaces the reference's all_reduce of the
  * [N,3] force array (calculator/active.py:601); the only collective left is the caller's all-reduce
  * of E_d[1] and W_d[9].
  *   peer_f_h [world]  host array of device pointers: peer_f_h[r] = rank r's accumulation buffer
- *                     (3*N doubles, cell order, zero on entry), mapped into this device's address space
+ *                     (3*N doubles, cell order, zero on entry; entries of atoms the rank does not own hold scratch afterwards), mapped into this device's address space
  *                     (e.g. torch symmetric memory / cudaIpcOpenMemHandle); peer_f_h[rank] is local.
  * After ALL ranks have finished this call (the caller's E/W all-reduce is the barrier), each rank reads
  * its own forces with sgpr_p2p_collect. */
@@ -168,10 +169,10 @@ int sgpr_p2p_collect(sgpr_handle h, void* stream, const double* own_f_d, double*
  * (which half a step uses is the low bit of a step counter that lives on the device: the arguments of a warm step are
  * identical from step to step, so it replays as ONE CUDA graph)
  * peer_base_h[r] = base address of rank r's block as mapped on THIS device.  Per step each rank
- *   1. clears its accumulation buffer of the next step,  2. evaluates the environments it owns (forces on atoms of other
- *   ranks are added into their buffers over NVLink),  3. writes its E and virial into EVERY rank's mailbox and then
+ *   1. clears its accumulation buffer of the next step,  2. evaluates the environments it owns and pushes the forces it
+ *   accumulated on atoms of other ranks into their buffers over NVLink,  3. writes its E and virial into EVERY rank's mailbox and then
  *   the stamp (st.release.sys),  4. waits until all stamps of the step have arrived in its own mailbox -- every
- *   rank's force kernel has then finished -- and sums the world contributions in rank order (bit-identical on all
+ *   rank's push has then finished -- and sums the world contributions in rank order (bit-identical on all
  *   ranks),  5. copies its own forces to F_d [N,3] (caller's order, rows of owned atoms) and fills owned_d [N].
  * E_d [1], W_d [9], F_d, owned_d are device pointers; everything is enqueued on `stream` (warm steps: one CUDA graph,
  * no host synchronisation -- see "Asynchronous steps").  All ranks must call it once per step, the same number of times.

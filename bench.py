@@ -231,7 +231,7 @@ def run_reference(workload, steps, warmup, procs=None):
     procs = procs or min(os.cpu_count() or 1, 64)
     if ref_runner.reference_available():
         apc = reference_sample_plan(w, procs)
-        out = ref_bench.run(workload, steps, warmup, procs, rep=ref_bench.sample_rep(procs, apc))
+        out = ref_bench.run(workload, steps, warmup, procs, rep=ref_bench.sample_rep(procs, apc), timeout=1500)
         nodes = out["node_seconds"]
         sample = (f"the UNMODIFIED reference (theforce ActiveCalculator.calculate, prediction mode, {out['reference']} copy) on a "
                   f"{out['atoms']}-atom periodic cell of the same family (fcc rep {out['rep']}, same species mix / rattle / per-step "
@@ -244,25 +244,38 @@ def run_reference(workload, steps, warmup, procs=None):
     return run_port(workload, steps, warmup, procs)
 
 
-def run_port(workload, steps, warmup, procs=None):
+def run_port(workload, steps, warmup, procs=None, timeout=300):
     """The numpy restatement (oracle/sgpr_oracle.py) on the host cores: a sample of the full-size structure's
     environments per step.  Second CPU figure next to the reference's (it is vectorised where the reference loops in
-    Python, so it is the faster of the two), and the fallback when the reference package is absent."""
-    from autoforce_b200 import synth
-
-    w = synth.WORKLOADS[workload]
+    Python, so it is the faster of the two), and the fallback when the reference package is absent.
+    Runs in a fresh interpreter (its worker pool forks; this process may hold a CUDA context) with a hard time limit."""
     procs = procs or min(os.cpu_count() or 1, 64)
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        env[k] = "1"
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--port-worker", workload, str(steps), str(warmup), str(procs)]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("numpy port worker failed: " + r.stderr[-500:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def port_worker(workload, steps, warmup, procs):
+    from autoforce_b200 import synth
     from oracle.cpu_bench import CpuBench
     from oracle.sgpr_oracle import neighbor_list
 
+    w = synth.WORKLOADS[workload]
     pos_variants, cell, numbers = workload_inputs(workload, 4)[1:]
     model = synth.synth_model(w["Zs"], w["M"], 1, lmax=w["lmax"], nmax=w["nmax"], rc=w["rc"], neighbors_fn=neighbor_list)
     cb = CpuBench(model, pos_variants, cell, numbers, 32 * procs, procs)
     value, sec = cb.run(steps, warmup)
     cb.close()
-    return dict(value=value, ms_per_step=sec * 1e3, cores=procs, kind="port",
-                sample=f"{cb.sample} of {len(numbers)} atoms per step (full neighbour environments, all {model.M} inducing LCEs), "
-                       f"{procs} worker processes x 1 thread; oracle/sgpr_oracle.py (vectorised numpy restatement)", work=None)
+    print(json.dumps(dict(value=value, ms_per_step=sec * 1e3, cores=procs, kind="port",
+                          sample=f"{cb.sample} of {len(numbers)} atoms per step (full neighbour environments, all {model.M} inducing "
+                                 f"LCEs), {procs} worker processes x 1 thread; oracle/sgpr_oracle.py (vectorised numpy restatement)",
+                          work=None)), flush=True)
 
 
 def cpu_arm(args, world, rank):
@@ -681,4 +694,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) >= 6 and sys.argv[1] == "--port-worker":
+        port_worker(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    else:
+        main()
